@@ -1,0 +1,630 @@
+// tcgen05 implicit-GEMM convolution kernels for sm_100a (B200).
+//
+// Two kernels cover every dense contraction of the GCC training step
+// (reference call sites: nn.Conv2d / nn.ConvTranspose2d in models/Pix2Pix.py:31-56,
+// 216-260, 280-300 and the Gram bmm in models/Pix2Pix.py:733-740):
+//
+//  * conv_gemm_kernel  ("pixel-major" GEMM):  Y[pix, r] = sum_{tap, c} X[pix (+) tap, c] * Wp[r][tap][c]
+//      A = activation patches, fetched by TMA straight from the NHWC bf16 tensor as a 4-D box
+//          (64 channels x Wt x Ht x Nt pixels, zero fill outside the image = conv zero padding),
+//      B = packed weights [rows][taps][channels] (K-major), D = 128 pixels x BLOCK_N rows in TMEM.
+//      Used for Conv2d fprop, Conv2d dgrad, ConvTranspose2d fprop/dgrad, 1x1 convs, Gram backward.
+//      Stride-2 gathers use four parity views of the input (one tensor map each); stride-2
+//      scatters (transposed conv) run as four sub-pixel classes with a strided output.
+//
+//  * wgrad_gemm_kernel ("channel-major" GEMM): dW[r][tap][c] = sum_pix P[pix, r] * Q[pix (+) tap, c]
+//      both operands are MN-major tiles (64 pixels x 64 channels boxes), D = 128 r x BLOCK_N c.
+//      Used for all weight gradients and (batched, tap = 0, P = Q) for the Gram matrices.
+//
+// Pipeline per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA
+// issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  smem ring of STAGES slots
+// guarded by full/empty mbarriers; accumulator hand-off through a tmem_full mbarrier.
+#include "common.cuh"
+
+namespace gcc {
+
+static constexpr int kMaxTaps = 49;
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one SWIZZLE_128B row
+
+struct GemmGeom {
+  CUtensorMap a_maps[4];  // A-side activation views (parity variants for stride-2 gathers)
+  CUtensorMap b_map;      // conv_gemm: packed weights (3-D).  wgrad: unused
+  CUtensorMap p_map;      // wgrad: M-side activation (4-D).  conv_gemm: unused
+  int num_taps;
+  int k_chunks;  // conv_gemm: ceil(C / 64) channel chunks per tap
+  short tap_map[kMaxTaps];
+  short tap_dh[kMaxTaps];
+  short tap_dw[kMaxTaps];
+  short tap_widx[kMaxTaps];
+  // pixel-tile geometry (powers of two): tile = Nt x Ht x Wt pixels
+  int log_wt, log_ht, log_nt;
+  int tiles_w, tiles_h, tiles_n;
+  int GN, GH, GW;  // valid extents of the pixel grid
+  // conv_gemm output (bf16 NHWC, possibly strided / channel-offset)
+  bf16* out;
+  long long out_sn, out_sh, out_sw;  // element strides of grid coords (n, a, b)
+  int out_cols;                      // number of physical channels to write (multiple of 8)
+  int bias_cols;                     // logical rows that receive bias
+  const float* bias;
+  int act;  // 0 none, 1 leaky-relu(slope), 2 tanh
+  float slope;
+  // wgrad output (fp32 [batch][R][T][C])
+  float* dw;
+  int R, C, T_total;     // logical sizes of the fp32 output
+  int splits;            // split-K factor over pixel blocks
+  int batched;           // 1: one output matrix per image n (Gram)
+  int atomic_out;        // 1: red.add into dw, 0: plain store
+  float scale;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == 1) return v > 0.f ? v : v * slope;
+  if (act == 2) return tanhf(v);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ GemmGeom p) {
+  constexpr uint32_t kABytes = kBlockM * 128;
+  constexpr uint32_t kBBytes = BLOCK_N * 128;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int bx = blockIdx.x;
+  const int tw = bx % p.tiles_w;
+  bx /= p.tiles_w;
+  const int th = bx % p.tiles_h;
+  const int tn = bx / p.tiles_h;
+  const int b0 = tw << p.log_wt, a0 = th << p.log_ht, n0 = tn << p.log_nt;
+  const int n_tile = blockIdx.y;
+  const int num_kb = p.num_taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_maps[0]);
+    tma_prefetch_desc(&p.b_map);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / p.k_chunks;
+        const int kc = kb - tap * p.k_chunks;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        uint8_t* sa = smem + stage * kStageBytes;
+        tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, b0 + p.tap_dw[tap],
+                    a0 + p.tap_dh[tap], n0);
+        tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK, p.tap_widx[tap], n_tile * BLOCK_N);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wt_mask = (1 << p.log_wt) - 1, ht_mask = (1 << p.log_ht) - 1;
+    const int b = b0 + (r & wt_mask);
+    const int a = a0 + ((r >> p.log_wt) & ht_mask);
+    const int n = n0 + (r >> (p.log_wt + p.log_ht));
+    const bool valid = (n < p.GN) && (a < p.GH) && (b < p.GW);
+    bf16* orow = p.out + (long long)n * p.out_sn + (long long)a * p.out_sh + (long long)b * p.out_sw;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
+      const int col0 = n_tile * BLOCK_N + c0;
+      if (col0 >= p.out_cols) break;  // warp-uniform
+      uint32_t v[32];
+      if constexpr (kChunk == 32) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      } else {
+        uint32_t v16[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v16[i];
+      }
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < kChunk / 8; ++g) {
+          const int col = col0 + g * 8;
+          if (col < p.out_cols) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float x = __uint_as_float(v[g * 8 + i]);
+              if (p.bias != nullptr && col + i < p.bias_cols) x += __ldg(p.bias + col + i);
+              f[i] = apply_act(x, p.act, p.slope);
+            }
+            uint4 o;
+            o.x = pack_bf16(f[0], f[1]);
+            o.y = pack_bf16(f[2], f[3]);
+            o.z = pack_bf16(f[4], f[5]);
+            o.w = pack_bf16(f[6], f[7]);
+            *reinterpret_cast<uint4*>(orow + col) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW[r][tap][c] (+)= scale * sum_pix P[pix, r] * Q[pix (+) tap, c]
+// grid = (r tiles of 128, c tiles of BLOCK_N, taps * splits [* batch])
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__ GemmGeom p) {
+  constexpr uint32_t kBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
+  constexpr uint32_t kABytes = 2 * kBoxBytes;
+  constexpr uint32_t kBBytes = (BLOCK_N / 64) * kBoxBytes;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BLOCK_N;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int r_tile = blockIdx.x, c_tile = blockIdx.y;
+  int bz = blockIdx.z;
+  const int split = bz % p.splits;
+  bz /= p.splits;
+  const int tap = bz % p.num_taps;
+  const int img = bz / p.num_taps;  // only meaningful when batched
+
+  // pixel blocks handled by this CTA
+  const int tiles_n = p.batched ? 1 : p.tiles_n;
+  const int total_pb = p.tiles_w * p.tiles_h * tiles_n;
+  const int per = (total_pb + p.splits - 1) / p.splits;
+  const int pb_begin = split * per;
+  const int pb_end = min(total_pb, pb_begin + per);
+  const int num_kb = max(0, pb_end - pb_begin);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_maps[0]);
+    tma_prefetch_desc(&p.p_map);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+      const CUtensorMap* qmap = &p.a_maps[p.tap_map[tap]];
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        int t = pb;
+        const int tw = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tn = t / p.tiles_h;
+        const int b0 = tw << p.log_wt, a0 = th << p.log_ht;
+        const int n0 = p.batched ? img : (tn << p.log_nt);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        uint8_t* sa = smem + stage * kStageBytes;
+        tma_load_4d(sa, &p.p_map, &full_bar[stage], r_tile * 128, b0, a0, n0);
+        tma_load_4d(sa + kBoxBytes, &p.p_map, &full_bar[stage], r_tile * 128 + 64, b0, a0, n0);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tma_load_4d(sa + kABytes + j * kBoxBytes, qmap, &full_bar[stage], c_tile * BLOCK_N + j * 64, b0 + dw,
+                      a0 + dh, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < 64 / 16; ++k) {
+          // MN-major SW128: 8-pixel groups are 1024 B apart (SBO), 64-channel atoms 8192 B apart (LBO)
+          const uint64_t da = make_smem_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
+          umma_bf16(tmem_base, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (num_kb > 0) {
+    const int q = warp & 3;
+    const int r = r_tile * 128 + q * 32 + lane;
+    const bool valid = r < p.R;
+    float* orow = p.dw + ((long long)(p.batched ? img : 0) * p.R + r) * ((long long)p.T_total * p.C) +
+                  (long long)p.tap_widx[tap] * p.C;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      const int col0 = c_tile * BLOCK_N + c0;
+      if (col0 >= p.C) break;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = col0 + i;
+          if (col < p.C) {
+            const float x = __uint_as_float(v[i]) * p.scale;
+            if (p.atomic_out)
+              atomicAdd(orow + col, x);
+            else
+              orow[col] = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace gcc
+
+// =============================================================================== host side
+using namespace gcc;
+
+static int ilog2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// choose a power-of-two pixel tile (Wt, Ht, Nt) with Wt*Ht*Nt == pixels
+static void choose_tile(int pixels, int GN, int GH, int GW, int* lw, int* lh, int* ln) {
+  int lp = ilog2_ceil(pixels);
+  int w = ilog2_ceil(GW);
+  if (w > lp) w = lp;
+  int h = ilog2_ceil(GH);
+  if (h > lp - w) h = lp - w;
+  int n = lp - w - h;
+  *lw = w;
+  *lh = h;
+  *ln = n;
+}
+
+// 4-D activation view: dims (C, W', H', N) over an NHWC bf16 tensor, optionally the stride-2
+// parity sub-grid (ph, pw).  box = (64, 2^lw, 2^lh, 2^ln).
+static int make_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int C, int sub, int ph, int pw,
+                        int lw, int lh, int ln) {
+  const bf16* base = reinterpret_cast<const bf16*>(x);
+  uint64_t dims[4], strides[3];
+  if (sub == 1) {
+    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N;
+    strides[0] = (uint64_t)C * 2;
+    strides[1] = (uint64_t)W * C * 2;
+    strides[2] = (uint64_t)H * W * C * 2;
+  } else {
+    base += ((long long)ph * W + pw) * C;
+    dims[0] = C;
+    dims[1] = (W - pw + 1) / 2;
+    dims[2] = (H - ph + 1) / 2;
+    dims[3] = N;
+    strides[0] = (uint64_t)C * 4;
+    strides[1] = (uint64_t)W * C * 4;
+    strides[2] = (uint64_t)H * W * C * 2;
+  }
+  uint32_t box[4] = {64u, 1u << lw, 1u << lh, 1u << ln};
+  return gcc_make_tmap_bf16(m, base, 4, dims, strides, box);
+}
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+template <int BLOCK_N, int STAGES>
+static int launch_conv_gemm(const GemmGeom& g, int m_tiles, int n_tiles, cudaStream_t st) {
+  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess) {
+      gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
+      return GCC_ERR_CUDA;
+    }
+    configured = true;
+  }
+  conv_gemm_kernel<BLOCK_N, STAGES><<<dim3(m_tiles, n_tiles), 192, smem, st>>>(g);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_wgrad_gemm(const GemmGeom& g, dim3 grid, cudaStream_t st) {
+  const int smem = STAGES * (2 * 8192 + (BLOCK_N / 64) * 8192) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess) {
+      gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
+      return GCC_ERR_CUDA;
+    }
+    configured = true;
+  }
+  wgrad_gemm_kernel<BLOCK_N, STAGES><<<grid, 192, smem, st>>>(g);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+static int g_force_block_n = 0;  // test hook
+extern "C" void gcc_debug_force_block_n(int bn) { g_force_block_n = bn; }
+
+static int pick_block_n(int rows) {
+  if (g_force_block_n) return g_force_block_n;
+  if (rows <= 64) return 64;
+  if (rows <= 128) return 128;
+  if (rows % 256 == 0 || rows > 512) return 256;
+  return 128;
+}
+
+// Fill taps for a gather (conv) relation: in = s*o + k - p.
+static int fill_gather_taps(GemmGeom& g, int KH, int KW, int stride, int pad) {
+  if (KH * KW > kMaxTaps) return GCC_ERR_ARG;
+  g.num_taps = KH * KW;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      const int t = kh * KW + kw;
+      const int th = kh - pad, tw = kw - pad;
+      if (stride == 1) {
+        g.tap_map[t] = 0;
+        g.tap_dh[t] = (short)th;
+        g.tap_dw[t] = (short)tw;
+      } else {
+        const int ph = ((th % 2) + 2) % 2, pw = ((tw % 2) + 2) % 2;
+        g.tap_map[t] = (short)(ph * 2 + pw);
+        g.tap_dh[t] = (short)floordiv(th, 2);
+        g.tap_dw[t] = (short)floordiv(tw, 2);
+      }
+      g.tap_widx[t] = (short)t;
+    }
+  return GCC_OK;
+}
+
+extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
+                                  const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
+                                  int KH, int KW, int stride, int pad, int act, float slope, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((Cx % 8) || (Cw % 8) || (Cy % 8) || (y_coff % 8) || T != KH * KW || (stride != 1 && stride != 2) ||
+      KH * KW > kMaxTaps) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: bad arguments");
+    return GCC_ERR_ARG;
+  }
+  const int Rp = (R + 7) / 8 * 8;
+  if (y_coff + Rp > Cy) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: output channel window out of range");
+    return GCC_ERR_ARG;
+  }
+  const int BN = pick_block_n(Rp);
+  const int n_tiles = (Rp + BN - 1) / BN;
+  const int Ck = Cx < Cw ? Cx : Cw;  // contraction extent (both are zero padded to their physical size)
+
+  const int classes = (transposed && stride == 2) ? 4 : 1;
+  for (int cls = 0; cls < classes; ++cls) {
+    GemmGeom g;
+    memset(&g, 0, sizeof(g));
+    int GH, GW;
+    int qh = 0, qw = 0;
+    if (!transposed) {
+      GH = OH; GW = OW;
+      if (stride == 2 && ((H % 2) || (W % 2))) {
+        gcc_set_error(__FILE__, __LINE__, "stride-2 conv needs even H, W");
+        return GCC_ERR_ARG;
+      }
+      int rc = fill_gather_taps(g, KH, KW, stride, pad);
+      if (rc) return rc;
+    } else {
+      qh = cls / 2; qw = cls % 2;
+      if (stride == 1) { GH = OH; GW = OW; }
+      else { GH = (OH - qh + 1) / 2; GW = (OW - qw + 1) / 2; }
+      if (GH <= 0 || GW <= 0) continue;
+      // scatter relation: out = s*in + k - p  <=>  in = (out + p - k) / s when divisible
+      int nt = 0;
+      for (int kh = 0; kh < KH; ++kh)
+        for (int kw = 0; kw < KW; ++kw) {
+          int dh, dw;
+          if (stride == 1) { dh = pad - kh; dw = pad - kw; }
+          else {
+            if (((qh + pad - kh) % 2) || ((qw + pad - kw) % 2)) continue;
+            dh = floordiv(qh + pad - kh, 2);
+            dw = floordiv(qw + pad - kw, 2);
+          }
+          g.tap_map[nt] = 0;
+          g.tap_dh[nt] = (short)dh;
+          g.tap_dw[nt] = (short)dw;
+          g.tap_widx[nt] = (short)(kh * KW + kw);
+          ++nt;
+        }
+      g.num_taps = nt;
+    }
+    g.k_chunks = (Ck + kBlockK - 1) / kBlockK;
+    g.GN = N; g.GH = GH; g.GW = GW;
+    choose_tile(kBlockM, N, GH, GW, &g.log_wt, &g.log_ht, &g.log_nt);
+    g.tiles_w = (GW + (1 << g.log_wt) - 1) >> g.log_wt;
+    g.tiles_h = (GH + (1 << g.log_ht) - 1) >> g.log_ht;
+    g.tiles_n = (N + (1 << g.log_nt) - 1) >> g.log_nt;
+    const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+
+    int rc = 0;
+    if (!transposed && stride == 2) {
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw)
+          rc |= make_act_map(&g.a_maps[ph * 2 + pw], x, N, H, W, Cx, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt);
+    } else {
+      rc |= make_act_map(&g.a_maps[0], x, N, H, W, Cx, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)Cw, (uint64_t)T, (uint64_t)R};
+      uint64_t strides[2] = {(uint64_t)Cw * 2, (uint64_t)Cw * T * 2};
+      uint32_t box[3] = {64u, 1u, (uint32_t)BN};
+      rc |= gcc_make_tmap_bf16(&g.b_map, w, 3, dims, strides, box);
+    }
+    if (rc) return GCC_ERR_DRIVER;
+
+    bf16* yb = reinterpret_cast<bf16*>(y) + y_coff;
+    const int os = (transposed && stride == 2) ? 2 : 1;
+    g.out = yb + ((long long)qh * OW + qw) * Cy;
+    g.out_sn = (long long)OH * OW * Cy;
+    g.out_sh = (long long)OW * Cy * os;
+    g.out_sw = (long long)Cy * os;
+    g.out_cols = Rp;
+    g.bias_cols = R;
+    g.bias = bias;
+    g.act = act;
+    g.slope = slope;
+
+    if (g.num_taps == 0) {
+      gcc_set_error(__FILE__, __LINE__, "transposed conv class with no taps is not supported");
+      return GCC_ERR_ARG;
+    }
+    if (BN == 64) rc = launch_conv_gemm<64, 4>(g, m_tiles, n_tiles, st);
+    else if (BN == 128) rc = launch_conv_gemm<128, 3>(g, m_tiles, n_tiles, st);
+    else rc = launch_conv_gemm<256, 4>(g, m_tiles, n_tiles, st);
+    if (rc) return rc;
+  }
+  return GCC_OK;
+}
+
+// dW[b][r][t][c] (+)= scale * sum_{pix} P[n, oh, ow, r] * Q[n, s*oh + kh - p, s*ow + kw - p, c]
+// P: [N, OH, OW, Cp] bf16, Q: [N, H, W, Cq] bf16, dW fp32 [batch?][R][KH*KW][C].
+extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int Cp, const void* qmat, int H, int W,
+                                   int Cq, float* dw, int R, int C, int KH, int KW, int stride, int pad,
+                                   int batched, int accumulate, float scale, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((Cp % 8) || (Cq % 8) || (stride != 1 && stride != 2) || KH * KW > kMaxTaps || R > Cp || C > Cq) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_wgrad_gemm_bf16: bad arguments");
+    return GCC_ERR_ARG;
+  }
+  if (stride == 2 && ((H % 2) || (W % 2))) {
+    gcc_set_error(__FILE__, __LINE__, "stride-2 wgrad needs even H, W");
+    return GCC_ERR_ARG;
+  }
+  GemmGeom g;
+  memset(&g, 0, sizeof(g));
+  int rc = fill_gather_taps(g, KH, KW, stride, pad);
+  if (rc) return rc;
+  g.GN = N; g.GH = OH; g.GW = OW;
+  if (batched) {
+    choose_tile(64, 1, OH, OW, &g.log_wt, &g.log_ht, &g.log_nt);
+    // a batched tile must not straddle images
+    if (g.log_nt != 0) { g.log_nt = 0; }
+  } else {
+    choose_tile(64, N, OH, OW, &g.log_wt, &g.log_ht, &g.log_nt);
+  }
+  // when the grid is smaller than 64 pixels per image in batched mode the box is still 64 pixels:
+  // widen h/w logs so that the product stays 64 (extra rows are OOB -> zero)
+  while (g.log_wt + g.log_ht + g.log_nt < 6) ++g.log_ht;
+  g.tiles_w = (OW + (1 << g.log_wt) - 1) >> g.log_wt;
+  g.tiles_h = (OH + (1 << g.log_ht) - 1) >> g.log_ht;
+  g.tiles_n = (N + (1 << g.log_nt) - 1) >> g.log_nt;
+
+  rc = make_act_map(&g.p_map, pmat, N, OH, OW, Cp, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
+  if (stride == 2) {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        rc |= make_act_map(&g.a_maps[ph * 2 + pw], qmat, N, H, W, Cq, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt);
+  } else {
+    rc |= make_act_map(&g.a_maps[0], qmat, N, H, W, Cq, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
+  }
+  if (rc) return GCC_ERR_DRIVER;
+
+  const int BN = g_force_block_n ? g_force_block_n : (C <= 64 ? 64 : (C <= 128 ? 128 : 256));
+  const int r_tiles = (R + 127) / 128;
+  const int c_tiles = (C + BN - 1) / BN;
+  const int total_pb = g.tiles_w * g.tiles_h * (batched ? 1 : g.tiles_n);
+  const int base_ctas = r_tiles * c_tiles * g.num_taps * (batched ? N : 1);
+  int splits = 1;
+  // aim for >= 2 waves of CTAs while keeping >= 8 pixel blocks per CTA
+  while (base_ctas * splits < 2 * kNumSMs && total_pb / (splits * 2) >= 8) splits *= 2;
+  g.splits = splits;
+  g.batched = batched;
+  g.atomic_out = (splits > 1 || accumulate) ? 1 : 0;
+  g.scale = scale;
+  g.dw = dw;
+  g.R = R;
+  g.C = C;
+  g.T_total = KH * KW;
+  if (splits > 1 && !accumulate) {
+    const size_t bytes = (size_t)(batched ? N : 1) * R * KH * KW * C * sizeof(float);
+    if (cudaMemsetAsync(dw, 0, bytes, st) != cudaSuccess) return GCC_ERR_CUDA;
+  }
+  dim3 grid(r_tiles, c_tiles, g.num_taps * splits * (batched ? N : 1));
+  if (BN == 64) return launch_wgrad_gemm<64, 4>(g, grid, st);
+  if (BN == 128) return launch_wgrad_gemm<128, 3>(g, grid, st);
+  return launch_wgrad_gemm<256, 4>(g, grid, st);
+}
