@@ -1,0 +1,243 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (/root/reference) on CPU fp32.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python oracle/make_golden.py
+
+Shims (none touches arithmetic): stub modules for the missing `thop` and
+`skimage.metrics`; parameters are overwritten with the name-seeded deterministic values of
+oracle.gcc_oracle.init_like_reference so that fixtures do not depend on torch's RNG stream.
+The fixtures hold summary statistics (sum, |sum|, sum of squares, 24 strided samples) of every
+tensor of interest plus exact masks / channel counts, not the tensors themselves.
+"""
+import copy
+import os
+import sys
+import types
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+
+from oracle import gcc_oracle as O  # noqa: E402
+
+
+def import_reference():
+    thop = types.ModuleType("thop")
+    thop.profile = lambda *a, **k: (0.0, 0.0)
+    sys.modules["thop"] = thop
+    sk = types.ModuleType("skimage")
+    skm = types.ModuleType("skimage.metrics")
+    skm.peak_signal_noise_ratio = lambda *a, **k: 0.0
+    skm.structural_similarity = lambda *a, **k: 0.0
+    sk.metrics = skm
+    sys.modules["skimage"] = sk
+    sys.modules["skimage.metrics"] = skm
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    from options import options  # noqa
+    if not any(a.dest == "generator_only" for a in options.parser._actions):
+        options.parser.add_argument("--generator_only", action="store_true")
+    import models.Pix2Pix as P2P  # noqa
+    os.chdir(cwd)
+    return options, P2P
+
+
+def stats(t, nsamp=24):
+    t = t.detach().float().reshape(-1)
+    n = t.numel()
+    idx = torch.linspace(0, n - 1, min(nsamp, n)).long()
+    return {"n": n, "sum": float(t.double().sum()), "abs": float(t.double().abs().sum()),
+            "sq": float((t.double() ** 2).sum()), "samples": t[idx].tolist(), "idx": idx.tolist()}
+
+
+def make_opt(options, argv):
+    old = sys.argv
+    sys.argv = ["train.py"] + argv
+    try:
+        opt = options.parse()
+    finally:
+        sys.argv = old
+    opt.isTrain = True
+    return opt
+
+
+def set_det_params(model, tag):
+    sd = model.netG.state_dict()
+    O.init_like_reference(sd, tag + ".netG.")
+    model.netG.load_state_dict(sd)
+    sd = model.netD.state_dict()
+    O.init_like_reference(sd, tag + ".netD.")
+    model.netD.load_state_dict(sd)
+    if hasattr(model, "transform_convs"):
+        import math
+        for i, conv in enumerate(model.transform_convs):
+            cin = conv.weight.shape[1]
+            conv.weight.data.copy_(O.det_uniform("%s.transform.%d" % (tag, i), conv.weight.shape, 1.0 / math.sqrt(cin)))
+
+
+def build_reference_pair(options, P2P, argv, small, cfgs=(None, None)):
+    opt = make_opt(options, argv)
+    for k, v in small.items():
+        setattr(opt, k, v)
+    model = P2P.Pix2PixModel(opt, filter_cfgs=cfgs[0], channel_cfgs=cfgs[1])
+    teacher_opt = copy.deepcopy(opt)  # train.py:92-105
+    teacher_opt.ngf = opt.teacher_ngf
+    teacher_opt.ndf = opt.teacher_ndf
+    teacher_opt.darts_discriminator = False
+    teacher_opt.online_distillation = False
+    teacher_opt.generator_only = False
+    teacher = P2P.Pix2PixModel(teacher_opt)
+    teacher.model_train()
+    setattr(model, "teacher_model", teacher)
+    model.init_distillation()
+    teacher.init_distillation()
+    set_det_params(model, "S")
+    set_det_params(teacher, "T")
+    model.model_train()
+    return opt, model, teacher
+
+
+def record_model(rec, prefix, model):
+    for k, v in model.netG.state_dict().items():
+        rec[prefix + ".G." + k] = stats(v)
+    for k, v in model.netD.state_dict().items():
+        rec[prefix + ".D." + k] = stats(v)
+    for k, v in model.netG.named_parameters():
+        if v.grad is not None:
+            rec[prefix + ".G.grad." + k] = stats(v.grad)
+    for k, v in model.netD.named_parameters():
+        if v.grad is not None:
+            rec[prefix + ".D.grad." + k] = stats(v.grad)
+    if hasattr(model, "transform_convs"):
+        for i, c in enumerate(model.transform_convs):
+            rec[prefix + ".transform.%d" % i] = stats(c.weight)
+            if c.weight.grad is not None:
+                rec[prefix + ".transform.grad.%d" % i] = stats(c.weight.grad)
+
+
+def run_step_case(options, P2P, name, argv, small, batch, iters, cfgs=(None, None)):
+    torch.manual_seed(0)
+    opt, model, teacher = build_reference_pair(options, P2P, argv, small, cfgs)
+    out = {"config": {"argv": argv, "small": small, "batch": batch, "iters": iters, "cfgs": cfgs,
+                      "direction": opt.direction}, "iters": []}
+    for it in range(iters):
+        rec = {}
+        A = O.det_image("%s.A.%d" % (name, it), batch, 3, 256, 256)
+        B = O.det_image("%s.B.%d" % (name, it), batch, 3, 256, 256)
+        model.set_input({"A": A, "B": B, "A_paths": "", "B_paths": ""})
+        model.optimize_parameters()
+        rec["fake_B"] = stats(model.fake_B)
+        rec["Tfake_B"] = stats(teacher.fake_B)
+        for i, f in enumerate(model.target_distillation_features):
+            rec["target_feature.%d" % i] = stats(f)
+        for i, f in enumerate(model.get_distillation_features()):
+            rec["student_feature.%d" % i] = stats(f)
+        record_model(rec, "S", model)
+        record_model(rec, "T", teacher)
+        for n in ("G_GAN", "G_L1", "D_real", "D_fake", "content", "gram"):
+            rec["loss.S." + n] = float(getattr(model, "loss_" + n))
+        for n in ("G_GAN", "G_L1", "D_real", "D_fake"):
+            rec["loss.T." + n] = float(getattr(teacher, "loss_" + n))
+        # arch step on a validation batch (train.py:147-151)
+        vA = O.det_image("%s.vA.%d" % (name, it), batch, 3, 256, 256)
+        vB = O.det_image("%s.vB.%d" % (name, it), batch, 3, 256, 256)
+        model.set_input({"A": vA, "B": vB, "A_paths": "", "B_paths": ""})
+        model.clipping_mask_alpha()
+        model.optimizer_netD_arch()
+        for n in ("D_arch_diff", "D_arch", "teacher_D_arch_diff"):
+            rec["loss.S." + n] = float(getattr(model, "loss_" + n))
+        for k, v in model.netD.named_parameters():
+            if k.endswith("alpha"):
+                rec["arch.alpha." + k] = stats(v)
+                rec["arch.alpha_grad." + k] = stats(v.grad)
+        for k, v in model.netD.state_dict().items():
+            if "running" in k:
+                rec["arch.S.D." + k] = stats(v)
+        for k, v in teacher.netD.state_dict().items():
+            if "running" in k:
+                rec["arch.T.D." + k] = stats(v)
+        rec["losses"] = dict(model.get_current_losses())
+        out["iters"].append(rec)
+        print(name, "iter", it, {k: round(v, 5) for k, v in rec["losses"].items()}, flush=True)
+    return out
+
+
+def run_prune_case(options, P2P):
+    out = {}
+    # U-Net scale / norm prune at fixed thresholds on deterministic weights
+    for mode, thr_list in (("scale_prune", [0.98, 1.0, 1.02]), ("norm_prune", [2.0, 6.0, 10.0])):
+        opt = make_opt(options, ["--dataroot", "x/cityscapes", "--model", "pix2pix", "--ngf", "16", "--ndf", "16",
+                                 "--gpu_ids", "-1", "--" + mode, "--no_dropout"])
+        model = P2P.Pix2PixModel(opt)
+        set_det_params(model, "P")
+        for thr in thr_list:
+            pruned = getattr(model, mode)(thr)
+            out["%s@%g" % (mode, thr)] = (list(pruned.filter_cfgs), list(pruned.channel_cfgs))
+        if mode == "scale_prune":
+            mx, mn = model.max_min_bn_scale()
+        else:
+            mx, mn = model.max_min_conv_norm()
+        out[mode + ".maxmin"] = (float(mx), float(mn))
+    opt = make_opt(options, ["--dataroot", "x/cityscapes", "--model", "pix2pix", "--ngf", "16", "--ndf", "16",
+                             "--gpu_ids", "-1", "--norm_prune", "--backbone", "resnet"])
+    model = P2P.Pix2PixModel(opt)
+    set_det_params(model, "P")
+    for thr in (0.5, 2.3, 2.6):
+        pruned = model.resnet_prune(thr)
+        out["resnet_prune@%g" % thr] = list(pruned.filter_cfgs)
+    mx, mn = model.max_min_conv_norm()
+    out["resnet.maxmin"] = (float(mx), float(mn))
+    return out
+
+
+def run_gate_case(P2P):
+    from models.DifferentiableOp import DifferentiableOP
+    op = DifferentiableOP(6, 0.5)
+    op.alpha.data.copy_(torch.tensor([0.7, 0.5, 0.2, 1.0, 0.0, 0.5000001]))
+    x = O.det_normal("gate.x", (2, 6, 3, 3))
+    x.requires_grad_(True)
+    y = op(x)
+    gy = O.det_normal("gate.gy", (2, 6, 3, 3))
+    y.backward(gy)
+    return {"alpha": op.alpha.data.tolist(), "mask": op.get_current_mask().tolist(), "y": y.detach().clone(),
+            "dx": x.grad.clone(), "dalpha": op.alpha.grad.clone()}
+
+
+def run_ganloss_case():
+    from models.GANLoss import GANLoss
+    pred = O.det_normal("ganloss.pred", (3, 1, 30, 30))
+    out = {}
+    for mode in ("hinge", "lsgan", "vanilla", "wgangp"):
+        crit = GANLoss(mode)
+        for real in (True, False):
+            out["%s.D.%s" % (mode, real)] = float(crit(pred, real, for_discriminator=True))
+        out["%s.G" % mode] = float(crit(pred, True, for_discriminator=False))
+    return out
+
+
+def main():
+    options, P2P = import_reference()
+    gold = os.path.join(REPO, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+    base = ["--dataroot", "x/cityscapes", "--model", "pix2pix", "--darts_discriminator", "--online_distillation",
+            "--lambda_content", "50", "--lambda_gram", "1e4", "--gpu_ids", "-1", "--no_dropout"]
+    tiny = {"ngf": 8, "teacher_ngf": 16, "ndf": 16, "teacher_ndf": 16}
+    torch.save(run_step_case(options, P2P, "unet_tiny", base, tiny, batch=2, iters=2),
+               os.path.join(gold, "pix2pix_unet_tiny.pt"))
+    fc = [8, 13, 30, 61, 64, 59, 40, 64, 37, 50, 64, 48, 27, 14, 5]
+    cc = [8, 13, 30, 61, 64, 59, 40, 64, 37 + 40, 50 + 59, 64 + 64, 48 + 61, 27 + 30, 14 + 13, 5 + 8]
+    torch.save(run_step_case(options, P2P, "unet_pruned", base, tiny, batch=1, iters=1, cfgs=(fc, cc)),
+               os.path.join(gold, "pix2pix_unet_pruned.pt"))
+    rcfg = [8, 16, 29, 21, 29, 17, 29, 30, 29, 11, 29, 25, 29, 32, 29, 9, 29, 27, 29, 19, 29, 13, 7]
+    torch.save(run_step_case(options, P2P, "resnet_tiny", base + ["--backbone", "resnet"], tiny, batch=1, iters=1,
+                             cfgs=(rcfg, None)), os.path.join(gold, "pix2pix_resnet_tiny.pt"))
+    torch.save({"prune": run_prune_case(options, P2P), "gate": run_gate_case(P2P), "ganloss": run_ganloss_case()},
+               os.path.join(gold, "pix2pix_small_ops.pt"))
+    print("golden fixtures written to", gold)
+
+
+if __name__ == "__main__":
+    main()
