@@ -92,8 +92,10 @@ __global__ void wgrad_direct_kernel(const bf16* __restrict__ pm, int N, int OH, 
 
 extern "C" int gcc_conv_direct_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                                     const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
-                                    int KH, int KW, int stride, int pad, int act, float slope, void* stream) {
+                                    int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
+                                    void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (w_per_image) { gcc_set_error(__FILE__, __LINE__, "direct conv: per-image weights unsupported"); return GCC_ERR_ARG; }
   const int Rp = (R + 7) / 8 * 8;
   const long long total = (long long)N * OH * OW * Rp;
   const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);

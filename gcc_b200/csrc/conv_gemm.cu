@@ -33,6 +33,7 @@ struct GemmGeom {
   CUtensorMap p_map;      // wgrad: M-side activation (4-D).  conv_gemm: unused
   int num_taps;
   int k_chunks;  // conv_gemm: ceil(C / 64) channel chunks per tap
+  int w_per_image;  // conv_gemm: 1 = weights [N][R][C] (1x1 only), tap index = image index
   short tap_map[kMaxTaps];
   short tap_dh[kMaxTaps];
   short tap_dw[kMaxTaps];
@@ -122,7 +123,8 @@ __global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ 
         uint8_t* sa = smem + stage * kStageBytes;
         tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, b0 + p.tap_dw[tap],
                     a0 + p.tap_dh[tap], n0);
-        tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK, p.tap_widx[tap], n_tile * BLOCK_N);
+        tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK,
+                    p.w_per_image ? n0 : (int)p.tap_widx[tap], n_tile * BLOCK_N);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -458,8 +460,13 @@ static int fill_gather_taps(GemmGeom& g, int KH, int KW, int stride, int pad) {
 
 extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                                   const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
-                                  int KH, int KW, int stride, int pad, int act, float slope, void* stream) {
+                                  int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
+                                  void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (w_per_image && (KH != 1 || KW != 1 || stride != 1 || pad != 0 || transposed)) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: per-image weights need a 1x1 stride-1 conv");
+    return GCC_ERR_ARG;
+  }
   if ((Cx % 8) || (Cw % 8) || (Cy % 8) || (y_coff % 8) || T != KH * KW || (stride != 1 && stride != 2) ||
       KH * KW > kMaxTaps) {
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: bad arguments");
@@ -515,6 +522,11 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
     g.k_chunks = (Ck + kBlockK - 1) / kBlockK;
     g.GN = N; g.GH = GH; g.GW = GW;
     choose_tile(kBlockM, N, GH, GW, &g.log_wt, &g.log_ht, &g.log_nt);
+    g.w_per_image = w_per_image;
+    if (w_per_image) {  // a tile must not straddle images
+      g.log_ht += g.log_nt;
+      g.log_nt = 0;
+    }
     g.tiles_w = (GW + (1 << g.log_wt) - 1) >> g.log_wt;
     g.tiles_h = (GH + (1 << g.log_ht) - 1) >> g.log_ht;
     g.tiles_n = (N + (1 << g.log_nt) - 1) >> g.log_nt;
@@ -529,8 +541,8 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
       rc |= make_act_map(&g.a_maps[0], x, N, H, W, Cx, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
     }
     {
-      uint64_t dims[3] = {(uint64_t)Cw, (uint64_t)T, (uint64_t)R};
-      uint64_t strides[2] = {(uint64_t)Cw * 2, (uint64_t)Cw * T * 2};
+      uint64_t dims[3] = {(uint64_t)Cw, (uint64_t)(w_per_image ? N : T), (uint64_t)R};
+      uint64_t strides[2] = {(uint64_t)Cw * 2 * (w_per_image ? R : 1), (uint64_t)Cw * 2 * (w_per_image ? 1 : T)};
       uint32_t box[3] = {64u, 1u, (uint32_t)BN};
       rc |= gcc_make_tmap_bf16(&g.b_map, w, 3, dims, strides, box);
     }

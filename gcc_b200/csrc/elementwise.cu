@@ -1,0 +1,511 @@
+// Elementwise / layout kernels: NCHW fp32 <-> NHWC bf16 boundary conversion, channel-window copies
+// (torch.cat of the reference, models/Pix2Pix.py:77,467,471,516), activations, dropout, residual add,
+// weight packing, bias gradients, reflection padding and the depthwise 3x3 convolution of the
+// MobileResNet blocks (models/Pix2Pix.py:132-145).  All HBM-bound, vectorised where alignment allows.
+#include "common.cuh"
+
+namespace gcc {
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU;
+  x ^= x >> 15; x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+
+// ---- boundary layout conversion -------------------------------------------------------------
+// dst[n,h,w,c_off + c] = bf16(src[n,c,h,w]); channels [c_off + C, zero_to) are zeroed.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int C, long long HW,
+                                    int Cp, int c_off, int zero_to) {
+  const long long total = (long long)N * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i % HW;
+    bf16* d = dst + i * Cp;
+    for (int c = 0; c < C; ++c) d[c_off + c] = __float2bfloat16(src[(n * C + c) * HW + p]);
+    for (int c = c_off + C; c < zero_to; ++c) d[c] = __float2bfloat16(0.f);
+  }
+}
+// dst[n,c,h,w] (+)= float(src[n,h,w,c_off + c])
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int N, int C, long long HW,
+                                    int Cp, int c_off, int accumulate) {
+  const long long total = (long long)N * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % HW;
+    const long long nc = i / HW;
+    const int c = (int)(nc % C);
+    const long long n = nc / C;
+    const float v = __bfloat162float(src[(n * HW + p) * Cp + c_off + c]);
+    if (accumulate) dst[i] += v;
+    else dst[i] = v;
+  }
+}
+
+// ---- channel window copy (concat / split) ---------------------------------------------------
+// dst[p, d_off + c] (=|+=) src[p, s_off + c], c < C.  Vector path when everything is 8-aligned.
+__global__ void copy_channels_vec_kernel(const bf16* __restrict__ src, int Cs, int s_off, bf16* __restrict__ dst,
+                                         int Cd, int d_off, int G, long long npix, int accumulate) {
+  const long long nvec = npix * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const long long p = i / G;
+    uint4 v = *reinterpret_cast<const uint4*>(src + p * Cs + s_off + g * 8);
+    uint4* d = reinterpret_cast<uint4*>(dst + p * Cd + d_off + g * 8);
+    if (accumulate) {
+      const uint4 o = *d;
+      v.x = pack_bf16(bf16_lo(v.x) + bf16_lo(o.x), bf16_hi(v.x) + bf16_hi(o.x));
+      v.y = pack_bf16(bf16_lo(v.y) + bf16_lo(o.y), bf16_hi(v.y) + bf16_hi(o.y));
+      v.z = pack_bf16(bf16_lo(v.z) + bf16_lo(o.z), bf16_hi(v.z) + bf16_hi(o.z));
+      v.w = pack_bf16(bf16_lo(v.w) + bf16_lo(o.w), bf16_hi(v.w) + bf16_hi(o.w));
+    }
+    *d = v;
+  }
+}
+__global__ void copy_channels_scalar_kernel(const bf16* __restrict__ src, int Cs, int s_off, bf16* __restrict__ dst,
+                                            int Cd, int d_off, int C, long long npix, int accumulate) {
+  const long long total = npix * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long p = i / C;
+    const float v = __bfloat162float(src[p * Cs + s_off + c]);
+    bf16* d = dst + p * Cd + d_off + c;
+    *d = __float2bfloat16(accumulate ? v + __bfloat162float(*d) : v);
+  }
+}
+
+// ---- activations / dropout / add ------------------------------------------------------------
+// mode 1 leaky-relu, 2 relu, 3 tanh
+__global__ void act_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long nvec, int mode,
+                               float slope) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = bf16_lo(w[k]), b = bf16_hi(w[k]);
+      if (mode == 1) { a = a > 0.f ? a : a * slope; b = b > 0.f ? b : b * slope; }
+      else if (mode == 2) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+      else if (mode == 3) { a = tanhf(a); b = tanhf(b); }
+      o[k] = pack_bf16(a, b);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+// dx = dy * f'(.) where ref is the forward INPUT for (leaky-)relu and the forward OUTPUT for tanh
+__global__ void act_bwd_kernel(const bf16* __restrict__ ref, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                               long long nvec, int mode, float slope) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = reinterpret_cast<const uint4*>(ref)[i];
+    const uint4 d = reinterpret_cast<const uint4*>(dy)[i];
+    const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+    const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float ra = bf16_lo(rw[k]), rb = bf16_hi(rw[k]);
+      float da = bf16_lo(dw[k]), db = bf16_hi(dw[k]);
+      if (mode == 1) { da *= ra > 0.f ? 1.f : slope; db *= rb > 0.f ? 1.f : slope; }
+      else if (mode == 2) { da = ra > 0.f ? da : 0.f; db = rb > 0.f ? db : 0.f; }
+      else if (mode == 3) { da *= 1.f - ra * ra; db *= 1.f - rb * rb; }
+      o[k] = pack_bf16(da, db);
+    }
+    reinterpret_cast<uint4*>(dx)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+// Counter-based Bernoulli(keep = 1-p) dropout, scale 1/(1-p); the same (seed, index) regenerates the
+// mask in backward (nn.Dropout(0.5), Pix2Pix.py:64).  seed is read from device memory so that a
+// captured CUDA graph draws a fresh mask on every replay.
+__global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n, float p,
+                               const unsigned long long* __restrict__ seed_ptr, unsigned int salt) {
+  const unsigned long long seed = *seed_ptr;
+  const uint32_t s0 = hash_u32((uint32_t)seed ^ salt), s1 = hash_u32((uint32_t)(seed >> 32) + 0x9e3779b9U);
+  const float scale = 1.f / (1.f - p);
+  const uint32_t cut = (uint32_t)(p * 4294967296.0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t r = hash_u32((uint32_t)i * 0x9e3779b1U + s0) ^ hash_u32((uint32_t)(i >> 32) + s1);
+    const float v = __bfloat162float(x[i]);
+    y[i] = __float2bfloat16(r >= cut ? v * scale : 0.f);
+  }
+}
+__global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y,
+                           long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(a)[i];
+    const uint4 v = reinterpret_cast<const uint4*>(b)[i];
+    uint4 o;
+    o.x = pack_bf16(bf16_lo(u.x) + bf16_lo(v.x), bf16_hi(u.x) + bf16_hi(v.x));
+    o.y = pack_bf16(bf16_lo(u.y) + bf16_lo(v.y), bf16_hi(u.y) + bf16_hi(v.y));
+    o.z = pack_bf16(bf16_lo(u.z) + bf16_lo(v.z), bf16_hi(u.z) + bf16_hi(v.z));
+    o.w = pack_bf16(bf16_lo(u.w) + bf16_lo(v.w), bf16_hi(u.w) + bf16_hi(v.w));
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+
+// ---- weight packing --------------------------------------------------------------------------
+// src fp32 [D0][T][D1] (channels_last storage of an OIHW / IOHW parameter)
+//   direct     bf16 [D0][T][D1p]      transposed bf16 [D1][T][D0p]    (pads stay zero)
+__global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ direct,
+                                   bf16* __restrict__ transposed, int D0, int T, int D1, int D1p, int D0p) {
+  const long long total = (long long)D0 * T * D1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d1 = (int)(i % D1);
+    const long long r = i / D1;
+    const int t = (int)(r % T);
+    const int d0 = (int)(r / T);
+    const bf16 v = __float2bfloat16(src[i]);
+    if (direct) direct[((long long)d0 * T + t) * D1p + d1] = v;
+    if (transposed) transposed[((long long)d1 * T + t) * D0p + d0] = v;
+  }
+}
+
+// ---- bias gradient: db[c] = sum over pixels of dy[p, c_off + c] --------------------------------
+__global__ void colsum_kernel(const bf16* __restrict__ dy, long long npix, int Cp, int c_off, int C,
+                              float* __restrict__ out) {
+  // one warp per channel-slab of pixels; threads stride over pixels, channels looped
+  for (int c = blockIdx.y; c < C; c += gridDim.y) {
+    float acc = 0.f;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix;
+         p += (long long)gridDim.x * blockDim.x)
+      acc += __bfloat162float(dy[p * Cp + c_off + c]);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + c, acc);
+  }
+}
+
+// ---- reflection padding (nn.ReflectionPad2d) fwd / bwd --------------------------------------
+__device__ __forceinline__ int reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+__global__ void reflect_pad_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int G,
+                                   int pad) {
+  const int OH = H + 2 * pad, OW = W + 2 * pad;
+  const long long nvec = (long long)N * OH * OW * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH);
+    const long long n = t / OH;
+    const int ih = reflect(oh - pad, H), iw = reflect(ow - pad, W);
+    reinterpret_cast<uint4*>(y)[i] = reinterpret_cast<const uint4*>(x)[((n * H + ih) * W + iw) * G + g];
+  }
+}
+// dx[n,ih,iw] = sum of dy over all padded positions that mirror onto (ih, iw)
+__global__ void reflect_pad_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int G,
+                                       int pad) {
+  const int OH = H + 2 * pad, OW = W + 2 * pad;
+  const long long nvec = (long long)N * H * W * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int iw = (int)(t % W); t /= W;
+    const int ih = (int)(t % H);
+    const long long n = t / H;
+    int hs[3], ws[3], nh = 0, nw = 0;
+    hs[nh++] = ih + pad;
+    if (ih >= 1 && ih <= pad) hs[nh++] = pad - ih;
+    if (ih <= H - 2 && ih >= H - 1 - pad) hs[nh++] = pad + 2 * (H - 1) - ih;
+    ws[nw++] = iw + pad;
+    if (iw >= 1 && iw <= pad) ws[nw++] = pad - iw;
+    if (iw <= W - 2 && iw >= W - 1 - pad) ws[nw++] = pad + 2 * (W - 1) - iw;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        const uint4 u = reinterpret_cast<const uint4*>(dy)[((n * OH + hs[a]) * OW + ws[b]) * G + g];
+        acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x);
+        acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+        acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z);
+        acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+      }
+    reinterpret_cast<uint4*>(dx)[i] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                                                 pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+
+// ---- depthwise 3x3 (groups = C) with fused reflection padding 1 -------------------------------
+// w: fp32 [C][9], bias fp32 [C].  y[n,h,w,c] = b[c] + sum_k w[c][k] * x[n, refl(h+kh-1), refl(w+kw-1), c]
+__global__ void dw3x3_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ bias, bf16* __restrict__ y, int N, int H, int W, int G,
+                                 int C) {
+  const long long nvec = (long long)N * H * W * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int ow = (int)(t % W); t /= W;
+    const int oh = (int)(t % H);
+    const long long n = t / H;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = (bias && g * 8 + k < C) ? bias[g * 8 + k] : 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = reflect(oh + kh - 1, H);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = reflect(ow + kw - 1, W);
+        const uint4 u = reinterpret_cast<const uint4*>(x)[((n * H + ih) * W + iw) * G + g];
+        const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                             bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = g * 8 + k;
+          if (c < C) acc[k] += xv[k] * w[c * 9 + kh * 3 + kw];
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                                                pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+// data gradient: scatter form of the reflected gather = gather over the (<= 3x3 x mirror) sources.
+// Implemented as: dxp = zero-padded correlation on the reflect-PADDED grid, then folded by
+// reflect_pad_bwd.  Here: dyp-style direct accumulation over taps with explicit mirror bookkeeping
+// is avoided by computing on the padded grid: dxp[n, ph, pw, c] = sum_k w[c][k] * dy[n, ph-kh, pw-kw, c].
+__global__ void dw3x3_bwd_data_padded_kernel(const bf16* __restrict__ dy, const float* __restrict__ w,
+                                             bf16* __restrict__ dxp, int N, int H, int W, int G, int C) {
+  const int PH = H + 2, PW = W + 2;
+  const long long nvec = (long long)N * PH * PW * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int pw = (int)(t % PW); t /= PW;
+    const int ph = (int)(t % PH);
+    const long long n = t / PH;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int oh = ph - kh;
+      if (oh < 0 || oh >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ow = pw - kw;
+        if (ow < 0 || ow >= W) continue;
+        const uint4 u = reinterpret_cast<const uint4*>(dy)[((n * H + oh) * W + ow) * G + g];
+        const float dv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                             bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = g * 8 + k;
+          if (c < C) acc[k] += dv[k] * w[c * 9 + kh * 3 + kw];
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(dxp)[i] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                                                  pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+// weight / bias gradient: dw[c][k] = sum_{n,h,w} dy[n,h,w,c] * x[n, refl(h+kh-1), refl(w+kw-1), c]
+// block = (G groups) x lanes; per-thread 8 channels x 10 accumulators; smem reduce; atomics.
+__global__ void dw3x3_bwd_weight_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                        float* __restrict__ dw, float* __restrict__ dbias, int N, int H, int W, int G,
+                                        int C, int lanes) {
+  extern __shared__ float sred[];  // [lanes][G][80]
+  const int tid = threadIdx.x;
+  const int g = tid % G, lane = tid / G;
+  float acc[8][10];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int j = 0; j < 10; ++j) acc[k][j] = 0.f;
+  const long long npix = (long long)N * H * W;
+  if (lane < lanes) {
+    for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+      const int ow = (int)(p % W);
+      const int oh = (int)((p / W) % H);
+      const long long n = p / ((long long)W * H);
+      const uint4 du = reinterpret_cast<const uint4*>(dy)[p * G + g];
+      const float dv[8] = {bf16_lo(du.x), bf16_hi(du.x), bf16_lo(du.y), bf16_hi(du.y),
+                           bf16_lo(du.z), bf16_hi(du.z), bf16_lo(du.w), bf16_hi(du.w)};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k][9] += dv[k];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = reflect(oh + kh - 1, H);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = reflect(ow + kw - 1, W);
+          const uint4 u = reinterpret_cast<const uint4*>(x)[((n * H + ih) * W + iw) * G + g];
+          const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                               bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k][kh * 3 + kw] += dv[k] * xv[k];
+        }
+      }
+    }
+    float* r = sred + ((long long)lane * G + g) * 80;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int j = 0; j < 10; ++j) r[k * 10 + j] = acc[k][j];
+  }
+  __syncthreads();
+  for (int e = tid; e < G * 80; e += blockDim.x) {
+    const int gg = e / 80, kj = e % 80;
+    const int k = kj / 10, j = kj % 10;
+    const int c = gg * 8 + k;
+    if (c >= C) continue;
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += sred[((long long)l * G + gg) * 80 + kj];
+    if (j < 9) atomicAdd(dw + c * 9 + j, a);
+    else if (dbias) atomicAdd(dbias + c, a);
+  }
+}
+
+static inline int blocks_for(long long n, int per = 256) {
+  long long b = (n + per - 1) / per;
+  const long long cap = 148LL * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace gcc
+
+using namespace gcc;
+
+extern "C" int gcc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, long long HW, int Cp, int c_off,
+                                         int zero_to, void* stream) {
+  nchw_to_nhwc_kernel<<<blocks_for((long long)N * HW), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, N, C, HW, Cp,
+                                                                                       c_off, zero_to);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, long long HW, int Cp, int c_off,
+                                         int accumulate, void* stream) {
+  nhwc_to_nchw_kernel<<<blocks_for((long long)N * C * HW), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, N, C,
+                                                                                           HW, Cp, c_off, accumulate);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_copy_channels_bf16(const void* src, int Cs, int s_off, void* dst, int Cd, int d_off, int C,
+                                      long long npix, int accumulate, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(Cs % 8) && !(s_off % 8) && !(Cd % 8) && !(d_off % 8) && !(C % 8)) {
+    const int G = C / 8;
+    copy_channels_vec_kernel<<<blocks_for(npix * G), 256, 0, st>>>((const bf16*)src, Cs, s_off, (bf16*)dst, Cd, d_off,
+                                                                   G, npix, accumulate);
+  } else {
+    copy_channels_scalar_kernel<<<blocks_for(npix * C), 256, 0, st>>>((const bf16*)src, Cs, s_off, (bf16*)dst, Cd,
+                                                                      d_off, C, npix, accumulate);
+  }
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_act_fwd_bf16(const void* x, void* y, long long n, int mode, float slope, void* stream) {
+  if (n % 8) { gcc_set_error(__FILE__, __LINE__, "act: element count must be a multiple of 8"); return GCC_ERR_ARG; }
+  act_fwd_kernel<<<blocks_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n / 8, mode, slope);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_act_bwd_bf16(const void* ref, const void* dy, void* dx, long long n, int mode, float slope,
+                                void* stream) {
+  if (n % 8) { gcc_set_error(__FILE__, __LINE__, "act: element count must be a multiple of 8"); return GCC_ERR_ARG; }
+  act_bwd_kernel<<<blocks_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)ref, (const bf16*)dy, (bf16*)dx,
+                                                                      n / 8, mode, slope);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_dropout_bf16(const void* x, void* y, long long n, float p, const void* seed_dev, int salt,
+                                void* stream) {
+  dropout_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n, p,
+                                                                  (const unsigned long long*)seed_dev,
+                                                                  (unsigned int)salt);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_add_bf16(const void* a, const void* b, void* y, long long n, void* stream) {
+  if (n % 8) { gcc_set_error(__FILE__, __LINE__, "add: element count must be a multiple of 8"); return GCC_ERR_ARG; }
+  add_kernel<<<blocks_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n / 8);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_pack_weight_bf16(const float* src, void* direct, void* transposed, int D0, int T, int D1, int D1p,
+                                    int D0p, void* stream) {
+  pack_weight_kernel<<<blocks_for((long long)D0 * T * D1), 256, 0, (cudaStream_t)stream>>>(
+      src, (bf16*)direct, (bf16*)transposed, D0, T, D1, D1p, D0p);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_bias_grad_bf16(const void* dy, long long npix, int Cp, int c_off, int C, float* out, int accumulate,
+                                  void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate && cudaMemsetAsync(out, 0, sizeof(float) * C, st) != cudaSuccess) return GCC_ERR_CUDA;
+  int bx = (int)((npix + 255) / 256);
+  if (bx > 128) bx = 128;
+  if (bx < 1) bx = 1;
+  colsum_kernel<<<dim3(bx, C > 64 ? 64 : C), 256, 0, st>>>((const bf16*)dy, npix, Cp, c_off, C, out);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_reflect_pad_bf16(const void* x, void* y, int N, int H, int W, int Cp, int pad, int backward,
+                                    void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cp % 8 || pad >= H || pad >= W) { gcc_set_error(__FILE__, __LINE__, "reflect_pad: bad arguments"); return GCC_ERR_ARG; }
+  const int G = Cp / 8;
+  if (!backward)
+    reflect_pad_kernel<<<blocks_for((long long)N * (H + 2 * pad) * (W + 2 * pad) * G), 256, 0, st>>>(
+        (const bf16*)x, (bf16*)y, N, H, W, G, pad);
+  else  // x = dy on the padded grid [N, H+2p, W+2p, Cp], y = dx [N, H, W, Cp]
+    reflect_pad_bwd_kernel<<<blocks_for((long long)N * H * W * G), 256, 0, st>>>((const bf16*)x, (bf16*)y, N, H, W, G,
+                                                                                 pad);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_dw3x3_fwd_bf16(const void* x, const float* w, const float* bias, void* y, int N, int H, int W,
+                                  int Cp, int C, void* stream) {
+  if (Cp % 8) { gcc_set_error(__FILE__, __LINE__, "dw3x3: bad channel count"); return GCC_ERR_ARG; }
+  dw3x3_fwd_kernel<<<blocks_for((long long)N * H * W * (Cp / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, w, bias, (bf16*)y, N, H, W, Cp / 8, C);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+// dxp: scratch bf16 [N, H+2, W+2, Cp]; dx: [N, H, W, Cp]; dw fp32 [C][9]; dbias fp32 [C] (may be NULL)
+extern "C" int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w, void* dxp, void* dx, float* dw,
+                                  float* dbias, int N, int H, int W, int Cp, int C, int accumulate, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cp % 8 || Cp / 8 > 256) { gcc_set_error(__FILE__, __LINE__, "dw3x3: bad channel count"); return GCC_ERR_ARG; }
+  const int G = Cp / 8;
+  if (dx != nullptr) {
+    dw3x3_bwd_data_padded_kernel<<<blocks_for((long long)N * (H + 2) * (W + 2) * G), 256, 0, st>>>(
+        (const bf16*)dy, w, (bf16*)dxp, N, H, W, G, C);
+    GCC_CHECK_LAUNCH();
+    reflect_pad_bwd_kernel<<<blocks_for((long long)N * H * W * G), 256, 0, st>>>((const bf16*)dxp, (bf16*)dx, N, H, W,
+                                                                                 G, 1);
+    GCC_CHECK_LAUNCH();
+  }
+  if (dw != nullptr) {
+    if (!accumulate) {
+      if (cudaMemsetAsync(dw, 0, sizeof(float) * C * 9, st) != cudaSuccess) return GCC_ERR_CUDA;
+      if (dbias && cudaMemsetAsync(dbias, 0, sizeof(float) * C, st) != cudaSuccess) return GCC_ERR_CUDA;
+    }
+    int lanes = 128 / G;
+    if (lanes < 1) lanes = 1;
+    const int threads = (lanes * G + 31) / 32 * 32;
+    const long long npix = (long long)N * H * W;
+    long long bx = (npix + lanes * 16 - 1) / (lanes * 16);
+    if (bx > 148 * 4) bx = 148 * 4;
+    const size_t smem = sizeof(float) * lanes * G * 80;
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(dw3x3_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      configured = true;
+    }
+    dw3x3_bwd_weight_kernel<<<(unsigned)bx, threads, smem, st>>>((const bf16*)x, (const bf16*)dy, dw, dbias, N, H, W,
+                                                                 G, C, lanes);
+    GCC_CHECK_LAUNCH();
+  }
+  return GCC_OK;
+}

@@ -1,0 +1,217 @@
+// Loss reductions of the GCC step (all produce fp32 scalars on the device, no host sync):
+//   GAN losses ............. models/GANLoss.py:38-59 (hinge / lsgan / vanilla / wgangp means)
+//   L1 ..................... models/Pix2Pix.py:520   (criterionL1(fake_B, real_B))
+//   content / gram RMSE .... models/Pix2Pix.py:542-543 (sqrt(MSE(.)))
+// Inputs are NHWC bf16 activations [npix][Cp] of which the first C channels are logical, or fp32
+// matrices (Gram).  Warp-shuffle + one atomicAdd per block into a pre-zeroed fp32 accumulator.
+#include "common.cuh"
+
+namespace gcc {
+
+__device__ __forceinline__ void block_atomic_sum(float v, float* out) {
+  __shared__ float wsum[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) wsum[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < (blockDim.x + 31) / 32 ? wsum[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) atomicAdd(out, t);
+  }
+}
+
+// per-element GAN loss term and its derivative.  mode: 0 hinge, 1 lsgan, 2 vanilla, 3 wgangp.
+// kind: 0 = D on real, 1 = D on fake, 2 = G (target real, for_discriminator = False)
+__device__ __forceinline__ float gan_term(float x, int mode, int kind, float* grad) {
+  if (mode == 0) {
+    if (kind == 0) { const float v = x - 1.f; *grad = v < 0.f ? -1.f : 0.f; return -fminf(v, 0.f); }
+    if (kind == 1) { const float v = -x - 1.f; *grad = v < 0.f ? 1.f : 0.f; return -fminf(v, 0.f); }
+    *grad = -1.f;
+    return -x;
+  }
+  const float target = (kind == 1) ? 0.f : 1.f;
+  if (mode == 1) { const float d = x - target; *grad = 2.f * d; return d * d; }
+  if (mode == 2) {
+    // BCE with logits: max(x,0) - x*t + log(1 + exp(-|x|))
+    const float l = fmaxf(x, 0.f) - x * target + log1pf(expf(-fabsf(x)));
+    *grad = 1.f / (1.f + expf(-x)) - target;
+    return l;
+  }
+  *grad = (kind == 1) ? 1.f : -1.f;
+  return (kind == 1) ? x : -x;
+}
+
+__global__ void gan_loss_fwd_kernel(const bf16* __restrict__ pred, long long npix, int Cp, int C, int mode, int kind,
+                                    float inv_count, float* __restrict__ out) {
+  float acc = 0.f;
+  const long long total = npix * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C;
+    const int c = (int)(i % C);
+    float g;
+    acc += gan_term(__bfloat162float(pred[p * Cp + c]), mode, kind, &g);
+  }
+  block_atomic_sum(acc * inv_count, out);
+}
+// dpred = gout * d(term)/dx / count   (pad channels get zero)
+__global__ void gan_loss_bwd_kernel(const bf16* __restrict__ pred, long long npix, int Cp, int C, int mode, int kind,
+                                    float inv_count, const float* __restrict__ gout, bf16* __restrict__ dpred) {
+  const float go = *gout * inv_count;
+  const long long total = npix * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    float g = 0.f;
+    if (c < C) gan_term(__bfloat162float(pred[i]), mode, kind, &g);
+    dpred[i] = __float2bfloat16(c < C ? g * go : 0.f);
+  }
+}
+
+// out[0] += sum |a-b| * inv_count   (mode 0)   or   sum (a-b)^2 * inv_count   (mode 1)
+__global__ void diff_reduce_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long npix,
+                                        int Cp, int C, int mode, float inv_count, float* __restrict__ out) {
+  float acc = 0.f;
+  if (C == Cp && (Cp % 8) == 0) {
+    const long long nvec = npix * Cp / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+      const uint4 u = reinterpret_cast<const uint4*>(a)[i];
+      const uint4 v = reinterpret_cast<const uint4*>(b)[i];
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d0 = bf16_lo(uw[k]) - bf16_lo(vw[k]), d1 = bf16_hi(uw[k]) - bf16_hi(vw[k]);
+        acc += mode ? d0 * d0 + d1 * d1 : fabsf(d0) + fabsf(d1);
+      }
+    }
+  } else {
+    const long long total = npix * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const long long p = i / C;
+      const int c = (int)(i % C);
+      const float d = __bfloat162float(a[p * Cp + c]) - __bfloat162float(b[p * Cp + c]);
+      acc += mode ? d * d : fabsf(d);
+    }
+  }
+  block_atomic_sum(acc * inv_count, out);
+}
+// mode 0 (L1 mean):      da = gout * sign(a-b) * inv_count
+// mode 1 (RMSE = sqrt(mean sq)): da = gout * (a-b) * inv_count / rmse,  rmse = sqrt(*msq)
+__global__ void diff_bwd_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long npix, int Cp,
+                                     int C, int mode, float inv_count, const float* __restrict__ gout,
+                                     const float* __restrict__ msq, bf16* __restrict__ da) {
+  float go = *gout * inv_count;
+  if (mode == 1) go /= fmaxf(sqrtf(*msq), 1e-20f);
+  const long long total = npix * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    float r = 0.f;
+    if (c < C) {
+      const float d = __bfloat162float(a[i]) - __bfloat162float(b[i]);
+      r = mode ? d * go : (d > 0.f ? go : (d < 0.f ? -go : 0.f));
+    }
+    da[i] = __float2bfloat16(r);
+  }
+}
+
+// fp32 matrices (Gram): out += sum (a-b)^2 * inv_count
+__global__ void sqdiff_reduce_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                         float inv_count, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    acc += d * d;
+  }
+  block_atomic_sum(acc * inv_count, out);
+}
+// Gram RMSE backward: m[b][i][j] = bf16( coef * ((Gs-Gt)[i][j] + (Gs-Gt)[j][i]) ),
+// coef = gout * inv_count / rmse * gram_scale, so that dF = F m (one 1x1 conv_gemm per sample).
+__global__ void gram_bwd_matrix_kernel(const float* __restrict__ gs, const float* __restrict__ gt, int B, int C,
+                                       int Cp, float inv_count, float gram_scale, const float* __restrict__ gout,
+                                       const float* __restrict__ msq, bf16* __restrict__ m) {
+  const float coef = *gout * inv_count / fmaxf(sqrtf(*msq), 1e-20f) * gram_scale;
+  const long long total = (long long)B * C * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % Cp);
+    const long long bi = i / Cp;
+    const int r = (int)(bi % C);
+    const long long b = bi / C;
+    float v = 0.f;
+    if (j < C) {
+      const long long e1 = (b * C + r) * C + j, e2 = (b * C + j) * C + r;
+      v = coef * ((gs[e1] - gt[e1]) + (gs[e2] - gt[e2]));
+    }
+    m[i] = __float2bfloat16(v);
+  }
+}
+
+// tiny scalar program: out = sqrt(in)   (RMSE from mean-square, kept on device)
+__global__ void scalar_sqrt_kernel(const float* in, float* out) { *out = sqrtf(fmaxf(*in, 0.f)); }
+
+static inline int rblocks(long long n) {
+  long long b = (n + 1023) / 1024;
+  return (int)(b < 1 ? 1 : (b > 148 * 4 ? 148 * 4 : b));
+}
+
+}  // namespace gcc
+
+using namespace gcc;
+
+// out: fp32 scalar, must be zeroed by the caller (several terms may accumulate into one scalar).
+extern "C" int gcc_gan_loss_fwd_bf16(const void* pred, long long npix, int Cp, int C, int mode, int kind, float* out,
+                                     void* stream) {
+  const float inv = 1.f / (float)(npix * C);
+  gan_loss_fwd_kernel<<<rblocks(npix * C), 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, npix, Cp, C, mode, kind,
+                                                                          inv, out);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_gan_loss_bwd_bf16(const void* pred, long long npix, int Cp, int C, int mode, int kind,
+                                     const float* gout, void* dpred, void* stream) {
+  const float inv = 1.f / (float)(npix * C);
+  gan_loss_bwd_kernel<<<rblocks(npix * Cp), 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, npix, Cp, C, mode, kind,
+                                                                           inv, gout, (bf16*)dpred);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+// mode 0: out += mean|a-b| ; mode 1: out += mean (a-b)^2   over the logical [npix][C] elements
+extern "C" int gcc_diff_reduce_bf16(const void* a, const void* b, long long npix, int Cp, int C, int mode, float* out,
+                                    void* stream) {
+  const float inv = 1.f / (float)(npix * C);
+  diff_reduce_bf16_kernel<<<rblocks(npix * Cp / 4), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b,
+                                                                                   npix, Cp, C, mode, inv, out);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_diff_bwd_bf16(const void* a, const void* b, long long npix, int Cp, int C, int mode,
+                                 const float* gout, const float* msq, void* da, void* stream) {
+  const float inv = 1.f / (float)(npix * C);
+  diff_bwd_bf16_kernel<<<rblocks(npix * Cp), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, npix, Cp,
+                                                                            C, mode, inv, gout, msq, (bf16*)da);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_sqdiff_reduce_f32(const float* a, const float* b, long long n, float* out, void* stream) {
+  sqdiff_reduce_f32_kernel<<<rblocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, 1.f / (float)n, out);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_gram_bwd_matrix(const float* gs, const float* gt, int B, int C, int Cp, float gram_scale,
+                                   const float* gout, const float* msq, void* m, void* stream) {
+  const float inv = 1.f / ((float)B * C * C);
+  gram_bwd_matrix_kernel<<<rblocks((long long)B * C * Cp), 256, 0, (cudaStream_t)stream>>>(gs, gt, B, C, Cp, inv,
+                                                                                          gram_scale, gout, msq,
+                                                                                          (bf16*)m);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_scalar_sqrt(const float* in, float* out, void* stream) {
+  scalar_sqrt_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(in, out);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}

@@ -1,0 +1,452 @@
+// Batch-norm / instance-norm / channel-gate / activation kernels over NHWC bf16 activations.
+//
+// Forward of one "norm block" (reference: nn.BatchNorm2d / nn.InstanceNorm2d + DifferentiableOP +
+// (Leaky)ReLU, models/Pix2Pix.py:26-35,201,272-341 and models/DifferentiableOp.py:44-49):
+//     z = gamma * (x - mean) * rstd + beta          (identity when there is no norm)
+//     g = mask * z,  mask = (sign(alpha - t) + 1)/2 (1 when there is no gate)
+//     y = act(g)                                     act in {none, leaky-relu, relu}
+// and optionally a second output y2 = act2(g) written into a channel window of a wider buffer
+// (the U-Net skip concat: the reference's in-place LeakyReLU/ReLU aliasing, Pix2Pix.py:33,35,77).
+//
+// All kernels are HBM-bound: 16-byte vector accesses, channel index = vector index % (Cp/8), fp32
+// statistics accumulated per block in shared memory then one atomicAdd per (block, channel).
+#include "common.cuh"
+
+namespace gcc {
+
+struct Vec8 {
+  float v[8];
+};
+
+__device__ __forceinline__ Vec8 load8(const bf16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  Vec8 r;
+  r.v[0] = bf16_lo(u.x); r.v[1] = bf16_hi(u.x);
+  r.v[2] = bf16_lo(u.y); r.v[3] = bf16_hi(u.y);
+  r.v[4] = bf16_lo(u.z); r.v[5] = bf16_hi(u.z);
+  r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
+  return r;
+}
+__device__ __forceinline__ void store8(bf16* p, const Vec8& r) {
+  uint4 u;
+  u.x = pack_bf16(r.v[0], r.v[1]);
+  u.y = pack_bf16(r.v[2], r.v[3]);
+  u.z = pack_bf16(r.v[4], r.v[5]);
+  u.w = pack_bf16(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ float act_fwd(float g, int act, float slope) {
+  if (act == 1) return g > 0.f ? g : g * slope;
+  if (act == 2) return g > 0.f ? g : 0.f;
+  return g;
+}
+__device__ __forceinline__ float act_grad(float g, int act, float slope) {
+  if (act == 1) return g > 0.f ? 1.f : slope;
+  if (act == 2) return g > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+__device__ __forceinline__ float gate_value(const float* alpha, float thr, int c) {
+  if (alpha == nullptr) return 1.f;
+  const float d = alpha[c] - thr;
+  const float s = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  return (s + 1.f) * 0.5f;
+}
+
+// ---------------------------------------------------------------------------------- statistics
+// sums[(n)][0:Cp) += sum x ; sums[(n)][Cp:2Cp) += sum x^2   (grid.y = n when per_sample)
+__global__ void norm_stats_kernel(const bf16* __restrict__ x, long long npix, int Cp, int G, int lanes,
+                                  float* __restrict__ sums) {
+  extern __shared__ float red[];  // [lanes][G][16]
+  const int tid = threadIdx.x;
+  const int g = tid % G, lane = tid / G;
+  const bf16* xb = x + (long long)blockIdx.y * npix * Cp;
+  float* sb = sums + (long long)blockIdx.y * 2 * Cp;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (lane < lanes) {
+    for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+      const Vec8 a = load8(xb + p * Cp + g * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += a.v[i];
+        q[i] += a.v[i] * a.v[i];
+      }
+    }
+    float* r = red + ((long long)lane * G + g) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      r[i] = s[i];
+      r[8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < G * 16; e += blockDim.x) {
+    const int gg = e / 16, j = e % 16;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[((long long)l * G + gg) * 16 + j];
+    const int c = gg * 8 + (j & 7);
+    atomicAdd(sb + (j < 8 ? 0 : Cp) + c, acc);
+  }
+}
+
+struct NormArgs {
+  const bf16* x;
+  long long npix;  // pixels per statistics group (N*H*W for batch norm, H*W for instance norm)
+  int Cp, C, G;
+  int per_sample;
+  const float* sums;   // nullptr: identity (no normalisation)
+  const float* gamma;  // nullptr: 1
+  const float* beta;   // nullptr: 0
+  const float* alpha;  // nullptr: no gate
+  float thr, eps;
+  int act;
+  float slope;
+  int gate_after;  // 1: y = mask * act(z) (identity norm only: PatchGAN layer 0, Pix2Pix.py:320-322)
+};
+
+__device__ __forceinline__ void channel_affine(const NormArgs& a, int n, int c, float& mean, float& rstd,
+                                               float& gam, float& bet, float& mask) {
+  mean = 0.f;
+  rstd = 1.f;
+  if (a.sums != nullptr) {
+    const float* sb = a.sums + (long long)(a.per_sample ? n : 0) * 2 * a.Cp;
+    const float inv = 1.f / (float)a.npix;
+    mean = sb[c] * inv;
+    const float var = fmaxf(sb[a.Cp + c] * inv - mean * mean, 0.f);
+    rstd = rsqrtf(var + a.eps);
+  }
+  const bool live = c < a.C;
+  gam = (a.gamma != nullptr && live) ? a.gamma[c] : (live ? 1.f : 0.f);
+  bet = (a.beta != nullptr && live) ? a.beta[c] : 0.f;
+  mask = (a.alpha != nullptr && live) ? gate_value(a.alpha, a.thr, c) : 1.f;
+  if (!live) { mean = 0.f; rstd = 0.f; }
+}
+
+// -------------------------------------------------------------------------------------- forward
+__global__ void norm_apply_kernel(NormArgs a, int nimg, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp,
+                                  int y2_coff, int act2, float* running_mean, float* running_var, float momentum) {
+  const long long total_pix = a.per_sample ? a.npix * nimg : a.npix;
+  const long long nvec = total_pix * a.G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % a.G);
+    const long long pix = i / a.G;
+    const int n = a.per_sample ? (int)(pix / a.npix) : 0;
+    const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
+    Vec8 o, o2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float mean, rstd, gam, bet, mask;
+      channel_affine(a, n, g * 8 + k, mean, rstd, gam, bet, mask);
+      const float z = (xv.v[k] - mean) * rstd * gam + bet;
+      if (a.gate_after) {
+        o.v[k] = act_fwd(z, a.act, a.slope) * mask;
+        o2.v[k] = act_fwd(z, act2, a.slope) * mask;
+      } else {
+        const float gg = z * mask;
+        o.v[k] = act_fwd(gg, a.act, a.slope);
+        o2.v[k] = act_fwd(gg, act2, a.slope);
+      }
+    }
+    if (y != nullptr) store8(y + pix * a.Cp + g * 8, o);
+    if (y2 != nullptr) store8(y2 + pix * y2_Cp + y2_coff + g * 8, o2);
+  }
+  // running statistics (train-mode BatchNorm2d side effect; momentum 0.1, unbiased variance)
+  if (running_mean != nullptr && blockIdx.x == 0 && a.sums != nullptr) {
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      const float inv = 1.f / (float)a.npix;
+      const float mean = a.sums[c] * inv;
+      const float var = fmaxf(a.sums[a.Cp + c] * inv - mean * mean, 0.f);
+      const float unb = a.npix > 1 ? var * ((float)a.npix / (float)(a.npix - 1)) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+    }
+  }
+}
+
+// eval-mode batch norm: statistics come from the running buffers
+__global__ void norm_apply_eval_kernel(NormArgs a, const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                       long long total_pix, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp,
+                                       int y2_coff, int act2) {
+  const long long nvec = total_pix * a.G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % a.G);
+    const long long pix = i / a.G;
+    const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
+    Vec8 o, o2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g * 8 + k;
+      float z = 0.f, mask = 1.f;
+      if (c < a.C) {
+        const float rstd = rsqrtf(rvar[c] + a.eps);
+        z = (xv.v[k] - rmean[c]) * rstd * (a.gamma ? a.gamma[c] : 1.f) + (a.beta ? a.beta[c] : 0.f);
+        mask = gate_value(a.alpha, a.thr, c);
+      }
+      if (a.gate_after) {
+        o.v[k] = act_fwd(z, a.act, a.slope) * mask;
+        o2.v[k] = act_fwd(z, act2, a.slope) * mask;
+      } else {
+        const float gg = z * mask;
+        o.v[k] = act_fwd(gg, a.act, a.slope);
+        o2.v[k] = act_fwd(gg, act2, a.slope);
+      }
+    }
+    if (y != nullptr) store8(y + pix * a.Cp + g * 8, o);
+    if (y2 != nullptr) store8(y2 + pix * y2_Cp + y2_coff + g * 8, o2);
+  }
+}
+
+// ------------------------------------------------------------------------------------- backward
+// red[(n)][0:Cp) += sum dg ; red[(n)][Cp:2Cp) += sum dg * xhat      dg = dy*act'(g) + dy2*act2'(g)
+__global__ void norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
+                                       const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
+                                       float* __restrict__ red) {
+  extern __shared__ float sred[];  // [lanes][G][16]
+  const int tid = threadIdx.x;
+  const int g = tid % a.G, lane = tid / a.G;
+  const int n = blockIdx.y;
+  const long long pix0 = (long long)n * a.npix;  // blockIdx.y == 0 for batch norm
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  if (lane < lanes) {
+    float mean[8], rstd[8], gam[8], bet[8], mask[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) channel_affine(a, n, g * 8 + k, mean[k], rstd[k], gam[k], bet[k], mask[k]);
+    for (long long p = (long long)blockIdx.x * lanes + lane; p < a.npix; p += (long long)gridDim.x * lanes) {
+      const long long pix = pix0 + p;
+      const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
+      Vec8 d1, d2;
+      if (dy != nullptr) d1 = load8(dy + pix * dy_Cp + dy_coff + g * 8);
+      if (dy2 != nullptr) d2 = load8(dy2 + pix * dy2_Cp + dy2_coff + g * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (xv.v[k] - mean[k]) * rstd[k];
+        const float z = xh * gam[k] + bet[k];
+        const float gg = a.gate_after ? z : z * mask[k];
+        float dg = 0.f;
+        if (dy != nullptr) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
+        if (dy2 != nullptr) dg += d2.v[k] * act_grad(gg, act2, a.slope);
+        s1[k] += dg;
+        if (a.gate_after) {  // S2 = sum dy * act(z): the gate gradient of y = mask * act(z)
+          if (dy != nullptr) s2[k] += d1.v[k] * act_fwd(z, a.act, a.slope);
+          if (dy2 != nullptr) s2[k] += d2.v[k] * act_fwd(z, act2, a.slope);
+        } else {
+          s2[k] += dg * xh;
+        }
+      }
+    }
+    float* r = sred + ((long long)lane * a.G + g) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      r[i] = s1[i];
+      r[8 + i] = s2[i];
+    }
+  }
+  __syncthreads();
+  float* rb = red + (long long)n * 2 * a.Cp;
+  for (int e = tid; e < a.G * 16; e += blockDim.x) {
+    const int gg = e / 16, j = e % 16;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += sred[((long long)l * a.G + gg) * 16 + j];
+    atomicAdd(rb + (j < 8 ? 0 : a.Cp) + gg * 8 + (j & 7), acc);
+  }
+}
+
+// dx = gamma*rstd*mask * (dg - (S1 + xhat*S2)/M)   [norm]   or   dx = mask*dg [identity]
+// block 0 also accumulates dgamma += mask*S2, dbeta += mask*S1, dalpha += gamma*S2 + beta*S1 (summed over n).
+__global__ void norm_bwd_apply_kernel(NormArgs a, int nimg, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
+                                      const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
+                                      const float* __restrict__ red, bf16* __restrict__ dx, float* dgamma,
+                                      float* dbeta, float* dalpha) {
+  const long long total_pix = a.per_sample ? a.npix * nimg : a.npix;
+  const long long nvec = total_pix * a.G;
+  const float invM = 1.f / (float)a.npix;
+  if (dx != nullptr) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int g = (int)(i % a.G);
+      const long long pix = i / a.G;
+      const int n = a.per_sample ? (int)(pix / a.npix) : 0;
+      const float* rb = red + (long long)n * 2 * a.Cp;
+      const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
+      Vec8 d1, d2, o;
+      if (dy != nullptr) d1 = load8(dy + pix * dy_Cp + dy_coff + g * 8);
+      if (dy2 != nullptr) d2 = load8(dy2 + pix * dy2_Cp + dy2_coff + g * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = g * 8 + k;
+        float mean, rstd, gam, bet, mask;
+        channel_affine(a, n, c, mean, rstd, gam, bet, mask);
+        const float xh = (xv.v[k] - mean) * rstd;
+        const float gg = a.gate_after ? (xh * gam + bet) : (xh * gam + bet) * mask;
+        float dg = 0.f;
+        if (dy != nullptr) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
+        if (dy2 != nullptr) dg += d2.v[k] * act_grad(gg, act2, a.slope);
+        float r;
+        if (a.sums != nullptr)
+          r = gam * rstd * mask * (dg - (rb[c] + xh * rb[a.Cp + c]) * invM);
+        else
+          r = gam * mask * dg;
+        o.v[k] = (c < a.C) ? r : 0.f;
+      }
+      store8(dx + pix * a.Cp + g * 8, o);
+    }
+  }
+  if (blockIdx.x == 0 && (dgamma != nullptr || dbeta != nullptr || dalpha != nullptr)) {
+    const int groups = a.per_sample ? nimg : 1;
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      float S1 = 0.f, S2 = 0.f;
+      for (int n = 0; n < groups; ++n) {
+        S1 += red[(long long)n * 2 * a.Cp + c];
+        S2 += red[(long long)n * 2 * a.Cp + a.Cp + c];
+      }
+      const float gam = a.gamma ? a.gamma[c] : 1.f;
+      const float bet = a.beta ? a.beta[c] : 0.f;
+      const float mask = a.alpha ? gate_value(a.alpha, a.thr, c) : 1.f;
+      // parameter gradients ACCUMULATE (the arena is zeroed by zero_grad)
+      if (dgamma) dgamma[c] += mask * S2;
+      if (dbeta) dbeta[c] += mask * S1;
+      if (dalpha) dalpha[c] += a.gate_after ? S2 : gam * S2 + bet * S1;
+    }
+  }
+}
+
+static inline int stats_threads(int G, int* lanes) {
+  int l = 256 / G;
+  if (l < 1) l = 1;
+  *lanes = l;
+  int t = l * G;
+  return (t + 31) / 32 * 32;
+}
+
+}  // namespace gcc
+
+using namespace gcc;
+
+static int fill_args(NormArgs& a, const void* x, int N, long long HW, int Cp, int C, int per_sample,
+                     const float* sums, const float* gamma, const float* beta, const float* alpha, float thr,
+                     float eps, int act, float slope, int gate_after = 0) {
+  if (Cp % 8 || C > Cp || Cp / 8 > 512) {
+    gcc_set_error(__FILE__, __LINE__, "norm: channel count must be a multiple of 8 and <= 4096");
+    return GCC_ERR_ARG;
+  }
+  a.x = (const bf16*)x;
+  a.npix = per_sample ? HW : (long long)N * HW;
+  a.Cp = Cp; a.C = C; a.G = Cp / 8;
+  a.per_sample = per_sample;
+  a.sums = sums; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
+  a.thr = thr; a.eps = eps; a.act = act; a.slope = slope;
+  a.gate_after = gate_after;
+  if (gate_after && sums != nullptr) {
+    gcc_set_error(__FILE__, __LINE__, "norm: gate_after_act is only defined for the identity norm");
+    return GCC_ERR_ARG;
+  }
+  return GCC_OK;
+}
+
+static int ew_blocks(long long nvec) {
+  long long b = (nvec + 255) / 256;
+  const long long cap = 148LL * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// sums: fp32 [N if per_sample else 1][2][Cp]; zeroed here.
+extern "C" int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, int per_sample, float* sums,
+                                   void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cp % 8 || Cp / 8 > 512) {
+    gcc_set_error(__FILE__, __LINE__, "norm_stats: bad channel count");
+    return GCC_ERR_ARG;
+  }
+  const int G = Cp / 8;
+  const int groups = per_sample ? N : 1;
+  const long long npix = per_sample ? HW : (long long)N * HW;
+  if (cudaMemsetAsync(sums, 0, sizeof(float) * 2 * Cp * groups, st) != cudaSuccess) return GCC_ERR_CUDA;
+  int lanes;
+  const int threads = stats_threads(G, &lanes);
+  long long bx = (npix + lanes * 8 - 1) / (lanes * 8);
+  const long long cap = (148LL * 8 + groups - 1) / groups;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  norm_stats_kernel<<<dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * G * 16, st>>>(
+      (const bf16*)x, npix, Cp, G, lanes, sums);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+extern "C" int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, int Cp, int C, int per_sample,
+                                   const float* sums, const float* gamma, const float* beta, const float* alpha,
+                                   float thr, float eps, float* running_mean, float* running_var, float momentum,
+                                   int act, float slope, int gate_after, void* y2, int y2_Cp, int y2_coff, int act2,
+                                   void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NormArgs a;
+  int rc = fill_args(a, x, N, HW, Cp, C, per_sample, sums, gamma, beta, alpha, thr, eps, act, slope, gate_after);
+  if (rc) return rc;
+  if (y2 != nullptr && ((y2_Cp % 8) || (y2_coff % 8))) {
+    gcc_set_error(__FILE__, __LINE__, "norm_apply: second output window must be 8-channel aligned");
+    return GCC_ERR_ARG;
+  }
+  const long long nvec = (long long)N * HW * a.G;
+  norm_apply_kernel<<<ew_blocks(nvec), 256, 0, st>>>(a, N, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff, act2, running_mean,
+                                                     running_var, momentum);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+extern "C" int gcc_norm_apply_eval_bf16(const void* x, void* y, int N, long long HW, int Cp, int C,
+                                        const float* running_mean, const float* running_var, const float* gamma,
+                                        const float* beta, const float* alpha, float thr, float eps, int act,
+                                        float slope, void* y2, int y2_Cp, int y2_coff, int act2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NormArgs a;
+  int rc = fill_args(a, x, N, HW, Cp, C, 0, nullptr, gamma, beta, alpha, thr, eps, act, slope, 0);
+  if (rc) return rc;
+  const long long nvec = (long long)N * HW * a.G;
+  norm_apply_eval_kernel<<<ew_blocks(nvec), 256, 0, st>>>(a, running_mean, running_var, (long long)N * HW, (bf16*)y,
+                                                          (bf16*)y2, y2_Cp, y2_coff, act2);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+// red: fp32 workspace [N if per_sample else 1][2][Cp] (zeroed here).  dx may be NULL (only parameter
+// gradients wanted); dgamma/dbeta/dalpha may be NULL.
+extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int C, int per_sample, const float* sums,
+                                 const float* gamma, const float* beta, const float* alpha, float thr, float eps,
+                                 int act, float slope, int gate_after, const void* dy, int dy_Cp, int dy_coff,
+                                 const void* dy2, int dy2_Cp, int dy2_coff, int act2, float* red, void* dx,
+                                 float* dgamma, float* dbeta, float* dalpha, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NormArgs a;
+  int rc = fill_args(a, x, N, HW, Cp, C, per_sample, sums, gamma, beta, alpha, thr, eps, act, slope, gate_after);
+  if (rc) return rc;
+  if ((dy && ((dy_Cp % 8) || (dy_coff % 8))) || (dy2 && ((dy2_Cp % 8) || (dy2_coff % 8)))) {
+    gcc_set_error(__FILE__, __LINE__, "norm_bwd: gradient windows must be 8-channel aligned");
+    return GCC_ERR_ARG;
+  }
+  const int groups = per_sample ? N : 1;
+  const bool need_red = (sums != nullptr) || dgamma || dbeta || dalpha;
+  if (need_red) {
+    if (cudaMemsetAsync(red, 0, sizeof(float) * 2 * Cp * groups, st) != cudaSuccess) return GCC_ERR_CUDA;
+    int lanes;
+    const int threads = stats_threads(a.G, &lanes);
+    long long bx = (a.npix + lanes * 8 - 1) / (lanes * 8);
+    const long long cap = (148LL * 8 + groups - 1) / groups;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    norm_bwd_reduce_kernel<<<dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st>>>(
+        a, lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
+    GCC_CHECK_LAUNCH();
+  }
+  const long long nvec = (long long)N * HW * a.G;
+  norm_bwd_apply_kernel<<<dx ? ew_blocks(nvec) : 1, 256, 0, st>>>(a, N, (const bf16*)dy, dy_Cp, dy_coff,
+                                                                 (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red,
+                                                                 (bf16*)dx, dgamma, dbeta, dalpha);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}

@@ -1,0 +1,120 @@
+// Optimizer-side kernels: fused Adam over a flat parameter arena (torch.optim.Adam semantics as
+// used at models/Pix2Pix.py:382,415,430,431,440: no weight decay, no amsgrad, eps 1e-8), the
+// L1-sparsity gradient term (models/Pix2Pix.py:554-563) and the table-driven bf16 weight re-pack
+// that follows every optimizer step.
+#include "common.cuh"
+
+namespace gcc {
+
+// hyper (device memory): [0] lr, [1] beta1, [2] beta2, [3] eps, [4] step (as float bits of int)
+__global__ void adam_tick_kernel(float* hyper) {
+  int* step = reinterpret_cast<int*>(hyper + 4);
+  *step += 1;
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, const float* __restrict__ hyper) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+  const int step = *reinterpret_cast<const int*>(hyper + 4);
+  // bias corrections in double: 1 - beta^t = -expm1(t * log(beta))
+  const float bc1 = (float)(-expm1((double)step * log((double)b1)));
+  const float bc2_sqrt = (float)sqrt(-expm1((double)step * log((double)b2)));
+  const float step_size = lr / bc1;
+  const long long nvec = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define GCC_ADAM1(F)                                        \
+  mm.F = b1 * mm.F + (1.f - b1) * gg.F;                     \
+  vv.F = b2 * vv.F + (1.f - b2) * gg.F * gg.F;              \
+  pp.F -= step_size * mm.F / (sqrtf(vv.F) / bc2_sqrt + eps);
+    GCC_ADAM1(x) GCC_ADAM1(y) GCC_ADAM1(z) GCC_ADAM1(w)
+#undef GCC_ADAM1
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  for (long long i = nvec * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+__global__ void l1_sparsity_kernel(const float* __restrict__ w, float* __restrict__ g, long long n, float lambda) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    g[i] += lambda * (x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f));
+  }
+}
+
+__global__ void clamp_kernel(float* __restrict__ x, long long n, float lo, float hi) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = fminf(fmaxf(x[i], lo), hi);
+}
+
+// table entry (8 x int64): src, direct, transposed, D0, T, D1, D1p, D0p
+__global__ void pack_table_kernel(const long long* __restrict__ table) {
+  const long long* e = table + (long long)blockIdx.y * 8;
+  const float* src = reinterpret_cast<const float*>(e[0]);
+  bf16* direct = reinterpret_cast<bf16*>(e[1]);
+  bf16* transposed = reinterpret_cast<bf16*>(e[2]);
+  const int D0 = (int)e[3], T = (int)e[4], D1 = (int)e[5], D1p = (int)e[6], D0p = (int)e[7];
+  const long long total = (long long)D0 * T * D1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d1 = (int)(i % D1);
+    const long long r = i / D1;
+    const int t = (int)(r % T);
+    const int d0 = (int)(r / T);
+    const bf16 val = __float2bfloat16(src[i]);
+    if (direct) direct[((long long)d0 * T + t) * D1p + d1] = val;
+    if (transposed) transposed[((long long)d1 * T + t) * D0p + d0] = val;
+  }
+}
+
+}  // namespace gcc
+
+using namespace gcc;
+
+extern "C" int gcc_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float* hyper_dev,
+                                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, st>>>(hyper_dev);
+  GCC_CHECK_LAUNCH();
+  long long b = (n / 4 + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  adam_kernel<<<(unsigned)b, 256, 0, st>>>(p, g, m, v, n, hyper_dev);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_l1_sparsity_f32(const float* w, float* g, long long n, float lambda, void* stream) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  l1_sparsity_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(w, g, n, lambda);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_clamp_f32(float* x, long long n, float lo, float hi, void* stream) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  clamp_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(x, n, lo, hi);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+// table: device int64 [count][8] = {src fp32 ptr, direct bf16 ptr, transposed bf16 ptr, D0, T, D1, D1p, D0p}
+extern "C" int gcc_pack_weights_table(const void* table_dev, int count, void* stream) {
+  if (count <= 0) return GCC_OK;
+  pack_table_kernel<<<dim3(64, count), 256, 0, (cudaStream_t)stream>>>((const long long*)table_dev);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}

@@ -1,0 +1,454 @@
+"""autograd.Function wrappers over the C-ABI kernels.  Activations are NHWC bf16 tensors
+[N, H, W, Cp] (Cp = channels padded to a multiple of 8, pad channels are exactly zero).
+
+Parameter gradients are not returned to autograd: the kernels accumulate them straight into the
+owning ``ParamArena``'s flat gradient buffer (zeroed by ``arena.zero_grad()``), honouring the
+parameter's ``requires_grad`` flag exactly like the reference's set_requires_grad toggles
+(models/Pix2Pix.py:574-590).
+"""
+import torch
+
+from . import _lib
+from .arena import rp8
+
+call = _lib.call
+BN_EPS = 1e-5
+BN_MOM = 0.1
+
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(x):
+    if not x.is_cuda:
+        raise _lib.GccB200Error("gcc_b200 ops need CUDA tensors: there is no CPU fallback")
+    return x
+
+
+def _window(t):
+    """(pointer, channel stride) of an NHWC gradient that may be a channel-window view."""
+    n, h, w, c = t.shape
+    if t.stride(3) == 1:
+        cs = t.stride(2)
+        if t.stride(1) == w * cs and t.stride(0) == h * w * cs and cs % 8 == 0 and t.data_ptr() % 16 == 0:
+            return t, cs
+    t = t.contiguous()
+    return t, t.shape[3]
+
+
+def conv_out_hw(h, w, k, stride, pad, transposed, outpad=0):
+    if not transposed:
+        return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    return (h - 1) * stride - 2 * pad + k + outpad, (w - 1) * stride - 2 * pad + k + outpad
+
+
+class ConvFn(torch.autograd.Function):
+    """nn.Conv2d / nn.ConvTranspose2d (+ bias, + fused LeakyReLU/Tanh epilogue) on tcgen05."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, act, slope):
+        _check(x)
+        x = x.contiguous()
+        layer.arena.ensure_packed()
+        n, h, w, cx = x.shape
+        tr = 1 if layer.kind == "convT" else 0
+        oh, ow = conv_out_hw(h, w, layer.k, layer.stride, layer.pad, tr, layer.outpad)
+        cop = rp8(layer.cout)
+        y = torch.empty(n, oh, ow, cop, dtype=torch.bfloat16, device=x.device)
+        pk = layer.packs
+        wp = pk.direct if not tr else pk.transposed  # [cout][T][cin_p]
+        epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
+        call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), layer.cout, layer.k * layer.k,
+             wp.shape[2], None if bias is None else bias.data_ptr(), y.data_ptr(), oh, ow, cop, 0, tr, layer.k,
+             layer.k, layer.stride, layer.pad, epi, slope, 0, _st())
+        ctx.layer, ctx.act, ctx.slope = layer, act, slope
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        x, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        st = _st()
+        if ctx.act != ACT_NONE:
+            dpre = torch.empty_like(dy)
+            call("gcc_act_bwd_bf16", y.data_ptr(), dy.data_ptr(), dpre.data_ptr(), dy.numel(),
+                 1 if ctx.act == ACT_LRELU else 3, ctx.slope, st)
+        else:
+            dpre = dy
+        n, h, w, cx = x.shape
+        _, oh, ow, cop = dpre.shape
+        tr = layer.kind == "convT"
+        T = layer.k * layer.k
+        dx = None
+        if ctx.needs_input_grad[0]:
+            layer.arena.ensure_packed()
+            pk = layer.packs
+            wp = pk.transposed if not tr else pk.direct  # [cin][T][cout_p]
+            dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=x.device)
+            call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin, T, wp.shape[2], None,
+                 dx.data_ptr(), h, w, dx.shape[3], 0, 0 if tr else 1, layer.k, layer.k, layer.stride, layer.pad, 0,
+                 0.0, 0, st)
+            if dx.shape[3] != cx:
+                raise _lib.GccB200Error("conv input channel padding mismatch")
+        if ctx.needs_input_grad[1]:
+            gw = layer.arena.flat_grad[layer.wname]
+            if not tr:  # dW[co][tap][ci] = sum dy[.., co] * x[gather, ci]
+                call("gcc_wgrad_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, x.data_ptr(), h, w, cx, gw.data_ptr(),
+                     layer.cout, layer.cin, layer.k, layer.k, layer.stride, layer.pad, 0, 1, 1.0, st)
+            else:  # dW[ci][tap][co] = sum x[.., ci] * dy[gather, co]
+                call("gcc_wgrad_gemm_bf16", x.data_ptr(), n, h, w, cx, dpre.data_ptr(), oh, ow, cop, gw.data_ptr(),
+                     layer.cin, layer.cout, layer.k, layer.k, layer.stride, layer.pad, 0, 1, 1.0, st)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = layer.arena.flat_grad[layer.bname]
+            call("gcc_bias_grad_bf16", dpre.data_ptr(), n * oh * ow, cop, 0, layer.cout, gb.data_ptr(), 1, st)
+        return dx, None, None, None, None, None
+
+
+class NormActFn(torch.autograd.Function):
+    """[BatchNorm | InstanceNorm | identity] -> [channel gate] -> activation, with an optional second
+    activation output (the U-Net's relu'd skip copy)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, alpha, layer, act, act2):
+        _check(x)
+        x = x.contiguous()
+        n, h, w, cp = x.shape
+        st = _st()
+        mode = layer.mode  # 'bn', 'in', 'id'
+        per_sample = 1 if mode == "in" else 0
+        y = torch.empty_like(x)
+        y2 = torch.empty_like(x) if act2 is not None else None
+        gp = None if gamma is None else gamma.data_ptr()
+        bp = None if beta is None else beta.data_ptr()
+        ap = None if alpha is None else alpha.data_ptr()
+        sums = None
+        if mode == "bn" and not layer.training:
+            call("gcc_norm_apply_eval_bf16", x.data_ptr(), y.data_ptr(), n, h * w, cp, layer.c,
+                 layer.running_mean.data_ptr(), layer.running_var.data_ptr(), gp, bp, ap, layer.thr, BN_EPS, act,
+                 layer.slope, None if y2 is None else y2.data_ptr(), cp, 0, act2 or 0, st)
+            ctx.eval_bn = True
+        else:
+            ctx.eval_bn = False
+            if mode != "id":
+                sums = torch.empty((n if per_sample else 1) * 2 * cp, dtype=torch.float32, device=x.device)
+                call("gcc_norm_stats_bf16", x.data_ptr(), n, h * w, cp, per_sample, sums.data_ptr(), st)
+                if layer.stats_hook is not None:
+                    layer.stats_hook(sums)
+            rm = rv = None
+            if mode == "bn" and layer.running_mean is not None:
+                rm, rv = layer.running_mean.data_ptr(), layer.running_var.data_ptr()
+                layer.num_batches += 1
+            call("gcc_norm_apply_bf16", x.data_ptr(), y.data_ptr(), n, h * w, cp, layer.c, per_sample,
+                 None if sums is None else sums.data_ptr(), gp, bp, ap, layer.thr, BN_EPS, rm, rv, BN_MOM, act,
+                 layer.slope, 1 if (mode == "id" and alpha is not None) else 0,
+                 None if y2 is None else y2.data_ptr(), cp, 0, act2 or 0, st)
+        ctx.layer, ctx.act, ctx.act2 = layer, act, act2
+        ctx.save_for_backward(x, sums, gamma, beta, alpha)
+        ctx.set_materialize_grads(False)
+        if y2 is None:
+            return y
+        return y, y2
+
+    @staticmethod
+    def backward(ctx, dy, dy2=None):
+        layer = ctx.layer
+        if ctx.eval_bn:
+            raise _lib.GccB200Error("backward through eval-mode batch norm is not implemented")
+        x, sums, gamma, beta, alpha = ctx.saved_tensors
+        n, h, w, cp = x.shape
+        st = _st()
+        per_sample = 1 if layer.mode == "in" else 0
+        p1 = p2 = None
+        c1 = c2 = cp
+        if dy is not None:
+            dy, c1 = _window(dy)
+            p1 = dy.data_ptr()
+        if dy2 is not None:
+            dy2, c2 = _window(dy2)
+            p2 = dy2.data_ptr()
+        arena_of = lambda p: p._gcc_arena.flat_grad[p._gcc_name].data_ptr()
+        dgamma = arena_of(gamma) if (gamma is not None and ctx.needs_input_grad[1]) else None
+        dbeta = arena_of(beta) if (beta is not None and ctx.needs_input_grad[2]) else None
+        dalpha = arena_of(alpha) if (alpha is not None and ctx.needs_input_grad[3]) else None
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        red = torch.empty((n if per_sample else 1) * 2 * cp, dtype=torch.float32, device=x.device)
+        call("gcc_norm_bwd_bf16", x.data_ptr(), n, h * w, cp, layer.c, per_sample,
+             None if sums is None else sums.data_ptr(), None if gamma is None else gamma.data_ptr(),
+             None if beta is None else beta.data_ptr(), None if alpha is None else alpha.data_ptr(), layer.thr, BN_EPS,
+             ctx.act, layer.slope, 1 if (layer.mode == "id" and alpha is not None) else 0, p1, c1, 0, p2, c2, 0,
+             ctx.act2 or 0, red.data_ptr(),
+             None if dx is None else dx.data_ptr(), dgamma, dbeta, dalpha, st)
+        return dx, None, None, None, None, None, None
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mode, slope):
+        x = _check(x).contiguous()
+        y = torch.empty_like(x)
+        call("gcc_act_fwd_bf16", x.data_ptr(), y.data_ptr(), x.numel(), mode, slope, _st())
+        ctx.mode, ctx.slope = mode, slope
+        ctx.save_for_backward(y if mode == ACT_TANH else x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ref,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        call("gcc_act_bwd_bf16", ref.data_ptr(), dy.data_ptr(), dx.data_ptr(), dy.numel(), ctx.mode, ctx.slope, _st())
+        return dx, None, None
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout(p): counter-based mask keyed by (*seed, salt); backward replays the same mask."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, salt):
+        x = _check(x).contiguous()
+        y = torch.empty_like(x)
+        call("gcc_dropout_bf16", x.data_ptr(), y.data_ptr(), x.numel(), p, seed.data_ptr(), salt, _st())
+        ctx.p, ctx.salt = p, salt
+        ctx.save_for_backward(seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (seed,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        call("gcc_dropout_bf16", dy.data_ptr(), dx.data_ptr(), dy.numel(), ctx.p, seed.data_ptr(), ctx.salt, _st())
+        return dx, None, None, None
+
+
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _check(a).contiguous(), b.contiguous()
+        y = torch.empty_like(a)
+        call("gcc_add_bf16", a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _st())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+class CatFn(torch.autograd.Function):
+    """torch.cat([a, b], channel) on the logical channels (ca, cb)."""
+
+    @staticmethod
+    def forward(ctx, a, b, ca, cb):
+        a, b = _check(a).contiguous(), b.contiguous()
+        n, h, w, _ = a.shape
+        ct = rp8(ca + cb)
+        alloc = torch.empty if ct == ca + cb else torch.zeros
+        y = alloc(n, h, w, ct, dtype=torch.bfloat16, device=a.device)
+        st = _st()
+        call("gcc_copy_channels_bf16", a.data_ptr(), a.shape[3], 0, y.data_ptr(), ct, 0, ca, n * h * w, 0, st)
+        call("gcc_copy_channels_bf16", b.data_ptr(), b.shape[3], 0, y.data_ptr(), ct, ca, cb, n * h * w, 0, st)
+        ctx.dims = (ca, cb, a.shape[3], b.shape[3])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ca, cb, cap, cbp = ctx.dims
+        dy = dy.contiguous()
+        n, h, w, ct = dy.shape
+        st = _st()
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            if ca == cap and ca % 8 == 0:
+                da = dy[..., :ca]
+            else:
+                da = torch.zeros(n, h, w, cap, dtype=torch.bfloat16, device=dy.device)
+                call("gcc_copy_channels_bf16", dy.data_ptr(), ct, 0, da.data_ptr(), cap, 0, ca, n * h * w, 0, st)
+        if ctx.needs_input_grad[1]:
+            if cb == cbp and ca % 8 == 0 and cb % 8 == 0:
+                db = dy[..., ca:ca + cb]
+            else:
+                db = torch.zeros(n, h, w, cbp, dtype=torch.bfloat16, device=dy.device)
+                call("gcc_copy_channels_bf16", dy.data_ptr(), ct, ca, db.data_ptr(), cbp, 0, cb, n * h * w, 0, st)
+        return da, db, None, None
+
+
+class ReflectPadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        x = _check(x).contiguous()
+        n, h, w, cp = x.shape
+        y = torch.empty(n, h + 2 * pad, w + 2 * pad, cp, dtype=torch.bfloat16, device=x.device)
+        call("gcc_reflect_pad_bf16", x.data_ptr(), y.data_ptr(), n, h, w, cp, pad, 0, _st())
+        ctx.pad, ctx.shape = pad, (n, h, w, cp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, h, w, cp = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty(n, h, w, cp, dtype=torch.bfloat16, device=dy.device)
+        call("gcc_reflect_pad_bf16", dy.data_ptr(), dx.data_ptr(), n, h, w, cp, ctx.pad, 1, _st())
+        return dx, None
+
+
+class DwConvFn(torch.autograd.Function):
+    """Depthwise 3x3 conv with fused ReflectionPad2d(1) (SeparableConv2d's first conv)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer):
+        x = _check(x).contiguous()
+        n, h, w, cp = x.shape
+        y = torch.empty_like(x)
+        call("gcc_dw3x3_fwd_bf16", x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
+             y.data_ptr(), n, h, w, cp, layer.c, _st())
+        ctx.layer = layer
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, h, w, cp = x.shape
+        dx = dxp = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            dxp = torch.empty(n, h + 2, w + 2, cp, dtype=torch.bfloat16, device=x.device)
+        gw = layer.arena.flat_grad[layer.wname].data_ptr() if ctx.needs_input_grad[1] else None
+        gb = layer.arena.flat_grad[layer.bname].data_ptr() if (layer.bname and ctx.needs_input_grad[2]) else None
+        call("gcc_dw3x3_bwd_bf16", x.data_ptr(), dy.data_ptr(), weight.data_ptr(),
+             None if dxp is None else dxp.data_ptr(), None if dx is None else dx.data_ptr(), gw, gb, n, h, w, cp,
+             layer.c, 1, _st())
+        return dx, None, None, None
+
+
+# ------------------------------------------------------------------------------------- losses
+GAN_MODES = {"hinge": 0, "lsgan": 1, "vanilla": 2, "wgangp": 3}
+
+
+class GanLossFn(torch.autograd.Function):
+    """GANLoss.__call__ (models/GANLoss.py:38-59) on an NHWC bf16 prediction with c logical channels."""
+
+    @staticmethod
+    def forward(ctx, pred, c, mode, kind):
+        pred = _check(pred).contiguous()
+        out = torch.zeros((), dtype=torch.float32, device=pred.device)
+        npix = pred.numel() // pred.shape[-1]
+        call("gcc_gan_loss_fwd_bf16", pred.data_ptr(), npix, pred.shape[-1], c, mode, kind, out.data_ptr(), _st())
+        ctx.args = (npix, c, mode, kind)
+        ctx.save_for_backward(pred)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (pred,) = ctx.saved_tensors
+        npix, c, mode, kind = ctx.args
+        gout = gout.contiguous().float()
+        dp = torch.empty_like(pred)
+        call("gcc_gan_loss_bwd_bf16", pred.data_ptr(), npix, pred.shape[-1], c, mode, kind, gout.data_ptr(),
+             dp.data_ptr(), _st())
+        return dp, None, None, None
+
+
+class DiffLossFn(torch.autograd.Function):
+    """mode 0: mean |a - b| (nn.L1Loss);  mode 1: sqrt(mean (a - b)^2) (sqrt(nn.MSELoss)).  b is constant."""
+
+    @staticmethod
+    def forward(ctx, a, b, c, mode):
+        a, b = _check(a).contiguous(), b.contiguous()
+        npix = a.numel() // a.shape[-1]
+        acc = torch.zeros((), dtype=torch.float32, device=a.device)
+        st = _st()
+        call("gcc_diff_reduce_bf16", a.data_ptr(), b.data_ptr(), npix, a.shape[-1], c, mode, acc.data_ptr(), st)
+        if mode == 1:
+            out = torch.empty_like(acc)
+            call("gcc_scalar_sqrt", acc.data_ptr(), out.data_ptr(), st)
+        else:
+            out = acc
+        ctx.args = (npix, c, mode)
+        ctx.save_for_backward(a, b, acc)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b, acc = ctx.saved_tensors
+        npix, c, mode = ctx.args
+        gout = gout.contiguous().float()
+        da = torch.empty_like(a)
+        call("gcc_diff_bwd_bf16", a.data_ptr(), b.data_ptr(), npix, a.shape[-1], c, mode, gout.data_ptr(),
+             acc.data_ptr(), da.data_ptr(), _st())
+        return da, None, None, None
+
+
+def gram_matrix(f, c):
+    """Per-sample f f^T / (c h w) as fp32 [N, c, c] (models/Pix2Pix.py:733-740) on the tensor cores."""
+    f = _check(f).contiguous()
+    n, h, w, cp = f.shape
+    g = torch.empty(n, c, 1, c, dtype=torch.float32, device=f.device)
+    call("gcc_wgrad_gemm_bf16", f.data_ptr(), n, h, w, cp, f.data_ptr(), h, w, cp, g.data_ptr(), c, c, 1, 1, 1, 0, 1, 0,
+         1.0 / (c * h * w), _st())
+    return g.view(n, c, c)
+
+
+class GramRmseFn(torch.autograd.Function):
+    """sqrt(MSE(gram(f), gram_target)) (models/Pix2Pix.py:542); gram_target is a constant fp32 [N,c,c]."""
+
+    @staticmethod
+    def forward(ctx, f, gt, c):
+        f = _check(f).contiguous()
+        gs = gram_matrix(f, c)
+        acc = torch.zeros((), dtype=torch.float32, device=f.device)
+        out = torch.empty_like(acc)
+        st = _st()
+        call("gcc_sqdiff_reduce_f32", gs.data_ptr(), gt.data_ptr(), gs.numel(), acc.data_ptr(), st)
+        call("gcc_scalar_sqrt", acc.data_ptr(), out.data_ptr(), st)
+        ctx.c = c
+        ctx.save_for_backward(f, gs, gt, acc)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        f, gs, gt, acc = ctx.saved_tensors
+        c = ctx.c
+        n, h, w, cp = f.shape
+        st = _st()
+        gout = gout.contiguous().float()
+        m = torch.empty(n, c, cp, dtype=torch.bfloat16, device=f.device)
+        call("gcc_gram_bwd_matrix", gs.data_ptr(), gt.data_ptr(), n, c, cp, 1.0 / (c * h * w), gout.data_ptr(),
+             acc.data_ptr(), m.data_ptr(), st)
+        df = torch.empty_like(f)
+        call("gcc_conv_gemm_bf16", f.data_ptr(), n, h, w, cp, m.data_ptr(), c, 1, cp, None, df.data_ptr(), h, w, cp, 0,
+             0, 1, 1, 1, 0, 0, 0.0, 1, st)
+        return df, None, None
+
+
+# ------------------------------------------------------------------------------- boundary helpers
+def to_nhwc(x_nchw, out=None, c_off=0, cp=None):
+    """NCHW fp32 (device) -> NHWC bf16 channel window; returns the NHWC tensor."""
+    x_nchw = _check(x_nchw).contiguous().float()
+    n, c, h, w = x_nchw.shape
+    if out is None:
+        cp = cp or rp8(c)
+        out = torch.empty(n, h, w, cp, dtype=torch.bfloat16, device=x_nchw.device)
+        zero_to = cp
+    else:
+        cp = out.shape[3]
+        zero_to = c_off + c
+    call("gcc_nchw_f32_to_nhwc_bf16", x_nchw.data_ptr(), out.data_ptr(), n, c, h * w, cp, c_off, zero_to, _st())
+    return out
+
+
+def to_nchw(x_nhwc, c, c_off=0):
+    """NHWC bf16 -> NCHW fp32 (the reference's tensor convention at the model boundary)."""
+    x_nhwc = _check(x_nhwc).contiguous()
+    n, h, w, cp = x_nhwc.shape
+    out = torch.empty(n, c, h, w, dtype=torch.float32, device=x_nhwc.device)
+    call("gcc_nhwc_bf16_to_nchw_f32", x_nhwc.data_ptr(), out.data_ptr(), n, c, h * w, cp, c_off, 0, _st())
+    return out

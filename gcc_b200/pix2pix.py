@@ -1,0 +1,471 @@
+"""Pix2PixModel: the reference's model wrapper surface (/root/reference/models/Pix2Pix.py:350-952)
+driving the B200 kernels.  Method names, argument meaning, attribute names (``netG``, ``netD``,
+``teacher_model``, ``fake_B`` ...) and error behaviour follow the reference so that its ``train.py`` /
+``test.py`` loops drive this class unchanged:
+
+    model.set_input(data); model.optimize_parameters()
+    model.set_input(val);  model.clipping_mask_alpha(); model.optimizer_netD_arch()
+
+Differences that are deliberate: activations live on the device as NHWC bf16, the
+three Adam optimizers are fused flat-arena steps, and when ``torch.distributed`` is initialised the
+gradient arenas are all-reduced over NCCL before every optimizer step (data parallel).
+"""
+import copy
+import os
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .arena import ParamArena, rp8
+from .nets import (ConvLayer, MaskNLayerDiscriminator, MobileResnetGenerator, NLayerDiscriminator, UnetGenertor,
+                   unet_level_prefixes)
+from .ops import GAN_MODES
+
+
+class _ArenaOptimizer:
+    """torch.optim-like facade over a ParamArena (zero_grad / step / param_groups[0]['lr'])."""
+
+    def __init__(self, arena, lr, betas):
+        self.arena = arena
+        arena.lr, arena.betas = lr, betas
+        if arena.finalized:
+            arena._write_hyper()
+        self.param_groups = [{"lr": lr, "initial_lr": lr, "betas": betas}]
+
+    def zero_grad(self):
+        self.arena.zero_grad()
+
+    def step(self):
+        self.arena.set_lr(self.param_groups[0]["lr"])
+        _allreduce_grads(self.arena)
+        self.arena.step()
+
+
+def _dist_on():
+    return torch.distributed.is_available() and torch.distributed.is_initialized() and \
+        torch.distributed.get_world_size() > 1
+
+
+def _allreduce_grads(arena):
+    """Data parallel: average the flat gradient arena over ranks (NCCL over NVLink) before the step."""
+    if _dist_on():
+        torch.distributed.all_reduce(arena.G, op=torch.distributed.ReduceOp.SUM)
+        arena.G.mul_(1.0 / torch.distributed.get_world_size())
+
+
+class _LambdaLR:
+    def __init__(self, optimizer, fn):
+        self.optimizer, self.fn, self.epoch = optimizer, fn, 0
+        self.base = optimizer.param_groups[0]["lr"]
+
+    def step(self):
+        self.epoch += 1
+        self.optimizer.param_groups[0]["lr"] = self.base * self.fn(self.epoch)
+
+
+def get_scheduler(optimizer, opt):
+    """utils/util.py:288-303 (linear / step / cosine; plateau needs a metric and is not driven by the step)."""
+    import math
+    if opt.lr_policy == "linear":
+        return _LambdaLR(optimizer, lambda e: 1.0 - max(0, e + opt.epoch_count - opt.n_epochs) /
+                         float(opt.n_epochs_decay + 1))
+    if opt.lr_policy == "step":
+        return _LambdaLR(optimizer, lambda e: 0.1 ** (e // opt.lr_decay_iters))
+    if opt.lr_policy == "cosine":
+        return _LambdaLR(optimizer, lambda e: (1 + math.cos(math.pi * e / opt.n_epochs)) / 2)
+    raise NotImplementedError("learning rate policy [%s] is not implemented" % opt.lr_policy)
+
+
+class Pix2PixModel(nn.Module):
+
+    def __init__(self, opt, filter_cfgs=None, channel_cfgs=None):
+        super().__init__()
+        self.opt = opt
+        if len(opt.gpu_ids) == 0:
+            raise RuntimeError("gcc_b200.Pix2PixModel needs a CUDA device (gpu_ids): there is no CPU path")
+        self.device = torch.device("cuda:%d" % opt.gpu_ids[0])
+        ops.call("gcc_check_device")
+        self.filter_cfgs, self.channel_cfgs = filter_cfgs, channel_cfgs
+        self.loss_names = ["G_GAN", "G_L1", "D_real", "D_fake"]
+        self.visual_names = ["real_A", "fake_B", "real_B"]
+        self.current_D_arch_diff_loss = 0.0
+        self.teacher_model = None
+        dev = self.device
+        self.distill = bool(opt.online_distillation or getattr(opt, "normal_distillation", False))
+
+        # ---- generator + optimizer_G arena (transform convs first, as in Pix2Pix.py:403-415)
+        self.arena_G = ParamArena(dev)
+        self.transform_convs = []
+        if opt.backbone == "resnet":
+            self.generator_extract_layers = ["model.9", "model.12", "model.15", "model.18"]
+        else:
+            self.generator_extract_layers = ["model.model.1.model.2", "model.model.1.model.3.model.3.model.2",
+                                             "model.model.1.model.3.model.3.model.4", "model.model.1.model.4"]
+        self.discriminator_extract_layers = ["model.4", "model.12"] if opt.darts_discriminator else \
+            ["model.3", "model.9"]
+        if self.distill:
+            if opt.backbone == "resnet":
+                t_ch = [opt.teacher_ngf * 4] * 4
+                s_ch = [opt.ngf * 4] * 4 if filter_cfgs is None else [filter_cfgs[2]] * 4
+            else:
+                t_ch = [opt.teacher_ngf * 2, opt.teacher_ngf * 8, opt.teacher_ngf * 16, opt.teacher_ngf * 4]
+                s_ch = [opt.ngf * 2, opt.ngf * 8, opt.ngf * 16, opt.ngf * 4] if channel_cfgs is None else \
+                    [channel_cfgs[1], channel_cfgs[3], channel_cfgs[-4], channel_cfgs[-2]]
+            for i in range(4):
+                self.transform_convs.append(ConvLayer(self.arena_G, "transform.%d" % i, "conv", s_ch[i], t_ch[i], 1, 1, 0))
+        if opt.backbone == "resnet":
+            self.netG = MobileResnetGenerator(3, 3, ngf=opt.ngf, cfg=filter_cfgs, arena=self.arena_G, device=dev, opt=opt)
+        else:
+            self.netG = UnetGenertor(3, 3, opt.num_downs, ngf=opt.ngf, use_dropout=not opt.no_dropout,
+                                     filter_cfgs=filter_cfgs, channel_cfgs=channel_cfgs, arena=self.arena_G, device=dev)
+        self.arena_G.finalize()
+        self.netG.finalize()
+        for t in self.transform_convs:
+            t.bind()
+        self.optimizer_G = _ArenaOptimizer(self.arena_G, opt.lr, (0.5, 0.999))
+
+        # ---- discriminator (+ gate arena)
+        self.arena_D = ParamArena(dev)
+        if opt.darts_discriminator:
+            self.loss_names += ["D_arch_diff", "D_arch", "teacher_D_arch_diff"]
+            self.arena_A = ParamArena(dev)
+            self.netD = MaskNLayerDiscriminator(input_nc=6, ndf=opt.ndf, threshold=opt.threshold, arena=self.arena_D,
+                                                gate_arena=self.arena_A, device=dev)
+            self.arena_D.finalize()
+            self.arena_A.finalize()
+            self.netD.finalize()
+            self.optimizer_D = _ArenaOptimizer(self.arena_D, opt.lr, (0.5, 0.999))
+            self.optimizer_arch = _ArenaOptimizer(self.arena_A, opt.arch_lr, (0.9, 0.999))
+        else:
+            self.arena_A = None
+            self.netD = NLayerDiscriminator(input_nc=6, ndf=opt.ndf, arena=self.arena_D, device=dev)
+            self.arena_D.finalize()
+            self.netD.finalize()
+            self.optimizer_D = _ArenaOptimizer(self.arena_D, opt.lr, (0.5, 0.999))
+        self.init_net()
+
+        self.gan_mode = GAN_MODES.get(opt.gan_mode)
+        if self.gan_mode is None:
+            raise NotImplementedError("gan mode %s not implemented" % opt.gan_mode)
+        self.optimizers = [self.optimizer_G, self.optimizer_D]
+        self.schedulers = [get_scheduler(o, opt) for o in self.optimizers]
+        if opt.darts_discriminator and getattr(opt, "arch_lr_step", False):
+            arch_opt = copy.deepcopy(opt)
+            arch_opt.lr_policy = "step"
+            arch_opt.lr_decay_iters = opt.n_epochs - 1
+            self.arch_scheduler = get_scheduler(self.optimizer_arch, arch_opt)
+            self.schedulers.append(self.arch_scheduler)
+        self.total_generator_features = {}
+        self.total_discriminator_features = {}
+
+    # ------------------------------------------------------------------ init (util.init_weights)
+    def init_net(self):
+        """N(0, .02) conv weights, zero conv biases, BN gamma N(1, .02), BN beta N(0, 1)
+        (utils/util.py:261-286); transform convs keep nn.Conv2d's default kaiming-uniform; alpha = 1."""
+        import math
+        with torch.no_grad():
+            for arena in (self.arena_G, self.arena_D):
+                for (name, shape, kind) in arena.specs:
+                    p = arena.params[name]
+                    if name.startswith("transform."):
+                        bound = 1.0 / math.sqrt(shape[1])
+                        p.copy_(torch.empty(shape, device=self.device).uniform_(-bound, bound))
+                    elif len(shape) == 4:
+                        p.copy_(torch.empty(shape, device=self.device).normal_(0.0, 0.02))
+                    elif name.endswith(".weight"):
+                        p.copy_(torch.empty(shape, device=self.device).normal_(1.0, 0.02))
+                    elif name.endswith(".bias"):
+                        is_bn = (name[:-4] + "weight") in arena.params and len(arena.params[name[:-4] + "weight"].shape) == 1
+                        if is_bn:
+                            p.copy_(torch.empty(shape, device=self.device).normal_(0.0, 1.0))
+                        else:
+                            p.zero_()
+                arena.mark_dirty()
+
+    def sync_weights(self):
+        """Call after mutating parameters from outside (tests, checkpoint surgery)."""
+        for a in (self.arena_G, self.arena_D, self.arena_A):
+            if a is not None:
+                a.mark_dirty()
+
+    # ------------------------------------------------------------------ inputs / forward
+    def set_input(self, input):
+        self.input = input
+        AtoB = self.opt.direction == "AtoB"
+        A = input["A" if AtoB else "B"].to(self.device, non_blocking=True)
+        B = input["B" if AtoB else "A"].to(self.device, non_blocking=True)
+        self.image_paths = [input.get("A_paths" if AtoB else "B_paths"), input.get("B_paths" if AtoB else "A_paths")]
+        self._A_nchw, self._B_nchw = A, B
+        self.real_A_nhwc = ops.to_nhwc(A)
+        self.real_B_nhwc = ops.to_nhwc(B)
+        n, h, w, _ = self.real_A_nhwc.shape
+        real_AB = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=self.device)
+        ops.to_nhwc(A, out=real_AB, c_off=0)
+        ops.to_nhwc(B, out=real_AB, c_off=3)
+        real_AB[..., 6:].zero_()
+        self.real_AB = real_AB
+
+    @property
+    def real_A(self):
+        return self._A_nchw
+
+    @property
+    def real_B(self):
+        return self._B_nchw
+
+    @property
+    def fake_B(self):
+        """NCHW fp32 view of the generator output (the reference's tensor convention)."""
+        return ops.to_nchw(self.fake_B_nhwc.detach(), 3)
+
+    def forward(self):
+        self.fake_B_nhwc = self.netG(self.real_A_nhwc)
+        self.g_taps = list(self.netG.taps)
+
+    def _D(self, net, ab):
+        pred = net(ab)
+        return pred, list(net.taps)
+
+    def _fake_AB(self, fake, detach):
+        f = fake.detach() if detach else fake
+        return ops.CatFn.apply(self.real_A_nhwc, f, 3, 3)
+
+    def _gan(self, pred, kind):
+        return ops.GanLossFn.apply(pred, 1, self.gan_mode, kind)
+
+    # ------------------------------------------------------------------ losses / steps
+    def backward_D(self):
+        pred_fake, _ = self._D(self.netD, self._fake_AB(self.fake_B_nhwc, True))
+        self.loss_D_fake = self._gan(pred_fake, 1)
+        pred_real, self.d_taps = self._D(self.netD, self.real_AB)
+        self.loss_D_real = self._gan(pred_real, 0)
+        self.loss_D = (self.loss_D_fake + self.loss_D_real) * 0.5
+        self.loss_D.backward()
+
+    def get_D_arch_diff(self, isTeacher=False):
+        if isTeacher:
+            self.set_requires_grad(self.netD, False)
+        pred_fake, _ = self._D(self.netD, self._fake_AB(self.fake_B_nhwc, True))
+        self.loss_D_arch_fake = self._gan(pred_fake, 1)
+        self.loss_D_arch_fake_real = self._gan(pred_fake, 2)
+        pred_real, _ = self._D(self.netD, self.real_AB)
+        self.loss_D_arch_real = self._gan(pred_real, 0)
+        diff = (self.loss_D_arch_fake_real - self.loss_D_arch_fake).abs()
+        if isTeacher and not (isinstance(self.current_D_arch_diff_loss, float) and self.current_D_arch_diff_loss == 0.0):
+            b = self.opt.ema_beta
+            self.current_D_arch_diff_loss = b * diff + (1.0 - b) * self.current_D_arch_diff_loss
+        else:
+            self.current_D_arch_diff_loss = diff
+        return self.current_D_arch_diff_loss, torch.sign(self.loss_D_arch_fake_real - self.loss_D_arch_fake)
+
+    def backward_D_arch(self):
+        self.loss_teacher_D_arch_diff, _ = self.teacher_model.get_D_arch_diff(isTeacher=True)
+        self.loss_D_arch_diff, _ = self.get_D_arch_diff(isTeacher=False)
+        self.loss_D_arch = (self.loss_D_arch_diff - self.loss_teacher_D_arch_diff.detach()).abs()
+        self.loss_D_arch = self.loss_D_arch + (self.loss_D_arch_real + self.loss_D_arch_fake) * 0.5
+        self.loss_D_arch.backward()
+
+    def backward_G(self):
+        o = self.opt
+        pred_fake, self.d_taps = self._D(self.netD, self._fake_AB(self.fake_B_nhwc, False))
+        self.loss_G_GAN = self._gan(pred_fake, 2)
+        self.loss_G_L1 = ops.DiffLossFn.apply(self.fake_B_nhwc, self.real_B_nhwc, 3, 0) * o.lambda_L1
+        self.loss_G = self.loss_G_GAN + self.loss_G_L1
+        if self.distill:
+            T = self.teacher_model
+            self.Tfake_B_nhwc = T.fake_B_nhwc
+            feats = list(self.g_taps)
+            _, t_d_taps = self._D(T.netD, self._fake_AB(self.fake_B_nhwc, False))  # teacher D on the student fake
+            feats += t_d_taps
+            self.loss_content = 0.0
+            self.loss_gram = 0.0
+            for i, (f, c) in enumerate(feats):
+                if i < 4:
+                    f = self.transform_convs[i](f)
+                    c = self.transform_convs[i].cout
+                tgt, gram_t = self.target_distillation_features[i], self.target_grams[i]
+                self.loss_gram = self.loss_gram + ops.GramRmseFn.apply(f, gram_t, c)
+                self.loss_content = self.loss_content + ops.DiffLossFn.apply(f, tgt, c, 1)
+            self.loss_gram = o.lambda_gram * self.loss_gram
+            self.loss_content = o.lambda_content * self.loss_content
+            self.loss_G = self.loss_G + self.loss_gram + self.loss_content
+        self.loss_G.backward()
+        self.L1_sparsity()
+
+    def L1_sparsity(self):
+        o = self.opt
+        st = ops._st()
+        if o.lambda_weight > 0.0:
+            for (name, shape, kind) in self.arena_G.specs:
+                if len(shape) == 4 and not name.startswith("transform."):
+                    off, n = self.arena_G.offsets[[s[0] for s in self.arena_G.specs].index(name)]
+                    ops.call("gcc_l1_sparsity_f32", self.arena_G.P[off:].data_ptr(), self.arena_G.G[off:].data_ptr(), n,
+                             o.lambda_weight, st)
+        elif o.lambda_scale > 0.0:
+            names = [s[0] for s in self.arena_G.specs]
+            for (name, shape, kind) in self.arena_G.specs:
+                if len(shape) == 1 and name.endswith(".weight"):
+                    off, n = self.arena_G.offsets[names.index(name)]
+                    ops.call("gcc_l1_sparsity_f32", self.arena_G.P[off:].data_ptr(), self.arena_G.G[off:].data_ptr(), n,
+                             o.lambda_scale, st)
+
+    def optimize_parameters(self):
+        if self.opt.online_distillation:
+            T = self.teacher_model
+            T.set_input(self.input)
+            T.optimize_parameters()
+            feats = [f.detach() for f, _ in (T.g_taps + T.d_taps)]
+            chans = [c for _, c in (T.g_taps + T.d_taps)]
+            self.target_distillation_features = feats
+            self.target_grams = [ops.gram_matrix(f, c) for f, c in zip(feats, chans)]
+        self.forward()
+        self.set_requires_grad(self.netD, True)
+        self.set_netD_arch_grad(False)
+        self.optimizer_D.zero_grad()
+        self.backward_D()
+        self.optimizer_D.step()
+        self.set_requires_grad(self.netD, False)
+        self.optimizer_G.zero_grad()
+        self.backward_G()
+        self.optimizer_G.step()
+
+    def optimizer_netD_arch(self):
+        self.forward()
+        self.teacher_model.set_input(self.input)
+        self.teacher_model.forward()
+        self.set_requires_grad(self.netD, True)
+        self.set_netD_weight_grad(False)
+        self.optimizer_arch.zero_grad()
+        self.backward_D_arch()
+        self.optimizer_arch.step()
+
+    # ------------------------------------------------------------------ bookkeeping (reference surface)
+    def print_sparse_info(self, logger):
+        for i, mask in enumerate(self.netD.get_current_masks() if self.opt.darts_discriminator else []):
+            logger.info("netD gate %d sparsity ratio: %.2f" % (i, float((mask == 0.0).sum()) / mask.numel()))
+
+    def adaptive_ema_beta(self, epoch):
+        self.opt.ema_beta = 1.0 - epoch / (self.opt.n_epochs + self.opt.n_epochs_decay)
+
+    def update_learning_rate(self, epoch):
+        for s in self.schedulers:
+            s.step()
+        self.adaptive_ema_beta(epoch)
+        lr = self.optimizers[0].param_groups[0]["lr"]
+        print("learning rate = %.7f\tema beta = %.7f" % (lr, self.opt.ema_beta))
+
+    def set_requires_grad(self, nets, requires_grad=False):
+        if not isinstance(nets, list):
+            nets = [nets]
+        for net in nets:
+            if net is not None:
+                for p in net.parameters():
+                    p.requires_grad = requires_grad
+
+    def set_netD_weight_grad(self, requires_grad=False):
+        for p in self.arena_D.params.values():
+            p.requires_grad = requires_grad
+
+    def set_netD_arch_grad(self, requires_grad=False):
+        if self.arena_A is not None:
+            for p in self.arena_A.params.values():
+                p.requires_grad = requires_grad
+
+    def clipping_mask_alpha(self):
+        if self.arena_A is not None:
+            ops.call("gcc_clamp_f32", self.arena_A.P.data_ptr(), self.arena_A.numel, 0.0, 1.0, ops._st())
+
+    def model_train(self):
+        self.netG.train()
+        self.netD.train()
+
+    def model_eval(self):
+        self.netG.eval()
+        self.netD.eval()
+
+    def get_current_visuals(self):
+        ret = OrderedDict()
+        for name in self.visual_names:
+            if name == "Tfake_B":
+                ret[name] = ops.to_nchw(self.Tfake_B_nhwc.detach(), 3)
+            else:
+                ret[name] = getattr(self, name)
+        return ret
+
+    def get_current_losses(self):
+        ret = OrderedDict()
+        for name in self.loss_names:
+            ret[name] = float(getattr(self, "loss_" + name))  # AttributeError before the first arch step, as upstream
+        return ret
+
+    def init_distillation(self):
+        if self.distill:
+            if self.opt.lambda_content > 0.0:
+                self.loss_names.append("content")
+            if self.opt.lambda_gram > 0.0:
+                self.loss_names.append("gram")
+            self.visual_names.append("Tfake_B")
+
+    def get_distillation_features(self):
+        """NCHW fp32 copies of the taps, in the reference's order (generator taps then discriminator taps)."""
+        return [ops.to_nchw(f.detach(), c) for f, c in (self.g_taps + getattr(self, "d_taps", []))]
+
+    def gram(self, x):
+        b, c, h, w = x.shape
+        return ops.gram_matrix(ops.to_nhwc(x), c)
+
+    def get_cfg(self):
+        return self.filter_cfgs, self.channel_cfgs
+
+    def save_models(self, epoch, save_dir, fid=None, isbest=False, direction="AtoB"):
+        os.makedirs(save_dir, exist_ok=True)
+        ckpt = {"G": self.netG.state_dict(), "D": self.netD.state_dict(), "epoch": epoch,
+                "cfg": (self.filter_cfgs, self.channel_cfgs), "fid": fid}
+        path = os.path.join(save_dir, "model_best_%s.pth" % direction if isbest else "model_%d.pth" % epoch)
+        torch.save(ckpt, path)
+
+    def load_models(self, load_path, load_discriminator=True):
+        ckpt = torch.load(load_path, map_location=self.device)
+        self.netG.load_state_dict(ckpt["G"])
+        if load_discriminator:
+            self.netD.load_state_dict(ckpt["D"])
+        print("loading the model from %s" % load_path)
+        return ckpt["fid"], float("inf")
+
+    # ------------------------------------------------------------------ pruning (index selection)
+    def prune(self, threshold, lottery_path=None):
+        from . import prune as P
+        if self.opt.backbone == "resnet":
+            cfgs = (P.resnet_prune_cfg(self.netG.state_dict(), threshold), None)
+        elif self.opt.scale_prune:
+            cfgs = P.unet_scale_prune_cfg(self.netG.state_dict(), self.opt.ngf, threshold)
+        elif self.opt.norm_prune:
+            cfgs = P.unet_norm_prune_cfg(self.netG.state_dict(), self.opt.ngf, threshold)
+        else:
+            raise NotImplementedError("only scale and norm pruning are supported!!!")
+        return Pix2PixModel(self.opt, filter_cfgs=cfgs[0], channel_cfgs=cfgs[1])
+
+    def max_min_bn_scale(self):
+        from . import prune as P
+        return P.unet_max_min_bn_scale(self.netG.state_dict())
+
+    def max_min_conv_norm(self):
+        from . import prune as P
+        return P.max_min_conv_norm(self.netG.state_dict(), self.opt.backbone)
+
+
+def build_teacher(model, opt):
+    """train.py:92-105: teacher = same class, teacher widths, plain D, no distillation."""
+    topt = copy.deepcopy(opt)
+    topt.ngf, topt.ndf = opt.teacher_ngf, opt.teacher_ndf
+    topt.darts_discriminator = False
+    topt.online_distillation = False
+    topt.generator_only = False
+    teacher = Pix2PixModel(topt)
+    teacher.model_train()
+    setattr(model, "teacher_model", teacher)
+    model.init_distillation()
+    teacher.init_distillation()
+    return teacher

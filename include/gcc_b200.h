@@ -29,10 +29,11 @@ int gcc_check_device(void); /* non-zero unless the current device is sm_100 */
  *   (also used for the data gradients of both, with the transposed weight pack)
  *   x: [N,H,W,Cx] bf16, w: [R][T=KH*KW][Cw] bf16, y: [N,OH,OW,Cy] bf16, bias: [R] fp32 or NULL.
  *   act: 0 none, 1 leaky-relu(slope), 2 tanh.  stride in {1,2}.
+ *   w_per_image=1 (1x1 only): w is [N][R][Cw], one matrix per image (Gram-loss backward dF = F M).
  */
 int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                        const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
-                       int KW, int stride, int pad, int act, float slope, void* stream);
+                       int KW, int stride, int pad, int act, float slope, int w_per_image, void* stream);
 /* gcc_wgrad_gemm_bf16: dw[b][r][kh*KW+kw][c] (+)= scale * sum_{n,oy,ox} p[n,oy,ox,r] * q[n,stride*oy+kh-pad,stride*ox+kw-pad,c]
  *   weight gradient of Conv2d (p = dy, q = x) and ConvTranspose2d (p = x, q = dy); with batched=1,
  *   KH=KW=1, p == q it is the per-sample Gram matrix f f^T (models/Pix2Pix.py:733-740).
@@ -43,11 +44,96 @@ int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void
 /* CUDA-core cross-checks with identical signatures (tests only). */
 int gcc_conv_direct_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                          const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
-                         int KW, int stride, int pad, int act, float slope, void* stream);
+                         int KW, int stride, int pad, int act, float slope, int w_per_image, void* stream);
 int gcc_wgrad_direct_bf16(const void* p, int N, int OH, int OW, int Cp, const void* q, int H, int W, int Cq,
                           float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched, int accumulate,
                           float scale, void* stream);
 void gcc_debug_force_block_n(int bn);
+
+/* ---- norm / gate / activation blocks (norm.cu) ----
+ * One block = [BatchNorm2d | InstanceNorm2d | identity] -> [DifferentiableOP gate] -> [(Leaky)ReLU]
+ * (models/Pix2Pix.py:26-35,201,272-341; models/DifferentiableOp.py:22-59).
+ *   z = gamma*(x-mean)*rstd + beta ; g = mask(alpha,thr)*z ; y = act(g) ; optional y2 = act2(g) written
+ *   into channels [y2_coff, y2_coff+Cp) of a wider NHWC buffer (U-Net skip concat, Pix2Pix.py:77).
+ *   act/act2: 0 none, 1 leaky-relu(slope), 2 relu.  per_sample=1 -> instance norm statistics.
+ *   sums: fp32 [N if per_sample else 1][2][Cp] (sum x, sum x^2); NULL sums = identity (no norm).
+ *   alpha NULL = no gate.  gamma/beta NULL = 1/0.  mask = (sign(alpha-thr)+1)/2 evaluated in fp32.
+ *   gate_after=1 (identity norm only): y = mask*act(z), the conv -> LeakyReLU -> gate order of the first
+ *   MaskNLayerDiscriminator layer (Pix2Pix.py:320-322), whose gate gradient is sum dy*act(z). */
+int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, int per_sample, float* sums, void* stream);
+int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, int Cp, int C, int per_sample, const float* sums,
+                        const float* gamma, const float* beta, const float* alpha, float thr, float eps,
+                        float* running_mean, float* running_var, float momentum, int act, float slope,
+                        int gate_after, void* y2, int y2_Cp, int y2_coff, int act2, void* stream);
+int gcc_norm_apply_eval_bf16(const void* x, void* y, int N, long long HW, int Cp, int C, const float* running_mean,
+                             const float* running_var, const float* gamma, const float* beta, const float* alpha,
+                             float thr, float eps, int act, float slope, void* y2, int y2_Cp, int y2_coff, int act2,
+                             void* stream);
+/* backward of the block: dx (bf16, may be NULL), dgamma/dbeta/dalpha (fp32 [C], may be NULL; dalpha is
+ * the straight-through gate gradient sum dg*z; parameter gradients ACCUMULATE into their buffers).
+ * dy / dy2 are gradient windows of y / y2. */
+int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int C, int per_sample, const float* sums,
+                      const float* gamma, const float* beta, const float* alpha, float thr, float eps, int act,
+                      float slope, int gate_after, const void* dy, int dy_Cp, int dy_coff, const void* dy2, int dy2_Cp,
+                      int dy2_coff, int act2, float* red, void* dx, float* dgamma, float* dbeta, float* dalpha,
+                      void* stream);
+
+/* ---- elementwise / layout (elementwise.cu) ---- */
+/* set_input boundary (models/Pix2Pix.py:453-458): NCHW fp32 <-> NHWC bf16 channel windows */
+int gcc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, long long HW, int Cp, int c_off,
+                              int zero_to, void* stream);
+int gcc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, long long HW, int Cp, int c_off,
+                              int accumulate, void* stream);
+/* torch.cat / its gradient split (models/Pix2Pix.py:77,467,471,516) */
+int gcc_copy_channels_bf16(const void* src, int Cs, int s_off, void* dst, int Cd, int d_off, int C, long long npix,
+                           int accumulate, void* stream);
+/* mode 1 leaky-relu, 2 relu, 3 tanh; bwd takes the forward input (1,2) or output (3) as ref */
+int gcc_act_fwd_bf16(const void* x, void* y, long long n, int mode, float slope, void* stream);
+int gcc_act_bwd_bf16(const void* ref, const void* dy, void* dx, long long n, int mode, float slope, void* stream);
+/* nn.Dropout(p) (models/Pix2Pix.py:64): counter-based mask from (*seed_dev, salt, index); apply to dy for bwd */
+int gcc_dropout_bf16(const void* x, void* y, long long n, float p, const void* seed_dev, int salt, void* stream);
+int gcc_add_bf16(const void* a, const void* b, void* y, long long n, void* stream);
+/* fp32 [D0][T][D1] parameter -> bf16 [D0][T][D1p] and/or bf16 [D1][T][D0p] GEMM operand packs */
+int gcc_pack_weight_bf16(const float* src, void* direct, void* transposed, int D0, int T, int D1, int D1p, int D0p,
+                         void* stream);
+int gcc_bias_grad_bf16(const void* dy, long long npix, int Cp, int c_off, int C, float* out, int accumulate,
+                       void* stream);
+/* nn.ReflectionPad2d (models/Pix2Pix.py:161,215,259); backward=1: x is dy on the padded grid, y is dx */
+int gcc_reflect_pad_bf16(const void* x, void* y, int N, int H, int W, int Cp, int pad, int backward, void* stream);
+/* depthwise 3x3 with fused ReflectionPad2d(1) (SeparableConv2d, models/Pix2Pix.py:132-145) */
+int gcc_dw3x3_fwd_bf16(const void* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cp, int C,
+                       void* stream);
+int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w, void* dxp, void* dx, float* dw, float* dbias,
+                       int N, int H, int W, int Cp, int C, int accumulate, void* stream);
+
+/* ---- loss reductions (loss.cu) ---- */
+/* GANLoss (models/GANLoss.py:38-59). mode: 0 hinge, 1 lsgan, 2 vanilla, 3 wgangp.
+ * kind: 0 D-real, 1 D-fake, 2 G.  out is an fp32 device scalar that the caller zeroes. */
+int gcc_gan_loss_fwd_bf16(const void* pred, long long npix, int Cp, int C, int mode, int kind, float* out,
+                          void* stream);
+int gcc_gan_loss_bwd_bf16(const void* pred, long long npix, int Cp, int C, int mode, int kind, const float* gout,
+                          void* dpred, void* stream);
+/* mode 0: out += mean|a-b| (criterionL1, Pix2Pix.py:520); mode 1: out += mean (a-b)^2 (criterionMSE, :543) */
+int gcc_diff_reduce_bf16(const void* a, const void* b, long long npix, int Cp, int C, int mode, float* out,
+                         void* stream);
+/* mode 0: da = gout*sign(a-b)/count ; mode 1 (sqrt(MSE)): da = gout*(a-b)/(count*sqrt(*msq)) */
+int gcc_diff_bwd_bf16(const void* a, const void* b, long long npix, int Cp, int C, int mode, const float* gout,
+                      const float* msq, void* da, void* stream);
+int gcc_sqdiff_reduce_f32(const float* a, const float* b, long long n, float* out, void* stream);
+int gcc_gram_bwd_matrix(const float* gs, const float* gt, int B, int C, int Cp, float gram_scale, const float* gout,
+                        const float* msq, void* m, void* stream);
+int gcc_scalar_sqrt(const float* in, float* out, void* stream);
+
+/* ---- optimizer (optim.cu) ---- */
+/* torch.optim.Adam step over a flat fp32 arena (Pix2Pix.py:382-440). hyper_dev: device fp32[5] =
+ * {lr, beta1, beta2, eps, step(int bits)}; the step counter is incremented on the device. */
+int gcc_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float* hyper_dev, void* stream);
+/* L1_sparsity (Pix2Pix.py:554-563): g += lambda * sign(w) */
+int gcc_l1_sparsity_f32(const float* w, float* g, long long n, float lambda, void* stream);
+/* DifferentiableOP.clip_alpha (DifferentiableOp.py:51-53) */
+int gcc_clamp_f32(float* x, long long n, float lo, float hi, void* stream);
+/* re-pack all conv weights of a net after an optimizer step: device int64 table [count][8] */
+int gcc_pack_weights_table(const void* table_dev, int count, void* stream);
 
 #ifdef __cplusplus
 }

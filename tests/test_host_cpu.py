@@ -1,0 +1,111 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/gcc_b200.h declares, the host
+modules mirror the reference's state-dict layout, options and prune index selection match the oracle."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from oracle import gcc_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gcc_b200 import _build, _lib
+    path = _build.build()
+    lib = ctypes.CDLL(path)
+    protos = _lib.parse_header()
+    assert len(protos) >= 30
+    for name in protos:
+        assert hasattr(lib, name), "libgcc_b200.so lacks %s declared in include/gcc_b200.h" % name
+    lib.gcc_abi_version.restype = ctypes.c_int
+    assert lib.gcc_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a GPU instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gcc_b200 import _lib, ops
+    with pytest.raises(_lib.GccB200Error):
+        ops.ActFn.apply(torch.zeros(1, 2, 2, 8, dtype=torch.bfloat16), 1, 0.2)
+    from gcc_b200 import options
+    from gcc_b200.pix2pix import Pix2PixModel
+    opt = options.parse(["--dataroot", "x", "--gpu_ids", "-1"])
+    with pytest.raises(RuntimeError):
+        Pix2PixModel(opt)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gcc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def _check(net, shapes):
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(shapes.keys())
+    for k, s in shapes.items():
+        assert tuple(sd[k].shape) == tuple(s), k
+
+
+FC = [8, 13, 30, 61, 64, 59, 40, 64, 37, 50, 64, 48, 27, 14, 5]
+CC = [8, 13, 30, 61, 64, 59, 40, 64, 77, 109, 128, 109, 57, 27, 13]
+RC = [8, 16, 29, 21, 29, 17, 29, 30, 29, 11, 29, 25, 29, 32, 29, 9, 29, 27, 29, 19, 29, 13, 7]
+
+
+def test_state_dict_layout_matches_reference_names():
+    from gcc_b200 import nets
+    _check(nets.UnetGenertor(ngf=8, device="cpu"), O.unet_param_shapes(8))
+    _check(nets.UnetGenertor(ngf=8, filter_cfgs=FC, channel_cfgs=CC, device="cpu"), O.unet_param_shapes(8, FC, CC))
+    _check(nets.MobileResnetGenerator(ngf=8, device="cpu"), O.resnet_param_shapes(8))
+    _check(nets.MobileResnetGenerator(ngf=8, cfg=RC, device="cpu"), O.resnet_param_shapes(8, RC))
+    _check(nets.NLayerDiscriminator(6, 16, device="cpu"), O.patchgan_param_shapes(16, 6, False))
+    _check(nets.MaskNLayerDiscriminator(6, 16, device="cpu"), O.patchgan_param_shapes(16, 6, True))
+
+
+def test_state_dict_roundtrip_and_channels_last_storage():
+    from gcc_b200 import nets
+    net = nets.UnetGenertor(ngf=8, device="cpu")
+    P = O._make_params(O.unet_param_shapes(8), "S.netG.")
+    net.load_state_dict({k: v.detach() for k, v in P.items()})
+    sd = net.state_dict()
+    assert all(torch.equal(sd[k], P[k].detach()) for k in P)
+    w = net.arena.params["model.model.0.weight"]
+    assert w.shape == (8, 3, 4, 4) and w.stride() == (48, 1, 12, 3)  # [O][KH][KW][I] storage
+    assert w.grad.stride() == w.stride()
+    with pytest.raises(RuntimeError):
+        net.load_state_dict({"bogus": torch.zeros(1)})
+
+
+def test_prune_cfgs_bit_exact_vs_golden(golden_dir):
+    from gcc_b200 import prune
+    g = torch.load(os.path.join(golden_dir, "pix2pix_small_ops.pt"), weights_only=False)["prune"]
+    G = {k: v.detach() for k, v in O._make_params(O.unet_param_shapes(16), "P.netG.").items()}
+    for thr in (0.98, 1.0, 1.02):
+        assert prune.unet_scale_prune_cfg(G, 16, thr) == tuple(g["scale_prune@%g" % thr])
+    for thr in (2.0, 6.0, 10.0):
+        assert prune.unet_norm_prune_cfg(G, 16, thr) == tuple(g["norm_prune@%g" % thr])
+    mx, mn = prune.unet_max_min_bn_scale(G)
+    assert (mx, mn) == pytest.approx(g["scale_prune.maxmin"], rel=1e-6)
+    mx, mn = prune.max_min_conv_norm(G, "unet")
+    assert (mx, mn) == pytest.approx(g["norm_prune.maxmin"], rel=1e-6)
+    R = {k: v.detach() for k, v in O._make_params(O.resnet_param_shapes(16), "P.netG.").items()}
+    for thr in (0.5, 2.3, 2.6):
+        assert prune.resnet_prune_cfg(R, thr) == g["resnet_prune@%g" % thr]
+    mx, mn = prune.max_min_conv_norm(R, "resnet")
+    assert (mx, mn) == pytest.approx(g["resnet.maxmin"], rel=1e-6)
+
+
+def test_options_overrides():
+    from gcc_b200 import options
+    o = options.parse(["--dataroot", "./database/cityscapes/", "--ngf", "32", "--darts_discriminator"])
+    assert (o.lambda_L1, o.teacher_ndf, o.direction, o.load_size, o.gpu_ids) == (100.0, 128, "BtoA", 256, [0])
+    assert o.threshold == 0.5 and o.arch_lr == 1e-4 and o.gan_mode == "hinge" and o.ndf == 128
+    o = options.parse(["--dataroot", "x", "--lambda_scale", "0.01"])
+    assert (o.n_epochs, o.n_epochs_decay) == (10, 15)
+    with pytest.raises(NotImplementedError):
+        options.parse(["--dataroot", "x", "--model", "nope"])

@@ -1,0 +1,168 @@
+"""Whole-step parity on the B200: gcc_b200.Pix2PixModel (CUDA kernels through the C-ABI) against the CPU
+oracle (oracle/gcc_oracle.py, pinned to the reference by tests/golden) on identical deterministic
+parameters and inputs: one full GCC iteration = optimize_parameters() + optimizer_netD_arch().
+
+Tolerances (bf16 activations / fp32 accumulation vs the fp32 oracle; SURVEY.md 8d "tolerance guidance"):
+  activations / taps ..... relative L2 <= 3e-2
+  losses ................. |rel| <= 3e-2 (+2e-3 abs)
+  per-network gradients .. global relative L2 <= 8e-2 and cosine >= 0.995
+  gate masks ............. bit exact
+"""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _build(backbone, tiny, cfgs, no_dropout=True):
+    from gcc_b200 import options
+    from gcc_b200.pix2pix import Pix2PixModel, build_teacher
+    from oracle import gcc_oracle as O
+    argv = ["--dataroot", "x/cityscapes", "--model", "pix2pix", "--darts_discriminator", "--online_distillation",
+            "--lambda_content", "50", "--lambda_gram", "1e4", "--gpu_ids", "0", "--backbone", backbone]
+    if no_dropout:
+        argv.append("--no_dropout")
+    opt = options.parse(argv)
+    for k, v in tiny.items():
+        setattr(opt, k, v)
+    model = Pix2PixModel(opt, cfgs[0], cfgs[1])
+    teacher = build_teacher(model, opt)
+    oopt = O.Opt(backbone=backbone, direction=opt.direction, **tiny)
+    S, T = O.build_pair(oopt, cfgs[0], cfgs[1])
+    for mine, orc in ((model, S), (teacher, T)):
+        mine.netG.load_state_dict({k: v.detach() for k, v in orc.G.items()})
+        mine.netD.load_state_dict({k: v.detach() for k, v in orc.D.items()})
+        with torch.no_grad():
+            for i, w in enumerate(orc.transform):
+                mine.transform_convs[i].weight.copy_(w.detach())
+        mine.sync_weights()
+        mine.model_train()
+    return model, teacher, S, T, O
+
+
+def _arena_grads(arena):
+    return {n: arena.grads[n].detach().float().cpu() for n, _, _ in arena.specs}
+
+
+def _cmp_grads(report, tag, mine, oracle_named):
+    ga, gb = [], []
+    for name, g in oracle_named.items():
+        if g is None or name not in mine:
+            continue
+        ga.append(mine[name].flatten())
+        gb.append(g.detach().flatten())
+    a, b = torch.cat(ga), torch.cat(gb)
+    report[tag + ".grad.rel_l2"] = _rel_l2(a, b)
+    report[tag + ".grad.cos"] = _cos(a, b)
+
+
+CASES = {
+    "unet_tiny": ("unet", {"ngf": 8, "teacher_ngf": 16, "ndf": 16, "teacher_ndf": 16}, (None, None), 2),
+    "unet_pruned": ("unet", {"ngf": 8, "teacher_ngf": 16, "ndf": 16, "teacher_ndf": 16},
+                    ([8, 13, 30, 61, 64, 59, 40, 64, 37, 50, 64, 48, 27, 14, 5],
+                     [8, 13, 30, 61, 64, 59, 40, 64, 77, 109, 128, 109, 57, 27, 13]), 1),
+    "resnet_tiny": ("resnet", {"ngf": 8, "teacher_ngf": 16, "ndf": 16, "teacher_ndf": 16},
+                    ([8, 16, 29, 21, 29, 17, 29, 30, 29, 11, 29, 25, 29, 32, 29, 9, 29, 27, 29, 19, 29, 13, 7], None), 1),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_gcc_iteration_matches_oracle(name):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    backbone, tiny, cfgs, batch = CASES[name]
+    model, teacher, S, T, O = _build(backbone, tiny, cfgs)
+    A = O.det_image("%s.A.0" % name, batch, 3, 256, 256)
+    B = O.det_image("%s.B.0" % name, batch, 3, 256, 256)
+    report = {}
+
+    # ---- oracle
+    S.set_input(A, B)
+    S.optimize_parameters()
+    # ---- B200
+    model.set_input({"A": A, "B": B, "A_paths": "", "B_paths": ""})
+    model.optimize_parameters()
+    torch.cuda.synchronize()
+
+    report["fake_B"] = _rel_l2(model.fake_B.cpu(), S.fake_B.detach())
+    report["Tfake_B"] = _rel_l2(teacher.fake_B.cpu(), T.fake_B.detach())
+    from gcc_b200 import ops
+    for i, (f, c) in enumerate(model.g_taps):
+        report["student_tap.%d" % i] = _rel_l2(ops.to_nchw(f.detach(), c).cpu(), S.g_taps[i].detach())
+    for i, f in enumerate(model.target_distillation_features):
+        c = S.target_features[i].shape[1]
+        report["target_feature.%d" % i] = _rel_l2(ops.to_nchw(f, c).cpu(), S.target_features[i])
+    losses = {}
+    for n in ("G_GAN", "G_L1", "D_real", "D_fake", "content", "gram"):
+        losses["S." + n] = (float(getattr(model, "loss_" + n)), float(getattr(S, "loss_" + n)))
+    for n in ("G_GAN", "G_L1", "D_real", "D_fake"):
+        losses["T." + n] = (float(getattr(teacher, "loss_" + n)), float(getattr(T, "loss_" + n)))
+
+    _cmp_grads(report, "S.G", _arena_grads(model.arena_G), {k: v.grad for k, v in S.G.items() if v.dtype == torch.float32})
+    _cmp_grads(report, "S.transform", _arena_grads(model.arena_G),
+               {"transform.%d.weight" % i: w.grad for i, w in enumerate(S.transform)})
+    _cmp_grads(report, "S.D", _arena_grads(model.arena_D),
+               {k: v.grad for k, v in S.D.items() if v.dtype == torch.float32 and not k.endswith("alpha")})
+    _cmp_grads(report, "T.G", _arena_grads(teacher.arena_G), {k: v.grad for k, v in T.G.items() if v.dtype == torch.float32})
+    _cmp_grads(report, "T.D", _arena_grads(teacher.arena_D), {k: v.grad for k, v in T.D.items() if v.dtype == torch.float32})
+    # BN running statistics after the 11 D / 4 G forwards of the iteration
+    sd = model.netD.state_dict()
+    for k, v in S.D.items():
+        if "running" in k:
+            report["S.D." + k] = _rel_l2(sd[k].cpu(), v)
+
+    # ---- arch step on a validation batch
+    vA = O.det_image("%s.vA.0" % name, batch, 3, 256, 256)
+    vB = O.det_image("%s.vB.0" % name, batch, 3, 256, 256)
+    S.set_input(vA, vB)
+    S.clipping_mask_alpha()
+    S.optimizer_netD_arch()
+    model.set_input({"A": vA, "B": vB, "A_paths": "", "B_paths": ""})
+    model.clipping_mask_alpha()
+    model.optimizer_netD_arch()
+    torch.cuda.synchronize()
+    for n in ("D_arch_diff", "D_arch", "teacher_D_arch_diff"):
+        losses["S." + n] = (float(getattr(model, "loss_" + n)), float(getattr(S, "loss_" + n)))
+    _cmp_grads(report, "S.alpha", _arena_grads(model.arena_A), {k: v.grad for k, v in S.D.items() if k.endswith("alpha")})
+    masks_equal = all(torch.equal(m.cpu(), om) for m, om in zip(model.netD.get_current_masks(), S.current_masks()))
+    got = model.get_current_losses()
+    assert set(got) == set(S.get_current_losses())
+
+    report["losses"] = {k: {"b200": a, "oracle": b} for k, (a, b) in losses.items()}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "step_parity_%s.json" % name), "w") as f:
+        json.dump(report, f, indent=1)
+    print(json.dumps(report, indent=1))
+
+    bad = []
+    for k, v in report.items():
+        if k == "losses":
+            continue
+        if k.endswith(".cos"):
+            if v < 0.995:
+                bad.append((k, v))
+        elif k.endswith(".grad.rel_l2"):
+            if v > 8e-2:
+                bad.append((k, v))
+        elif v > 3e-2:
+            bad.append((k, v))
+    for k, (a, b) in losses.items():
+        if abs(a - b) > 3e-2 * abs(b) + 2e-3:
+            bad.append(("loss." + k, a, b))
+    assert masks_equal, "gate masks differ from the oracle"
+    assert not bad, bad
