@@ -7,6 +7,7 @@ raised (``GccB200Error``).
 import ctypes
 import os
 import re
+import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "gcc_b200.h")
@@ -81,9 +82,23 @@ def lib():
     return l
 
 
+_tls = threading.local()
+
+
+def _bind_thread(l):
+    """Once per host thread (torch's autograd engine runs backward on its own threads)."""
+    import torch
+    dev = torch.cuda.current_device()
+    if getattr(_tls, "device", None) != dev:
+        if l.gcc_bind_thread(dev) != 0:
+            raise GccB200Error("gcc_bind_thread(%d) failed: %s" % (dev, l.gcc_last_error().decode()))
+        _tls.device = dev
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
     l = lib()
+    _bind_thread(l)
     rc = getattr(l, name)(*args)
     if rc != 0:
         msg = l.gcc_last_error()

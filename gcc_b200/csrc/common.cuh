@@ -14,8 +14,11 @@
 #define GCC_ERR_CUDA 2
 #define GCC_ERR_DRIVER 3
 
+extern unsigned long long g_gcc_launches;  // kernels launched by this library (bench.py gpu_launches)
+
 #define GCC_CHECK_LAUNCH()                                 \
   do {                                                     \
+    ++g_gcc_launches;                                      \
     cudaError_t e__ = cudaGetLastError();                  \
     if (e__ != cudaSuccess) {                              \
       gcc_set_error(__FILE__, __LINE__, cudaGetErrorString(e__)); \

@@ -11,7 +11,22 @@ void gcc_set_error(const char* file, int line, const char* msg) {
 
 extern "C" const char* gcc_last_error(void) { return g_err; }
 
+unsigned long long g_gcc_launches = 0;
+extern "C" long long gcc_launch_count(void) { return (long long)g_gcc_launches; }
+
 extern "C" int gcc_abi_version(void) { return 1; }
+
+// The library links its own (static) CUDA runtime.  A host thread that has not yet issued a runtime
+// call through THIS runtime instance (e.g. torch's autograd worker threads) has no context bound for
+// the driver-API tensor-map encoder; bind the device's primary context once per thread.
+extern "C" int gcc_bind_thread(int device) {
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_bind_thread: cannot bind the device context");
+    cudaGetLastError();
+    return GCC_ERR_CUDA;
+  }
+  return GCC_OK;
+}
 
 // Fails (non-zero) unless the current device is an sm_100 part: there is no fallback path.
 extern "C" int gcc_check_device(void) {

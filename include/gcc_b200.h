@@ -21,6 +21,10 @@ extern "C" {
 int gcc_abi_version(void);
 const char* gcc_last_error(void);
 int gcc_check_device(void); /* non-zero unless the current device is sm_100 */
+/* call once per host thread before any other entry point: binds `device`'s primary context to the
+ * calling thread for this library's (statically linked) CUDA runtime. */
+int gcc_bind_thread(int device);
+long long gcc_launch_count(void); /* kernels launched by this library so far (host counter) */
 
 /* ---- dense contractions on tcgen05 tensor cores (conv_gemm.cu) ----
  * gcc_conv_gemm_bf16: y[n,oy,ox,y_coff+r] = act(bias[r] + sum_{kh,kw,c} x[n,iy,ix,c] * w[r][kh*KW+kw][c])
