@@ -25,8 +25,9 @@ __device__ __forceinline__ void block_atomic_sum(float v, float* out) {
 // kind: 0 = D on real, 1 = D on fake, 2 = G (target real, for_discriminator = False)
 __device__ __forceinline__ float gan_term(float x, int mode, int kind, float* grad) {
   if (mode == 0) {
-    if (kind == 0) { const float v = x - 1.f; *grad = v < 0.f ? -1.f : 0.f; return -fminf(v, 0.f); }
-    if (kind == 1) { const float v = -x - 1.f; *grad = v < 0.f ? 1.f : 0.f; return -fminf(v, 0.f); }
+    // torch.min(v, 0) splits the gradient evenly at an exact tie (v == 0); bf16 logits do hit it
+    if (kind == 0) { const float v = x - 1.f; *grad = v < 0.f ? -1.f : (v == 0.f ? -0.5f : 0.f); return -fminf(v, 0.f); }
+    if (kind == 1) { const float v = -x - 1.f; *grad = v < 0.f ? 1.f : (v == 0.f ? 0.5f : 0.f); return -fminf(v, 0.f); }
     *grad = -1.f;
     return -x;
   }

@@ -397,7 +397,7 @@ class Pix2PixModel(nn.Module):
     def get_current_losses(self):
         ret = OrderedDict()
         for name in self.loss_names:
-            ret[name] = float(getattr(self, "loss_" + name))  # AttributeError before the first arch step, as upstream
+            ret[name] = float(getattr(self, "loss_" + name).detach())  # AttributeError before the first arch step, as upstream
         return ret
 
     def init_distillation(self):

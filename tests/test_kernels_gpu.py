@@ -298,7 +298,8 @@ def test_gan_loss(G, mode, kind):
     (loss * 3.0).backward()
     pr = bf(pred).requires_grad_(True)
     if mode == "hinge":
-        lr = [-torch.clamp(pr - 1, max=0).mean(), -torch.clamp(-pr - 1, max=0).mean(), -pr.mean()][kind]
+        z = torch.zeros_like(pr)
+        lr = [-torch.min(pr - 1, z).mean(), -torch.min(-pr - 1, z).mean(), -pr.mean()][kind]
     elif mode == "lsgan":
         lr = ((pr - (0.0 if kind == 1 else 1.0)) ** 2).mean()
     elif mode == "vanilla":
