@@ -39,6 +39,8 @@ def parse_args():
     p.add_argument("--no_dropout", action="store_true")
     p.add_argument("--cpu_iters", type=int, default=3, help="timed CPU-baseline iterations (batch 1)")
     p.add_argument("--skip_cpu_baseline", action="store_true")
+    p.add_argument("--skip_e2e", action="store_true", help="profiling runs only")
+    p.add_argument("--skip_roofline", action="store_true", help="profiling runs only")
     p.add_argument("--graph", type=int, default=0, help="reserved")
     return p.parse_args()
 
@@ -268,8 +270,11 @@ def run_b200(args):
         sampler.start()
     ms, launches = timed(args.steps, devb, False)
     clocks = sampler.stop() if rank == 0 else None
-    step(host[0], True)  # warm the host-input path once
-    ms_e2e, _ = timed(args.steps, host, True)
+    if args.skip_e2e:
+        ms_e2e = float("nan")
+    else:
+        step(host[0], True)  # warm the host-input path once
+        ms_e2e, _ = timed(args.steps, host, True)
 
     if rank != 0:
         if world > 1:
@@ -297,7 +302,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
     }
     if world == 1:
-        line["roofline"] = dominant_kernel_roofline(B, pk)
+        if not args.skip_roofline:
+            line["roofline"] = dominant_kernel_roofline(B, pk)
         if not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_rate(args, iters=args.cpu_iters)
     else:

@@ -168,16 +168,32 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
 }
 
 // ---- bias gradient: db[c] = sum over pixels of dy[p, c_off + c] --------------------------------
-__global__ void colsum_kernel(const bf16* __restrict__ dy, long long npix, int Cp, int c_off, int C,
-                              float* __restrict__ out) {
-  // one warp per channel-slab of pixels; threads stride over pixels, channels looped
-  for (int c = blockIdx.y; c < C; c += gridDim.y) {
+// thread = (channel group of 8, pixel lane); 16-byte loads; shared-memory reduce over lanes; one atomic per
+// (block, channel).  Requires Cp % 8 == 0 and c_off % 8 == 0 (activations always satisfy this).
+__global__ void colsum_vec_kernel(const bf16* __restrict__ dy, long long npix, int Cp, int c_off, int C, int G,
+                                  int lanes, float* __restrict__ out) {
+  extern __shared__ float red[];  // [lanes][G][8]
+  const int tid = threadIdx.x;
+  const int g = tid % G, lane = tid / G;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < lanes) {
+    for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+      const uint4 u = *reinterpret_cast<const uint4*>(dy + p * Cp + c_off + g * 8);
+      s[0] += bf16_lo(u.x); s[1] += bf16_hi(u.x);
+      s[2] += bf16_lo(u.y); s[3] += bf16_hi(u.y);
+      s[4] += bf16_lo(u.z); s[5] += bf16_hi(u.z);
+      s[6] += bf16_lo(u.w); s[7] += bf16_hi(u.w);
+    }
+    float* r = red + ((long long)lane * G + g) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = s[i];
+  }
+  __syncthreads();
+  for (int e = tid; e < G * 8; e += blockDim.x) {
+    if (e >= C) continue;
     float acc = 0.f;
-    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix;
-         p += (long long)gridDim.x * blockDim.x)
-      acc += __bfloat162float(dy[p * Cp + c_off + c]);
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out + c, acc);
+    for (int l = 0; l < lanes; ++l) acc += red[(long long)l * G * 8 + e];
+    atomicAdd(out + e, acc);
   }
 }
 
@@ -366,6 +382,86 @@ __global__ void dw3x3_bwd_weight_kernel(const bf16* __restrict__ x, const bf16* 
   }
 }
 
+// ---- im2col / col2im for k4 s2 p1 layers whose image side has <= 8 channels (Cp == 8) -----------
+// These layers (PatchGAN / U-Net first conv, U-Net last ConvTranspose) have K or N = 3..6 channels: as an
+// implicit GEMM every tap would be a 64-wide k-block that is 7/8 zeros.  Instead the 16 taps x 8 channels
+// are laid out as ONE 128-wide K (or N) so the same tcgen05 kernels run them as 1x1 convs.
+// col[n,oh,ow,(kh*4+kw)*8 + c] = img[n, 2*oh+kh-1, 2*ow+kw-1, c]   (zero outside the image)
+__global__ void im2col_k4s2_c8_kernel(const uint4* __restrict__ img, uint4* __restrict__ col, int N, int H, int W) {
+  const int OH = H / 2, OW = W / 2;
+  const long long total = (long long)N * OH * OW * 16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i & 15);
+    long long t = i >> 4;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH);
+    const long long n = t / OH;
+    const int ih = 2 * oh + (tap >> 2) - 1, iw = 2 * ow + (tap & 3) - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = img[(n * H + ih) * W + iw];
+    col[i] = v;
+  }
+}
+// img[n,iy,ix,c] = act(bias[c] + sum_{kh,kw} col[n,(iy+1-kh)/2,(ix+1-kw)/2, idx(kh,kw,c)]) over the taps whose
+// source index is integral and inside the col grid.  order 0: idx = (kh*4+kw)*8+c, order 1: idx = c*16+kh*4+kw.
+__global__ void col2im_k4s2_c8_kernel(const bf16* __restrict__ col, int Ccol, int order, int C,
+                                      const float* __restrict__ bias, int act, uint4* __restrict__ img, int N, int H,
+                                      int W) {
+  const int OH = H / 2, OW = W / 2;
+  const long long total = (long long)N * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % W);
+    long long t = i / W;
+    const int iy = (int)(t % H);
+    const long long n = t / H;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = (bias != nullptr && c < C) ? bias[c] : 0.f;
+    const int kh0 = (iy + 1) & 1, kw0 = (ix + 1) & 1;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int kh = kh0 + 2 * a;
+      const int oh = (iy + 1 - kh) / 2;
+      if (iy + 1 - kh < 0 || oh >= OH) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int kw = kw0 + 2 * b;
+        const int ow = (ix + 1 - kw) / 2;
+        if (ix + 1 - kw < 0 || ow >= OW) continue;
+        const bf16* row = col + ((n * OH + oh) * OW + ow) * (long long)Ccol;
+        const int tap = kh * 4 + kw;
+        if (order == 0) {
+          const uint4 u = *reinterpret_cast<const uint4*>(row + tap * 8);
+          acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x);
+          acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+          acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z);
+          acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+        } else {
+          for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(row[c * 16 + tap]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c >= C) acc[c] = 0.f;
+      else if (act == 2) acc[c] = tanhf(acc[c]);
+    }
+    img[i] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                        pack_bf16(acc[6], acc[7]));
+  }
+}
+// g[r][tap][c] += tmp[r][tap*8 + c]   (c < C <= 8): weight gradient of a col-path layer back to [R][16][C]
+__global__ void unpad_wgrad_c8_kernel(const float* __restrict__ tmp, float* __restrict__ g, int R, int C) {
+  const int total = R * 16 * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int rt = i / C;
+    g[i] += tmp[(long long)rt * 8 + c];
+  }
+}
+
 static inline int blocks_for(long long n, int per = 256) {
   long long b = (n + per - 1) / per;
   const long long cap = 148LL * 16;
@@ -443,10 +539,19 @@ extern "C" int gcc_bias_grad_bf16(const void* dy, long long npix, int Cp, int c_
                                   void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate && cudaMemsetAsync(out, 0, sizeof(float) * C, st) != cudaSuccess) return GCC_ERR_CUDA;
-  int bx = (int)((npix + 255) / 256);
-  if (bx > 128) bx = 128;
+  if ((Cp % 8) || (c_off % 8)) {
+    gcc_set_error(__FILE__, __LINE__, "bias_grad: channel window must be 8-aligned");
+    return GCC_ERR_ARG;
+  }
+  const int G = (C + 7) / 8;
+  int lanes = 256 / G;
+  if (lanes < 1) lanes = 1;
+  const int threads = (lanes * G + 31) / 32 * 32;
+  long long bx = (npix + lanes * 16 - 1) / (lanes * 16);
+  if (bx > 148 * 8) bx = 148 * 8;
   if (bx < 1) bx = 1;
-  colsum_kernel<<<dim3(bx, C > 64 ? 64 : C), 256, 0, st>>>((const bf16*)dy, npix, Cp, c_off, C, out);
+  colsum_vec_kernel<<<(unsigned)bx, threads, sizeof(float) * lanes * G * 8, st>>>((const bf16*)dy, npix, Cp, c_off, C, G,
+                                                                                lanes, out);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -507,5 +612,27 @@ extern "C" int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w,
                                                                  G, C, lanes);
     GCC_CHECK_LAUNCH();
   }
+  return GCC_OK;
+}
+
+extern "C" int gcc_im2col_k4s2_c8(const void* img, void* col, int N, int H, int W, void* stream) {
+  if ((H % 2) || (W % 2)) { gcc_set_error(__FILE__, __LINE__, "im2col: H, W must be even"); return GCC_ERR_ARG; }
+  im2col_k4s2_c8_kernel<<<blocks_for((long long)N * (H / 2) * (W / 2) * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)img, (uint4*)col, N, H, W);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_col2im_k4s2_c8(const void* col, int Ccol, int order, int C, const float* bias, int act, void* img,
+                                  int N, int H, int W, void* stream) {
+  if ((H % 2) || (W % 2) || C > 8 || (Ccol % 8)) { gcc_set_error(__FILE__, __LINE__, "col2im: bad arguments"); return GCC_ERR_ARG; }
+  col2im_k4s2_c8_kernel<<<blocks_for((long long)N * H * W), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)col, Ccol, order, C, bias, act, (uint4*)img, N, H, W);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_unpad_wgrad_c8(const float* tmp, float* g, int R, int C, void* stream) {
+  if (C > 8) { gcc_set_error(__FILE__, __LINE__, "unpad_wgrad: C must be <= 8"); return GCC_ERR_ARG; }
+  unpad_wgrad_c8_kernel<<<(R * 16 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tmp, g, R, C);
+  GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

@@ -125,36 +125,45 @@ __device__ __forceinline__ void channel_affine(const NormArgs& a, int n, int c, 
 }
 
 // -------------------------------------------------------------------------------------- forward
+// Per-channel coefficients are computed once per block into shared memory (p, q, m):
+//   y = act(x*p + q) * m   with p = rstd*gamma*mask, q = (beta - mean*rstd*gamma)*mask, m = 1
+//   (gate_after: p, q without the mask and m = mask).  grid.y = sample index for instance norm.
 __global__ void norm_apply_kernel(NormArgs a, int nimg, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp,
                                   int y2_coff, int act2, float* running_mean, float* running_var, float momentum) {
-  const long long total_pix = a.per_sample ? a.npix * nimg : a.npix;
-  const long long nvec = total_pix * a.G;
+  extern __shared__ float coef[];  // [3][Cp]
+  float* cp = coef;
+  float* cq = coef + a.Cp;
+  float* cm = coef + 2 * a.Cp;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < a.Cp; c += blockDim.x) {
+    float mean, rstd, gam, bet, mask;
+    channel_affine(a, n, c, mean, rstd, gam, bet, mask);
+    const float mk = a.gate_after ? 1.f : mask;
+    cp[c] = rstd * gam * mk;
+    cq[c] = (bet - mean * rstd * gam) * mk;
+    cm[c] = a.gate_after ? mask : 1.f;
+  }
+  __syncthreads();
+  const long long pix0 = a.per_sample ? (long long)n * a.npix : 0;
+  const long long nvec = a.npix * a.G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % a.G);
-    const long long pix = i / a.G;
-    const int n = a.per_sample ? (int)(pix / a.npix) : 0;
+    const long long pix = pix0 + i / a.G;
     const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
     Vec8 o, o2;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float mean, rstd, gam, bet, mask;
-      channel_affine(a, n, g * 8 + k, mean, rstd, gam, bet, mask);
-      const float z = (xv.v[k] - mean) * rstd * gam + bet;
-      if (a.gate_after) {
-        o.v[k] = act_fwd(z, a.act, a.slope) * mask;
-        o2.v[k] = act_fwd(z, act2, a.slope) * mask;
-      } else {
-        const float gg = z * mask;
-        o.v[k] = act_fwd(gg, a.act, a.slope);
-        o2.v[k] = act_fwd(gg, act2, a.slope);
-      }
+      const int c = g * 8 + k;
+      const float z = xv.v[k] * cp[c] + cq[c];
+      o.v[k] = act_fwd(z, a.act, a.slope) * cm[c];
+      o2.v[k] = act_fwd(z, act2, a.slope) * cm[c];
     }
     if (y != nullptr) store8(y + pix * a.Cp + g * 8, o);
     if (y2 != nullptr) store8(y2 + pix * y2_Cp + y2_coff + g * 8, o2);
   }
   // running statistics (train-mode BatchNorm2d side effect; momentum 0.1, unbiased variance)
-  if (running_mean != nullptr && blockIdx.x == 0 && a.sums != nullptr) {
+  if (running_mean != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && a.sums != nullptr) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       const float inv = 1.f / (float)a.npix;
       const float mean = a.sums[c] * inv;
@@ -258,21 +267,45 @@ __global__ void norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __rest
 }
 
 // dx = gamma*rstd*mask * (dg - (S1 + xhat*S2)/M)   [norm]   or   dx = mask*dg [identity]
-// block 0 also accumulates dgamma += mask*S2, dbeta += mask*S1, dalpha += gamma*S2 + beta*S1 (summed over n).
+// rewritten with per-channel shared-memory coefficients: gg = x*p + q, dx = c1*dg - c2 - c3*x.
+// block (0,0) also accumulates dgamma += mask*S2, dbeta += mask*S1, dalpha += gamma*S2 + beta*S1 (summed over n).
 __global__ void norm_bwd_apply_kernel(NormArgs a, int nimg, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
                                       const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
                                       const float* __restrict__ red, bf16* __restrict__ dx, float* dgamma,
                                       float* dbeta, float* dalpha) {
-  const long long total_pix = a.per_sample ? a.npix * nimg : a.npix;
-  const long long nvec = total_pix * a.G;
+  extern __shared__ float coef[];  // [5][Cp]
+  float* cp = coef;
+  float* cq = coef + a.Cp;
+  float* c1 = coef + 2 * a.Cp;
+  float* c2 = coef + 3 * a.Cp;
+  float* c3 = coef + 4 * a.Cp;
+  const int n = blockIdx.y;
   const float invM = 1.f / (float)a.npix;
   if (dx != nullptr) {
+    const float* rb = red + (long long)n * 2 * a.Cp;
+    for (int c = threadIdx.x; c < a.Cp; c += blockDim.x) {
+      float mean, rstd, gam, bet, mask;
+      channel_affine(a, n, c, mean, rstd, gam, bet, mask);
+      const float mk = a.gate_after ? 1.f : mask;
+      cp[c] = rstd * gam * mk;
+      cq[c] = (bet - mean * rstd * gam) * mk;
+      const float k1 = gam * rstd * mask;
+      c1[c] = (c < a.C) ? k1 : 0.f;
+      if (a.sums != nullptr && c < a.C) {
+        c2[c] = k1 * invM * (rb[c] - rb[a.Cp + c] * rstd * mean);
+        c3[c] = k1 * invM * rb[a.Cp + c] * rstd;
+      } else {
+        c2[c] = 0.f;
+        c3[c] = 0.f;
+      }
+    }
+    __syncthreads();
+    const long long pix0 = a.per_sample ? (long long)n * a.npix : 0;
+    const long long nvec = a.npix * a.G;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
          i += (long long)gridDim.x * blockDim.x) {
       const int g = (int)(i % a.G);
-      const long long pix = i / a.G;
-      const int n = a.per_sample ? (int)(pix / a.npix) : 0;
-      const float* rb = red + (long long)n * 2 * a.Cp;
+      const long long pix = pix0 + i / a.G;
       const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
       Vec8 d1, d2, o;
       if (dy != nullptr) d1 = load8(dy + pix * dy_Cp + dy_coff + g * 8);
@@ -280,30 +313,22 @@ __global__ void norm_bwd_apply_kernel(NormArgs a, int nimg, const bf16* __restri
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int c = g * 8 + k;
-        float mean, rstd, gam, bet, mask;
-        channel_affine(a, n, c, mean, rstd, gam, bet, mask);
-        const float xh = (xv.v[k] - mean) * rstd;
-        const float gg = a.gate_after ? (xh * gam + bet) : (xh * gam + bet) * mask;
+        const float gg = xv.v[k] * cp[c] + cq[c];
         float dg = 0.f;
         if (dy != nullptr) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
         if (dy2 != nullptr) dg += d2.v[k] * act_grad(gg, act2, a.slope);
-        float r;
-        if (a.sums != nullptr)
-          r = gam * rstd * mask * (dg - (rb[c] + xh * rb[a.Cp + c]) * invM);
-        else
-          r = gam * mask * dg;
-        o.v[k] = (c < a.C) ? r : 0.f;
+        o.v[k] = c1[c] * dg - c2[c] - c3[c] * xv.v[k];
       }
       store8(dx + pix * a.Cp + g * 8, o);
     }
   }
-  if (blockIdx.x == 0 && (dgamma != nullptr || dbeta != nullptr || dalpha != nullptr)) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr || dalpha != nullptr)) {
     const int groups = a.per_sample ? nimg : 1;
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       float S1 = 0.f, S2 = 0.f;
-      for (int n = 0; n < groups; ++n) {
-        S1 += red[(long long)n * 2 * a.Cp + c];
-        S2 += red[(long long)n * 2 * a.Cp + a.Cp + c];
+      for (int m = 0; m < groups; ++m) {
+        S1 += red[(long long)m * 2 * a.Cp + c];
+        S2 += red[(long long)m * 2 * a.Cp + a.Cp + c];
       }
       const float gam = a.gamma ? a.gamma[c] : 1.f;
       const float bet = a.beta ? a.beta[c] : 0.f;
@@ -349,6 +374,14 @@ static int fill_args(NormArgs& a, const void* x, int N, long long HW, int Cp, in
   return GCC_OK;
 }
 
+// blocks per statistics group so that the whole grid stays around 16 CTAs per SM
+static int group_blocks(long long nvec_per_group, int groups) {
+  long long b = (nvec_per_group + 255) / 256;
+  long long cap = (148LL * 16 + groups - 1) / groups;
+  if (cap < 1) cap = 1;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
 static int ew_blocks(long long nvec) {
   long long b = (nvec + 255) / 256;
   const long long cap = 148LL * 16;
@@ -392,9 +425,11 @@ extern "C" int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, 
     gcc_set_error(__FILE__, __LINE__, "norm_apply: second output window must be 8-channel aligned");
     return GCC_ERR_ARG;
   }
-  const long long nvec = (long long)N * HW * a.G;
-  norm_apply_kernel<<<ew_blocks(nvec), 256, 0, st>>>(a, N, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff, act2, running_mean,
-                                                     running_var, momentum);
+  const int groups = per_sample ? N : 1;
+  const long long nvec = a.npix * a.G;
+  const int bx = group_blocks(nvec, groups);
+  norm_apply_kernel<<<dim3(bx, groups), 256, sizeof(float) * 3 * Cp, st>>>(a, N, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff,
+                                                                          act2, running_mean, running_var, momentum);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -443,10 +478,11 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
         a, lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
     GCC_CHECK_LAUNCH();
   }
-  const long long nvec = (long long)N * HW * a.G;
-  norm_bwd_apply_kernel<<<dx ? ew_blocks(nvec) : 1, 256, 0, st>>>(a, N, (const bf16*)dy, dy_Cp, dy_coff,
-                                                                 (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red,
-                                                                 (bf16*)dx, dgamma, dbeta, dalpha);
+  const long long nvec = a.npix * a.G;
+  const int bx = dx ? group_blocks(nvec, groups) : 1;
+  norm_bwd_apply_kernel<<<dim3(bx, dx ? groups : 1), 256, sizeof(float) * 5 * Cp, st>>>(
+      a, N, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, (bf16*)dx, dgamma, dbeta,
+      dalpha);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

@@ -44,6 +44,9 @@ class ConvLayer:
         arena.add(self.wname, shape, kind)
         if bias:
             arena.add(self.bname, (cout,), "vec")
+        # k4 s2 p1 layers whose image side has <= 8 channels run through im2col/col2im (ops.ColConvFn)
+        self.colpath = (k == 4 and stride == 2 and pad == 1 and outpad == 0 and
+                        ((kind == "conv" and cin <= 8) or (kind == "convT" and cout <= 8)))
 
     def bind(self):
         self.weight = self.arena.params[self.wname]
@@ -51,7 +54,8 @@ class ConvLayer:
         self.packs = self.arena.packs[self.wname]
 
     def __call__(self, x, act=ACT_NONE, slope=0.2):
-        return ops.ConvFn.apply(x, self.weight, self.bias, self, act, slope)
+        fn = ops.ColConvFn if self.colpath else ops.ConvFn
+        return fn.apply(x, self.weight, self.bias, self, act, slope)
 
 
 class DwConvLayer:

@@ -110,6 +110,107 @@ class ConvFn(torch.autograd.Function):
         return dx, None, None, None, None, None
 
 
+class ColConvFn(torch.autograd.Function):
+    """k4 s2 p1 Conv2d with <= 8 input channels / ConvTranspose2d with <= 8 output channels: the image side is
+    expanded by im2col / folded by col2im (16 taps x 8 channels = one 128-wide GEMM dimension) and the
+    contraction runs as a 1x1 conv on the tcgen05 kernels (see elementwise.cu, "im2col / col2im")."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, act, slope):
+        _check(x)
+        x = x.contiguous()
+        layer.arena.ensure_packed()
+        st = _st()
+        n, h, w, cx = x.shape
+        pk = layer.packs
+        bp = None if bias is None else bias.data_ptr()
+        if layer.kind == "conv":
+            oh, ow = h // 2, w // 2
+            cop = rp8(layer.cout)
+            xcol = torch.empty(n, oh, ow, 128, dtype=torch.bfloat16, device=x.device)
+            call("gcc_im2col_k4s2_c8", x.data_ptr(), xcol.data_ptr(), n, h, w, st)
+            y = torch.empty(n, oh, ow, cop, dtype=torch.bfloat16, device=x.device)
+            epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
+            call("gcc_conv_gemm_bf16", xcol.data_ptr(), n, oh, ow, 128, pk.direct.data_ptr(), layer.cout, 1, 128, bp,
+                 y.data_ptr(), oh, ow, cop, 0, 0, 1, 1, 1, 0, epi, slope, 0, st)
+            saved = xcol
+        else:
+            oh, ow = 2 * h, 2 * w
+            ycol = torch.empty(n, h, w, 128, dtype=torch.bfloat16, device=x.device)
+            wp = pk.transposed  # [cout][16][cin_p] viewed as [cout*16][1][cin_p]
+            call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), layer.cout * 16, 1, wp.shape[2], None,
+                 ycol.data_ptr(), h, w, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, st)
+            y = torch.empty(n, oh, ow, 8, dtype=torch.bfloat16, device=x.device)
+            if act not in (ACT_NONE, ACT_TANH):
+                raise _lib.GccB200Error("col-path ConvTranspose supports none/tanh epilogues")
+            call("gcc_col2im_k4s2_c8", ycol.data_ptr(), 128, 1, layer.cout, bp, 2 if act == ACT_TANH else 0,
+                 y.data_ptr(), n, oh, ow, st)
+            saved = x
+        ctx.layer, ctx.act, ctx.slope = layer, act, slope
+        ctx.has_bias = bias is not None
+        ctx.xshape = (n, h, w, cx)
+        ctx.save_for_backward(saved, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        saved, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        st = _st()
+        dev = dy.device
+        if ctx.act != ACT_NONE:
+            dpre = torch.empty_like(dy)
+            call("gcc_act_bwd_bf16", y.data_ptr(), dy.data_ptr(), dpre.data_ptr(), dy.numel(),
+                 1 if ctx.act == ACT_LRELU else 3, ctx.slope, st)
+        else:
+            dpre = dy
+        n, h, w, cx = ctx.xshape
+        pk = layer.packs
+        dx = None
+        if layer.kind == "conv":
+            _, oh, ow, cop = dpre.shape
+            xcol = saved
+            if ctx.needs_input_grad[0]:
+                layer.arena.ensure_packed()
+                wp = pk.transposed  # [cin][16][cout_p] viewed as [cin*16][1][cout_p]
+                dcol = torch.empty(n, oh, ow, 128, dtype=torch.bfloat16, device=dev)
+                call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin * 16, 1,
+                     wp.shape[2], None, dcol.data_ptr(), oh, ow, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, st)
+                dx = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=dev)
+                call("gcc_col2im_k4s2_c8", dcol.data_ptr(), 128, 1, layer.cin, None, 0, dx.data_ptr(), n, h, w, st)
+            if ctx.needs_input_grad[1]:
+                tmp = torch.empty(layer.cout, 128, dtype=torch.float32, device=dev)
+                call("gcc_wgrad_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, xcol.data_ptr(), oh, ow, 128,
+                     tmp.data_ptr(), layer.cout, 128, 1, 1, 1, 0, 0, 0, 1.0, st)
+                call("gcc_unpad_wgrad_c8", tmp.data_ptr(), layer.arena.flat_grad[layer.wname].data_ptr(), layer.cout,
+                     layer.cin, st)
+            npix_out = n * oh * ow
+            bias_cp = cop
+        else:
+            x = saved
+            dcol = torch.empty(n, h, w, 128, dtype=torch.bfloat16, device=dev)
+            call("gcc_im2col_k4s2_c8", dpre.data_ptr(), dcol.data_ptr(), n, 2 * h, 2 * w, st)
+            if ctx.needs_input_grad[0]:
+                layer.arena.ensure_packed()
+                wp = pk.direct  # [cin][16][8] viewed as [cin][1][128]
+                dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=dev)
+                call("gcc_conv_gemm_bf16", dcol.data_ptr(), n, h, w, 128, wp.data_ptr(), layer.cin, 1, 128, None,
+                     dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, st)
+            if ctx.needs_input_grad[1]:
+                tmp = torch.empty(layer.cin, 128, dtype=torch.float32, device=dev)
+                call("gcc_wgrad_gemm_bf16", x.data_ptr(), n, h, w, cx, dcol.data_ptr(), h, w, 128, tmp.data_ptr(),
+                     layer.cin, 128, 1, 1, 1, 0, 0, 0, 1.0, st)
+                call("gcc_unpad_wgrad_c8", tmp.data_ptr(), layer.arena.flat_grad[layer.wname].data_ptr(), layer.cin,
+                     layer.cout, st)
+            npix_out = n * 4 * h * w
+            bias_cp = 8
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = layer.arena.flat_grad[layer.bname]
+            call("gcc_bias_grad_bf16", dpre.data_ptr(), npix_out, bias_cp, 0, layer.cout, gb.data_ptr(), 1, st)
+        return dx, None, None, None, None, None
+
+
 class NormActFn(torch.autograd.Function):
     """[BatchNorm | InstanceNorm | identity] -> [channel gate] -> activation, with an optional second
     activation output (the U-Net's relu'd skip copy)."""

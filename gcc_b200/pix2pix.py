@@ -91,6 +91,7 @@ class Pix2PixModel(nn.Module):
         self.loss_names = ["G_GAN", "G_L1", "D_real", "D_fake"]
         self.visual_names = ["real_A", "fake_B", "real_B"]
         self.current_D_arch_diff_loss = 0.0
+        self._ema_state = None
         self.teacher_model = None
         dev = self.device
         self.distill = bool(opt.online_distillation or getattr(opt, "normal_distillation", False))
@@ -253,9 +254,15 @@ class Pix2PixModel(nn.Module):
         pred_real, _ = self._D(self.netD, self.real_AB)
         self.loss_D_arch_real = self._gan(pred_real, 0)
         diff = (self.loss_D_arch_fake_real - self.loss_D_arch_fake).abs()
-        if isTeacher and not (isinstance(self.current_D_arch_diff_loss, float) and self.current_D_arch_diff_loss == 0.0):
-            b = self.opt.ema_beta
-            self.current_D_arch_diff_loss = b * diff + (1.0 - b) * self.current_D_arch_diff_loss
+        if isTeacher:
+            # EMA state (Pix2Pix.py:503-508) kept in ONE persistent device scalar so that a captured CUDA graph
+            # carries it across replays; the teacher D is frozen here, so the state is graph-free as upstream.
+            if self._ema_state is None:
+                self._ema_state = diff.detach().clone()
+            else:
+                b = self.opt.ema_beta
+                self._ema_state.copy_(b * diff.detach() + (1.0 - b) * self._ema_state)
+            self.current_D_arch_diff_loss = self._ema_state
         else:
             self.current_D_arch_diff_loss = diff
         return self.current_D_arch_diff_loss, torch.sign(self.loss_D_arch_fake_real - self.loss_D_arch_fake)

