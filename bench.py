@@ -263,11 +263,11 @@ def run_b200(args):
             ms = float(t)
         return ms, _lib.lib().gcc_launch_count() - l0
 
-    for i in range(args.warmup):
-        step(devb[i % nbatch], False)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # sampled from the warm-up on: the GPU is under the same load as in the timed region
+    for i in range(args.warmup):
+        step(devb[i % nbatch], False)
     ms, launches = timed(args.steps, devb, False)
     clocks = sampler.stop() if rank == 0 else None
     if args.skip_e2e:

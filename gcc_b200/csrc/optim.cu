@@ -62,22 +62,42 @@ __global__ void clamp_kernel(float* __restrict__ x, long long n, float lo, float
 }
 
 // table entry (8 x int64): src, direct, transposed, D0, T, D1, D1p, D0p
+// One CTA handles 32 x 32 (d0 x d1) tiles of one tap: coalesced fp32 reads along d1, coalesced bf16 writes of
+// the direct pack along d1 and, through a shared-memory transpose, of the transposed pack along d0.
 __global__ void pack_table_kernel(const long long* __restrict__ table) {
+  __shared__ float tile[32][33];
   const long long* e = table + (long long)blockIdx.y * 8;
   const float* src = reinterpret_cast<const float*>(e[0]);
   bf16* direct = reinterpret_cast<bf16*>(e[1]);
   bf16* transposed = reinterpret_cast<bf16*>(e[2]);
   const int D0 = (int)e[3], T = (int)e[4], D1 = (int)e[5], D1p = (int)e[6], D0p = (int)e[7];
-  const long long total = (long long)D0 * T * D1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int d1 = (int)(i % D1);
-    const long long r = i / D1;
+  const int t0 = (D0 + 31) / 32, t1 = (D1 + 31) / 32;
+  const long long ntiles = (long long)t0 * t1 * T;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+  for (long long tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    const int b1 = (int)(tile_id % t1);
+    const long long r = tile_id / t1;
     const int t = (int)(r % T);
-    const int d0 = (int)(r / T);
-    const bf16 val = __float2bfloat16(src[i]);
-    if (direct) direct[((long long)d0 * T + t) * D1p + d1] = val;
-    if (transposed) transposed[((long long)d1 * T + t) * D0p + d0] = val;
+    const int b0 = (int)(r / T);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d0 = b0 * 32 + ty + j * 8, d1 = b1 * 32 + tx;
+      float v = 0.f;
+      if (d0 < D0 && d1 < D1) {
+        v = src[((long long)d0 * T + t) * D1 + d1];
+        if (direct) direct[((long long)d0 * T + t) * D1p + d1] = __float2bfloat16(v);
+      }
+      tile[ty + j * 8][tx] = v;
+    }
+    __syncthreads();
+    if (transposed) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d1 = b1 * 32 + ty + j * 8, d0 = b0 * 32 + tx;
+        if (d0 < D0 && d1 < D1) transposed[((long long)d1 * T + t) * D0p + d0] = __float2bfloat16(tile[tx][ty + j * 8]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -114,7 +134,7 @@ extern "C" int gcc_clamp_f32(float* x, long long n, float lo, float hi, void* st
 // table: device int64 [count][8] = {src fp32 ptr, direct bf16 ptr, transposed bf16 ptr, D0, T, D1, D1p, D0p}
 extern "C" int gcc_pack_weights_table(const void* table_dev, int count, void* stream) {
   if (count <= 0) return GCC_OK;
-  pack_table_kernel<<<dim3(64, count), 256, 0, (cudaStream_t)stream>>>((const long long*)table_dev);
+  pack_table_kernel<<<dim3(128, count), 256, 0, (cudaStream_t)stream>>>((const long long*)table_dev);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
