@@ -175,7 +175,7 @@ def dominant_kernel_roofline(batch, pk):
 
     def launch():
         _lib.call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cin, wt.data_ptr(), cout, k * k, cin, None, y.data_ptr(),
-                  31, 31, cout, 0, 0, k, k, 1, 1, 0, 0.0, 0, st)
+                  31, 31, cout, 0, 0, k, k, 1, 1, 0, 0.0, 0, None, 0, st)
 
     for _ in range(3):
         launch()

@@ -339,6 +339,260 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant of conv_gemm_kernel (the one the library launches).
+//  * grid = min(#tiles, #SMs); each CTA walks tiles  tile = blockIdx.x + i * gridDim.x
+//  * the smem ring keeps running across tile boundaries (the TMA producer never drains)
+//  * TWO accumulator stages in TMEM (2 x BLOCK_N columns): the 8 epilogue warps drain tile i while the MMA
+//    warp already accumulates tile i+1  (tmem_full / tmem_empty mbarriers)
+//  * all sub-pixel classes of a stride-2 transposed conv are tiles of ONE launch
+//  * optional split-K (tiny pixel counts, long K: the U-Net's inner levels): fp32 red.add into a workspace,
+//    bias/activation/bf16 conversion by splitk_finalize_kernel
+struct ConvGeom2 {
+  CUtensorMap a_maps[4];
+  CUtensorMap b_map;
+  int num_classes;
+  int cls_tap_begin[5];
+  int cls_GH[4], cls_GW[4];
+  int cls_tiles_w[4], cls_tiles_h[4];
+  int cls_mtile_begin[5];
+  long long cls_out_off[4];
+  long long cls_part_off[4];
+  short tap_map[kMaxTaps];
+  short tap_dh[kMaxTaps];
+  short tap_dw[kMaxTaps];
+  short tap_widx[kMaxTaps];
+  int k_chunks, w_per_image;
+  int log_wt, log_ht, log_nt, GN;
+  int n_tiles, k_splits, total_tiles;
+  bf16* out;
+  long long out_sn, out_sh, out_sw;
+  int out_cols, bias_cols;
+  const float* bias;
+  int act;
+  float slope;
+  float* partial;
+  long long part_sn, part_sh, part_sw;
+};
+
+struct TileInfo {
+  int cls, n_tile, a0, b0, n0, tap0, kb0, kb1;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const ConvGeom2& p, int tile_id) {
+  TileInfo t;
+  int r = tile_id;
+  const int split = r % p.k_splits;
+  r /= p.k_splits;
+  const int m_total = p.cls_mtile_begin[p.num_classes];
+  int ml = r % m_total;
+  t.n_tile = r / m_total;
+  int cls = 0;
+  while (cls + 1 < p.num_classes && ml >= p.cls_mtile_begin[cls + 1]) ++cls;
+  t.cls = cls;
+  ml -= p.cls_mtile_begin[cls];
+  const int tw = ml % p.cls_tiles_w[cls];
+  ml /= p.cls_tiles_w[cls];
+  const int th = ml % p.cls_tiles_h[cls];
+  const int tn = ml / p.cls_tiles_h[cls];
+  t.b0 = tw << p.log_wt;
+  t.a0 = th << p.log_ht;
+  t.n0 = tn << p.log_nt;
+  t.tap0 = p.cls_tap_begin[cls];
+  const int num_kb = (p.cls_tap_begin[cls + 1] - t.tap0) * p.k_chunks;
+  const int per = (num_kb + p.k_splits - 1) / p.k_splits;
+  t.kb0 = split * per;
+  t.kb1 = min(num_kb, t.kb0 + per);
+  return t;
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __grid_constant__ ConvGeom2 p) {
+  constexpr uint32_t kABytes = kBlockM * 128;
+  constexpr uint32_t kBBytes = BLOCK_N * 128;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+  constexpr int kHalf = BLOCK_N / 2;  // columns per epilogue warp group
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_maps[0]);
+    tma_prefetch_desc(&p.b_map);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 8);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(p, tile);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          const int tl = kb / p.k_chunks;
+          const int kc = kb - tl * p.k_chunks;
+          const int tap = t.tap0 + tl;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          uint8_t* sa = smem + stage * kStageBytes;
+          tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, t.b0 + p.tap_dw[tap],
+                      t.a0 + p.tap_dh[tap], t.n0);
+          tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK,
+                      p.w_per_image ? t.n0 : (int)p.tap_widx[tap], t.n_tile * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(p, tile);
+        if (t.kb1 <= t.kb0) continue;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, kIdesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // epilogue warps 2..9: lane quarter = warp % 4, column half = (warp - 2) / 4
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int wt_mask = (1 << p.log_wt) - 1, ht_mask = (1 << p.log_ht) - 1;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileInfo t = decode_tile(p, tile);
+      if (t.kb1 <= t.kb0) continue;
+      const int b = t.b0 + (r & wt_mask);
+      const int a = t.a0 + ((r >> p.log_wt) & ht_mask);
+      const int n = t.n0 + (r >> (p.log_wt + p.log_ht));
+      const bool valid = (n < p.GN) && (a < p.cls_GH[t.cls]) && (b < p.cls_GW[t.cls]);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      if (p.k_splits == 1) {
+        bf16* orow = p.out + p.cls_out_off[t.cls] + (long long)n * p.out_sn + (long long)a * p.out_sh +
+                     (long long)b * p.out_sw;
+#pragma unroll 1
+        for (int c0 = half * kHalf; c0 < (half + 1) * kHalf; c0 += 32) {
+          const int col0 = t.n_tile * BLOCK_N + c0;
+          if (col0 >= p.out_cols) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_d + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col < p.out_cols) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float x = __uint_as_float(v[g * 8 + i]);
+                  if (p.bias != nullptr && col + i < p.bias_cols) x += __ldg(p.bias + col + i);
+                  f[i] = apply_act(x, p.act, p.slope);
+                }
+                uint4 o;
+                o.x = pack_bf16(f[0], f[1]);
+                o.y = pack_bf16(f[2], f[3]);
+                o.z = pack_bf16(f[4], f[5]);
+                o.w = pack_bf16(f[6], f[7]);
+                *reinterpret_cast<uint4*>(orow + col) = o;
+              }
+            }
+          }
+        }
+      } else {
+        float* prow = p.partial + p.cls_part_off[t.cls] + (long long)n * p.part_sn + (long long)a * p.part_sh +
+                      (long long)b * p.part_sw;
+#pragma unroll 1
+        for (int c0 = half * kHalf; c0 < (half + 1) * kHalf; c0 += 32) {
+          const int col0 = t.n_tile * BLOCK_N + c0;
+          if (col0 >= p.out_cols) break;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_d + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.out_cols) atomicAdd(prow + col0 + i, __uint_as_float(v[i]));
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// out[pix, y_coff + c] = bf16(act(partial[pix, c] + bias[c]))
+__global__ void splitk_finalize_kernel(const float* __restrict__ partial, bf16* __restrict__ out, long long npix, int Rp,
+                                       int Cy, int y_coff, int bias_cols, const float* __restrict__ bias, int act,
+                                       float slope) {
+  const long long total = npix * Rp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Rp);
+    const long long pix = i / Rp;
+    float v = partial[i];
+    if (bias != nullptr && c < bias_cols) v += bias[c];
+    out[pix * Cy + y_coff + c] = __float2bfloat16(apply_act(v, act, slope));
+  }
+}
+
 }  // namespace gcc
 
 // =============================================================================== host side
@@ -458,10 +712,41 @@ static int fill_gather_taps(GemmGeom& g, int KH, int KW, int stride, int pad) {
   return GCC_OK;
 }
 
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = kNumSMs;
+  }
+  return g_num_sms;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
+  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess) {
+      gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
+      return GCC_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int grid = g.total_tiles < num_sms() ? g.total_tiles : num_sms();
+  conv_gemm_persistent_kernel<BLOCK_N, STAGES><<<grid, 320, smem, st>>>(g);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+// splitk_ws: optional fp32 workspace of >= N*OH*OW*round8(R) elements; when given, layers with very few pixel
+// tiles and a long contraction split K across CTAs.  NULL disables split-K.
 extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                                   const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
                                   int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
-                                  void* stream) {
+                                  float* splitk_ws, long long ws_elems, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (w_per_image && (KH != 1 || KW != 1 || stride != 1 || pad != 0 || transposed)) {
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: per-image weights need a 1x1 stride-1 conv");
@@ -477,31 +762,50 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: output channel window out of range");
     return GCC_ERR_ARG;
   }
+  if (!transposed && stride == 2 && ((H % 2) || (W % 2))) {
+    gcc_set_error(__FILE__, __LINE__, "stride-2 conv needs even H, W");
+    return GCC_ERR_ARG;
+  }
   const int BN = pick_block_n(Rp);
-  const int n_tiles = (Rp + BN - 1) / BN;
   const int Ck = Cx < Cw ? Cx : Cw;  // contraction extent (both are zero padded to their physical size)
 
+  ConvGeom2 g;
+  memset(&g, 0, sizeof(g));
+  g.n_tiles = (Rp + BN - 1) / BN;
+  g.k_chunks = (Ck + kBlockK - 1) / kBlockK;
+  g.GN = N;
+  g.w_per_image = w_per_image;
   const int classes = (transposed && stride == 2) ? 4 : 1;
+  const int os = (transposed && stride == 2) ? 2 : 1;
+  // tile geometry from the largest class grid
+  const int GH0 = (transposed && stride == 2) ? (OH + 1) / 2 : OH;
+  const int GW0 = (transposed && stride == 2) ? (OW + 1) / 2 : OW;
+  choose_tile(kBlockM, N, GH0, GW0, &g.log_wt, &g.log_ht, &g.log_nt);
+  if (w_per_image) {  // a tile must not straddle images
+    g.log_ht += g.log_nt;
+    g.log_nt = 0;
+  }
+  const int tiles_n = (N + (1 << g.log_nt) - 1) >> g.log_nt;
+  int ntap = 0, ncls = 0, max_kb = 0;
   for (int cls = 0; cls < classes; ++cls) {
-    GemmGeom g;
-    memset(&g, 0, sizeof(g));
-    int GH, GW;
-    int qh = 0, qw = 0;
+    int GH, GW, qh = 0, qw = 0;
+    const int tap_begin = ntap;
     if (!transposed) {
       GH = OH; GW = OW;
-      if (stride == 2 && ((H % 2) || (W % 2))) {
-        gcc_set_error(__FILE__, __LINE__, "stride-2 conv needs even H, W");
-        return GCC_ERR_ARG;
-      }
-      int rc = fill_gather_taps(g, KH, KW, stride, pad);
+      GemmGeom tmp;
+      int rc = fill_gather_taps(tmp, KH, KW, stride, pad);
       if (rc) return rc;
+      for (int t = 0; t < tmp.num_taps; ++t) {
+        g.tap_map[ntap] = tmp.tap_map[t]; g.tap_dh[ntap] = tmp.tap_dh[t];
+        g.tap_dw[ntap] = tmp.tap_dw[t]; g.tap_widx[ntap] = tmp.tap_widx[t];
+        ++ntap;
+      }
     } else {
       qh = cls / 2; qw = cls % 2;
       if (stride == 1) { GH = OH; GW = OW; }
       else { GH = (OH - qh + 1) / 2; GW = (OW - qw + 1) / 2; }
       if (GH <= 0 || GW <= 0) continue;
       // scatter relation: out = s*in + k - p  <=>  in = (out + p - k) / s when divisible
-      int nt = 0;
       for (int kh = 0; kh < KH; ++kh)
         for (int kw = 0; kw < KW; ++kw) {
           int dh, dw;
@@ -511,63 +815,86 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
             dh = floordiv(qh + pad - kh, 2);
             dw = floordiv(qw + pad - kw, 2);
           }
-          g.tap_map[nt] = 0;
-          g.tap_dh[nt] = (short)dh;
-          g.tap_dw[nt] = (short)dw;
-          g.tap_widx[nt] = (short)(kh * KW + kw);
-          ++nt;
+          g.tap_map[ntap] = 0; g.tap_dh[ntap] = (short)dh; g.tap_dw[ntap] = (short)dw;
+          g.tap_widx[ntap] = (short)(kh * KW + kw);
+          ++ntap;
         }
-      g.num_taps = nt;
+      if (ntap == tap_begin) {
+        gcc_set_error(__FILE__, __LINE__, "transposed conv class with no taps is not supported");
+        return GCC_ERR_ARG;
+      }
     }
-    g.k_chunks = (Ck + kBlockK - 1) / kBlockK;
-    g.GN = N; g.GH = GH; g.GW = GW;
-    choose_tile(kBlockM, N, GH, GW, &g.log_wt, &g.log_ht, &g.log_nt);
-    g.w_per_image = w_per_image;
-    if (w_per_image) {  // a tile must not straddle images
-      g.log_ht += g.log_nt;
-      g.log_nt = 0;
-    }
-    g.tiles_w = (GW + (1 << g.log_wt) - 1) >> g.log_wt;
-    g.tiles_h = (GH + (1 << g.log_ht) - 1) >> g.log_ht;
-    g.tiles_n = (N + (1 << g.log_nt) - 1) >> g.log_nt;
-    const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+    g.cls_tap_begin[ncls] = tap_begin;
+    g.cls_GH[ncls] = GH;
+    g.cls_GW[ncls] = GW;
+    g.cls_tiles_w[ncls] = (GW + (1 << g.log_wt) - 1) >> g.log_wt;
+    g.cls_tiles_h[ncls] = (GH + (1 << g.log_ht) - 1) >> g.log_ht;
+    g.cls_mtile_begin[ncls + 1] = g.cls_mtile_begin[ncls] + g.cls_tiles_w[ncls] * g.cls_tiles_h[ncls] * tiles_n;
+    g.cls_out_off[ncls] = ((long long)qh * OW + qw) * Cy;
+    g.cls_part_off[ncls] = ((long long)qh * OW + qw) * Rp;
+    const int kb = (ntap - tap_begin) * g.k_chunks;
+    if (kb > max_kb) max_kb = kb;
+    ++ncls;
+  }
+  g.cls_tap_begin[ncls] = ntap;
+  g.num_classes = ncls;
+  const int m_total = g.cls_mtile_begin[ncls];
 
-    int rc = 0;
-    if (!transposed && stride == 2) {
-      for (int ph = 0; ph < 2; ++ph)
-        for (int pw = 0; pw < 2; ++pw)
-          rc |= make_act_map(&g.a_maps[ph * 2 + pw], x, N, H, W, Cx, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt);
-    } else {
-      rc |= make_act_map(&g.a_maps[0], x, N, H, W, Cx, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
-    }
-    {
-      uint64_t dims[3] = {(uint64_t)Cw, (uint64_t)(w_per_image ? N : T), (uint64_t)R};
-      uint64_t strides[2] = {(uint64_t)Cw * 2 * (w_per_image ? R : 1), (uint64_t)Cw * 2 * (w_per_image ? 1 : T)};
-      uint32_t box[3] = {64u, 1u, (uint32_t)BN};
-      rc |= gcc_make_tmap_bf16(&g.b_map, w, 3, dims, strides, box);
-    }
-    if (rc) return GCC_ERR_DRIVER;
+  int rc = 0;
+  if (!transposed && stride == 2) {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        rc |= make_act_map(&g.a_maps[ph * 2 + pw], x, N, H, W, Cx, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt);
+  } else {
+    rc |= make_act_map(&g.a_maps[0], x, N, H, W, Cx, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Cw, (uint64_t)(w_per_image ? N : T), (uint64_t)R};
+    uint64_t strides[2] = {(uint64_t)Cw * 2 * (w_per_image ? R : 1), (uint64_t)Cw * 2 * (w_per_image ? 1 : T)};
+    uint32_t box[3] = {64u, 1u, (uint32_t)BN};
+    rc |= gcc_make_tmap_bf16(&g.b_map, w, 3, dims, strides, box);
+  }
+  if (rc) return GCC_ERR_DRIVER;
 
-    bf16* yb = reinterpret_cast<bf16*>(y) + y_coff;
-    const int os = (transposed && stride == 2) ? 2 : 1;
-    g.out = yb + ((long long)qh * OW + qw) * Cy;
-    g.out_sn = (long long)OH * OW * Cy;
-    g.out_sh = (long long)OW * Cy * os;
-    g.out_sw = (long long)Cy * os;
-    g.out_cols = Rp;
-    g.bias_cols = R;
-    g.bias = bias;
-    g.act = act;
-    g.slope = slope;
+  g.out = reinterpret_cast<bf16*>(y) + y_coff;
+  g.out_sn = (long long)OH * OW * Cy;
+  g.out_sh = (long long)OW * Cy * os;
+  g.out_sw = (long long)Cy * os;
+  g.out_cols = Rp;
+  g.bias_cols = R;
+  g.bias = bias;
+  g.act = act;
+  g.slope = slope;
 
-    if (g.num_taps == 0) {
-      gcc_set_error(__FILE__, __LINE__, "transposed conv class with no taps is not supported");
-      return GCC_ERR_ARG;
+  // split-K only when the tile count leaves most SMs idle and K is long
+  g.k_splits = 1;
+  const long long out_elems = (long long)N * OH * OW * Rp;
+  const int base_tiles = m_total * g.n_tiles;
+  if (splitk_ws != nullptr && ws_elems >= out_elems && base_tiles * 2 <= num_sms() && max_kb >= 8) {
+    int ks = num_sms() / base_tiles;
+    if (ks > max_kb / 2) ks = max_kb / 2;
+    if (ks > 64) ks = 64;
+    if (ks > 1) {
+      g.k_splits = ks;
+      g.partial = splitk_ws;
+      g.part_sn = (long long)OH * OW * Rp;
+      g.part_sh = (long long)OW * Rp * os;
+      g.part_sw = (long long)Rp * os;
+      if (cudaMemsetAsync(splitk_ws, 0, sizeof(float) * out_elems, st) != cudaSuccess) return GCC_ERR_CUDA;
     }
-    if (BN == 64) rc = launch_conv_gemm<64, 4>(g, m_tiles, n_tiles, st);
-    else if (BN == 128) rc = launch_conv_gemm<128, 3>(g, m_tiles, n_tiles, st);
-    else rc = launch_conv_gemm<256, 4>(g, m_tiles, n_tiles, st);
-    if (rc) return rc;
+  }
+  g.total_tiles = base_tiles * g.k_splits;
+
+  if (BN == 64) rc = launch_conv_persistent<64, 8>(g, st);
+  else if (BN == 128) rc = launch_conv_persistent<128, 6>(g, st);
+  else rc = launch_conv_persistent<256, 4>(g, st);
+  if (rc) return rc;
+  if (g.k_splits > 1) {
+    long long b = (out_elems + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    splitk_finalize_kernel<<<(unsigned)b, 256, 0, st>>>(splitk_ws, reinterpret_cast<bf16*>(y), (long long)N * OH * OW, Rp,
+                                                       Cy, y_coff, R, bias, act, slope);
+    GCC_CHECK_LAUNCH();
   }
   return GCC_OK;
 }

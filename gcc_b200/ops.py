@@ -39,6 +39,16 @@ def _window(t):
     return t, t.shape[3]
 
 
+def _splitk_ws(n, oh, ow, rows, device):
+    """fp32 split-K scratch for layers with very few output pixels (U-Net inner levels); (ptr, elems)."""
+    pix = n * oh * ow
+    if pix > 16384:
+        return None, 0, None
+    elems = pix * rp8(rows)
+    ws = torch.empty(elems, dtype=torch.float32, device=device)
+    return ws.data_ptr(), elems, ws
+
+
 def conv_out_hw(h, w, k, stride, pad, transposed, outpad=0):
     if not transposed:
         return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
@@ -61,9 +71,10 @@ class ConvFn(torch.autograd.Function):
         pk = layer.packs
         wp = pk.direct if not tr else pk.transposed  # [cout][T][cin_p]
         epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
+        wsp, wse, _keep = _splitk_ws(n, oh, ow, layer.cout, x.device)
         call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), layer.cout, layer.k * layer.k,
              wp.shape[2], None if bias is None else bias.data_ptr(), y.data_ptr(), oh, ow, cop, 0, tr, layer.k,
-             layer.k, layer.stride, layer.pad, epi, slope, 0, _st())
+             layer.k, layer.stride, layer.pad, epi, slope, 0, wsp, wse, _st())
         ctx.layer, ctx.act, ctx.slope = layer, act, slope
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, y if act != ACT_NONE else None)
@@ -91,9 +102,10 @@ class ConvFn(torch.autograd.Function):
             pk = layer.packs
             wp = pk.transposed if not tr else pk.direct  # [cin][T][cout_p]
             dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=x.device)
+            wsp, wse, _keep = _splitk_ws(n, h, w, layer.cin, x.device)
             call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin, T, wp.shape[2], None,
                  dx.data_ptr(), h, w, dx.shape[3], 0, 0 if tr else 1, layer.k, layer.k, layer.stride, layer.pad, 0,
-                 0.0, 0, st)
+                 0.0, 0, wsp, wse, st)
             if dx.shape[3] != cx:
                 raise _lib.GccB200Error("conv input channel padding mismatch")
         if ctx.needs_input_grad[1]:
@@ -132,14 +144,14 @@ class ColConvFn(torch.autograd.Function):
             y = torch.empty(n, oh, ow, cop, dtype=torch.bfloat16, device=x.device)
             epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
             call("gcc_conv_gemm_bf16", xcol.data_ptr(), n, oh, ow, 128, pk.direct.data_ptr(), layer.cout, 1, 128, bp,
-                 y.data_ptr(), oh, ow, cop, 0, 0, 1, 1, 1, 0, epi, slope, 0, st)
+                 y.data_ptr(), oh, ow, cop, 0, 0, 1, 1, 1, 0, epi, slope, 0, None, 0, st)
             saved = xcol
         else:
             oh, ow = 2 * h, 2 * w
             ycol = torch.empty(n, h, w, 128, dtype=torch.bfloat16, device=x.device)
             wp = pk.transposed  # [cout][16][cin_p] viewed as [cout*16][1][cin_p]
             call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), layer.cout * 16, 1, wp.shape[2], None,
-                 ycol.data_ptr(), h, w, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, st)
+                 ycol.data_ptr(), h, w, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
             y = torch.empty(n, oh, ow, 8, dtype=torch.bfloat16, device=x.device)
             if act not in (ACT_NONE, ACT_TANH):
                 raise _lib.GccB200Error("col-path ConvTranspose supports none/tanh epilogues")
@@ -176,7 +188,7 @@ class ColConvFn(torch.autograd.Function):
                 wp = pk.transposed  # [cin][16][cout_p] viewed as [cin*16][1][cout_p]
                 dcol = torch.empty(n, oh, ow, 128, dtype=torch.bfloat16, device=dev)
                 call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin * 16, 1,
-                     wp.shape[2], None, dcol.data_ptr(), oh, ow, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, st)
+                     wp.shape[2], None, dcol.data_ptr(), oh, ow, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
                 dx = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=dev)
                 call("gcc_col2im_k4s2_c8", dcol.data_ptr(), 128, 1, layer.cin, None, 0, dx.data_ptr(), n, h, w, st)
             if ctx.needs_input_grad[1]:
@@ -196,7 +208,7 @@ class ColConvFn(torch.autograd.Function):
                 wp = pk.direct  # [cin][16][8] viewed as [cin][1][128]
                 dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=dev)
                 call("gcc_conv_gemm_bf16", dcol.data_ptr(), n, h, w, 128, wp.data_ptr(), layer.cin, 1, 128, None,
-                     dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, st)
+                     dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
             if ctx.needs_input_grad[1]:
                 tmp = torch.empty(layer.cin, 128, dtype=torch.float32, device=dev)
                 call("gcc_wgrad_gemm_bf16", x.data_ptr(), n, h, w, cx, dcol.data_ptr(), h, w, 128, tmp.data_ptr(),
@@ -526,7 +538,7 @@ class GramRmseFn(torch.autograd.Function):
              acc.data_ptr(), m.data_ptr(), st)
         df = torch.empty_like(f)
         call("gcc_conv_gemm_bf16", f.data_ptr(), n, h, w, cp, m.data_ptr(), c, 1, cp, None, df.data_ptr(), h, w, cp, 0,
-             0, 1, 1, 1, 0, 0, 0.0, 1, st)
+             0, 1, 1, 1, 0, 0, 0.0, 1, None, 0, st)
         return df, None, None
 
 

@@ -34,10 +34,13 @@ long long gcc_launch_count(void); /* kernels launched by this library so far (ho
  *   x: [N,H,W,Cx] bf16, w: [R][T=KH*KW][Cw] bf16, y: [N,OH,OW,Cy] bf16, bias: [R] fp32 or NULL.
  *   act: 0 none, 1 leaky-relu(slope), 2 tanh.  stride in {1,2}.
  *   w_per_image=1 (1x1 only): w is [N][R][Cw], one matrix per image (Gram-loss backward dF = F M).
+ *   splitk_ws: optional fp32 scratch of >= N*OH*OW*round8(R) elements enabling split-K for layers with very
+ *   few output pixels (U-Net inner levels); NULL disables it.
  */
 int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                        const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
-                       int KW, int stride, int pad, int act, float slope, int w_per_image, void* stream);
+                       int KW, int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
+                       long long ws_elems, void* stream);
 /* gcc_wgrad_gemm_bf16: dw[b][r][kh*KW+kw][c] (+)= scale * sum_{n,oy,ox} p[n,oy,ox,r] * q[n,stride*oy+kh-pad,stride*ox+kw-pad,c]
  *   weight gradient of Conv2d (p = dy, q = x) and ConvTranspose2d (p = x, q = dy); with batched=1,
  *   KH=KW=1, p == q it is the per-sample Gram matrix f f^T (models/Pix2Pix.py:733-740).
@@ -48,7 +51,8 @@ int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void
 /* CUDA-core cross-checks with identical signatures (tests only). */
 int gcc_conv_direct_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                          const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
-                         int KW, int stride, int pad, int act, float slope, int w_per_image, void* stream);
+                         int KW, int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
+                         long long ws_elems, void* stream);
 int gcc_wgrad_direct_bf16(const void* p, int N, int OH, int OW, int Cp, const void* q, int H, int W, int Cq,
                           float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched, int accumulate,
                           float scale, void* stream);
