@@ -462,6 +462,68 @@ __global__ void unpad_wgrad_c8_kernel(const float* __restrict__ tmp, float* __re
   }
 }
 
+// ---- k4 s1 p1 Conv2d with <= 8 OUTPUT channels (PatchGAN's 1-channel logits head, Pix2Pix.py:300,343) --------
+// fprop: ycol[pix_in, co*16+tap] = x[pix_in,:] . w[co,tap,:] is one 1x1 GEMM that reads x ONCE (instead of once
+// per tap); the 16 partial dot products are then folded:  y[n,oy,ox,co] = b[co] + sum_taps ycol[n,oy+kh-1,ox+kw-1,.]
+__global__ void fold_k4s1_kernel(const bf16* __restrict__ ycol, int Ccol, int C, const float* __restrict__ bias,
+                                 uint4* __restrict__ y, int N, int H, int W) {
+  const int OH = H - 1, OW = W - 1;  // k4 s1 p1
+  const long long total = (long long)N * OH * OW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW);
+    long long t = i / OW;
+    const int oy = (int)(t % OH);
+    const long long n = t / OH;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = (bias != nullptr && c < C) ? bias[c] : 0.f;
+    for (int kh = 0; kh < 4; ++kh) {
+      const int iy = oy + kh - 1;
+      if (iy < 0 || iy >= H) continue;
+      for (int kw = 0; kw < 4; ++kw) {
+        const int ix = ox + kw - 1;
+        if (ix < 0 || ix >= W) continue;
+        const bf16* row = ycol + ((n * H + iy) * W + ix) * (long long)Ccol;
+        for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(row[c * 16 + kh * 4 + kw]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c >= C) acc[c] = 0.f;
+    y[i] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                      pack_bf16(acc[6], acc[7]));
+  }
+}
+// backward expansion: dcol[n,iy,ix,tap*8+c] = dy[n, iy-kh+1, ix-kw+1, c]  (zero outside), dy [N,H-1,W-1,8]
+__global__ void unfold_k4s1_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dcol, int N, int H, int W) {
+  const int OH = H - 1, OW = W - 1;
+  const long long total = (long long)N * H * W * 16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i & 15);
+    long long t = i >> 4;
+    const int ix = (int)(t % W); t /= W;
+    const int iy = (int)(t % H);
+    const long long n = t / H;
+    const int oy = iy - (tap >> 2) + 1, ox = ix - (tap & 3) + 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (oy >= 0 && oy < OH && ox >= 0 && ox < OW) v = dy[(n * OH + oy) * OW + ox];
+    dcol[i] = v;
+  }
+}
+// g[c][tap][k] += tmp[tap*8 + c][k]   (c < C): weight gradient of the head back to [C][16][K]
+__global__ void unpad_wgrad_rows_kernel(const float* __restrict__ tmp, float* __restrict__ g, int C, int K) {
+  const long long total = (long long)C * 16 * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int ct = (int)(i / K);
+    const int tap = ct % 16, c = ct / 16;
+    g[i] += tmp[(long long)(tap * 8 + c) * K + k];
+  }
+}
+
 static inline int blocks_for(long long n, int per = 256) {
   long long b = (n + per - 1) / per;
   const long long cap = 148LL * 16;
@@ -633,6 +695,27 @@ extern "C" int gcc_col2im_k4s2_c8(const void* col, int Ccol, int order, int C, c
 extern "C" int gcc_unpad_wgrad_c8(const float* tmp, float* g, int R, int C, void* stream) {
   if (C > 8) { gcc_set_error(__FILE__, __LINE__, "unpad_wgrad: C must be <= 8"); return GCC_ERR_ARG; }
   unpad_wgrad_c8_kernel<<<(R * 16 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tmp, g, R, C);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+extern "C" int gcc_fold_k4s1_c8(const void* ycol, int Ccol, int C, const float* bias, void* y, int N, int H, int W,
+                                void* stream) {
+  if (C > 8 || H < 2 || W < 2) { gcc_set_error(__FILE__, __LINE__, "fold_k4s1: bad arguments"); return GCC_ERR_ARG; }
+  fold_k4s1_kernel<<<blocks_for((long long)N * (H - 1) * (W - 1)), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)ycol, Ccol, C, bias, (uint4*)y, N, H, W);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_unfold_k4s1_c8(const void* dy, void* dcol, int N, int H, int W, void* stream) {
+  unfold_k4s1_kernel<<<blocks_for((long long)N * H * W * 16), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy,
+                                                                                            (uint4*)dcol, N, H, W);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_unpad_wgrad_rows(const float* tmp, float* g, int C, int K, void* stream) {
+  if (C > 8) { gcc_set_error(__FILE__, __LINE__, "unpad_wgrad_rows: C must be <= 8"); return GCC_ERR_ARG; }
+  unpad_wgrad_rows_kernel<<<blocks_for((long long)C * 16 * K), 256, 0, (cudaStream_t)stream>>>(tmp, g, C, K);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

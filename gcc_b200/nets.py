@@ -47,6 +47,8 @@ class ConvLayer:
         # k4 s2 p1 layers whose image side has <= 8 channels run through im2col/col2im (ops.ColConvFn)
         self.colpath = (k == 4 and stride == 2 and pad == 1 and outpad == 0 and
                         ((kind == "conv" and cin <= 8) or (kind == "convT" and cout <= 8)))
+        # k4 s1 p1 convs with <= 8 output channels (PatchGAN logits head) run as a 1x1 GEMM + fold (ops.HeadConvFn)
+        self.headpath = (kind == "conv" and k == 4 and stride == 1 and pad == 1 and cout <= 8 and cin >= 64)
 
     def bind(self):
         self.weight = self.arena.params[self.wname]
@@ -54,7 +56,7 @@ class ConvLayer:
         self.packs = self.arena.packs[self.wname]
 
     def __call__(self, x, act=ACT_NONE, slope=0.2):
-        fn = ops.ColConvFn if self.colpath else ops.ConvFn
+        fn = ops.ColConvFn if self.colpath else (ops.HeadConvFn if self.headpath else ops.ConvFn)
         return fn.apply(x, self.weight, self.bias, self, act, slope)
 
 

@@ -223,6 +223,62 @@ class ColConvFn(torch.autograd.Function):
         return dx, None, None, None, None, None
 
 
+class HeadConvFn(torch.autograd.Function):
+    """k4 s1 p1 Conv2d with <= 8 output channels (the PatchGAN logits head): one 1x1 GEMM over the input
+    (read once) producing the 16 per-tap partial dot products, then a fold (see elementwise.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, act, slope):
+        _check(x)
+        if act != ACT_NONE:
+            raise _lib.GccB200Error("head conv has no fused activation")
+        x = x.contiguous()
+        layer.arena.ensure_packed()
+        st = _st()
+        n, h, w, cx = x.shape
+        pk = layer.packs
+        rows = layer.cout * 16
+        ycol = torch.empty(n, h, w, rp8(rows), dtype=torch.bfloat16, device=x.device)
+        wp = pk.direct  # [cout][16][cin_p] viewed as [cout*16][1][cin_p]
+        call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), rows, 1, wp.shape[2], None, ycol.data_ptr(),
+             h, w, ycol.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
+        y = torch.empty(n, h - 1, w - 1, 8, dtype=torch.bfloat16, device=x.device)
+        call("gcc_fold_k4s1_c8", ycol.data_ptr(), ycol.shape[3], layer.cout, None if bias is None else bias.data_ptr(),
+             y.data_ptr(), n, h, w, st)
+        ctx.layer = layer
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        st = _st()
+        n, h, w, cx = x.shape
+        dev = dy.device
+        dcol = torch.empty(n, h, w, 128, dtype=torch.bfloat16, device=dev)
+        call("gcc_unfold_k4s1_c8", dy.data_ptr(), dcol.data_ptr(), n, h, w, st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            layer.arena.ensure_packed()
+            wp = layer.packs.transposed  # [cin][16][8] viewed as [cin][1][128]
+            dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=dev)
+            call("gcc_conv_gemm_bf16", dcol.data_ptr(), n, h, w, 128, wp.data_ptr(), layer.cin, 1, 128, None,
+                 dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
+        if ctx.needs_input_grad[1]:
+            tmp = torch.empty(128, layer.cin, dtype=torch.float32, device=dev)
+            call("gcc_wgrad_gemm_bf16", dcol.data_ptr(), n, h, w, 128, x.data_ptr(), h, w, cx, tmp.data_ptr(), 128,
+                 layer.cin, 1, 1, 1, 0, 0, 0, 1.0, st)
+            call("gcc_unpad_wgrad_rows", tmp.data_ptr(), layer.arena.flat_grad[layer.wname].data_ptr(), layer.cout,
+                 layer.cin, st)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = layer.arena.flat_grad[layer.bname]
+            call("gcc_bias_grad_bf16", dy.data_ptr(), n * (h - 1) * (w - 1), 8, 0, layer.cout, gb.data_ptr(), 1, st)
+        return dx, None, None, None, None, None
+
+
 class NormActFn(torch.autograd.Function):
     """[BatchNorm | InstanceNorm | identity] -> [channel gate] -> activation, with an optional second
     activation output (the U-Net's relu'd skip copy)."""

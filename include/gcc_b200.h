@@ -124,6 +124,14 @@ int gcc_col2im_k4s2_c8(const void* col, int Ccol, int order, int C, const float*
                        int H, int W, void* stream);
 int gcc_unpad_wgrad_c8(const float* tmp, float* g, int R, int C, void* stream);
 
+/* k4 s1 p1 Conv2d with <= 8 output channels (PatchGAN logits head, Pix2Pix.py:300,343): the 1x1 GEMM
+ * ycol[pix, co*16+tap] = x[pix,:].w[co,tap,:] reads x once; fold sums the 16 shifted partials (+bias) into
+ * y [N,H-1,W-1,8]; unfold builds dcol[n,iy,ix,tap*8+c] = dy[n,iy-kh+1,ix-kw+1,c] for the data/weight gradients;
+ * unpad_wgrad_rows: g[c][tap][k] += tmp[tap*8+c][k]. */
+int gcc_fold_k4s1_c8(const void* ycol, int Ccol, int C, const float* bias, void* y, int N, int H, int W, void* stream);
+int gcc_unfold_k4s1_c8(const void* dy, void* dcol, int N, int H, int W, void* stream);
+int gcc_unpad_wgrad_rows(const float* tmp, float* g, int C, int K, void* stream);
+
 /* ---- loss reductions (loss.cu) ---- */
 /* GANLoss (models/GANLoss.py:38-59). mode: 0 hinge, 1 lsgan, 2 vanilla, 3 wgangp.
  * kind: 0 D-real, 1 D-fake, 2 G.  out is an fp32 device scalar that the caller zeroes. */

@@ -68,6 +68,8 @@ CONV_CASES = [
     (3, 16, 16, 6, 128, 4, 2, 1, 0, 0),   # col path: first conv of D
     (2, 16, 16, 128, 3, 4, 2, 1, 1, 0),   # col path (col2im): last ConvTranspose of the U-Net
     (2, 8, 8, 45, 3, 4, 2, 1, 1, 0),
+    (3, 31, 31, 256, 1, 4, 1, 1, 0, 0),   # head path: 1x1 GEMM + fold
+    (2, 15, 17, 72, 3, 4, 1, 1, 0, 0),
 ]
 
 
