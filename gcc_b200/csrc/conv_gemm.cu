@@ -373,6 +373,7 @@ struct ConvGeom2 {
   float slope;
   float* partial;
   long long part_sn, part_sh, part_sw;
+  int debug;  // bit0: skip global stores, bit1: skip TMEM loads (timing experiments only)
 };
 
 struct TileInfo {
@@ -423,6 +424,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   uint64_t* tmem_full_bar = empty_bar + STAGES;    // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  constexpr int kStagePitch = 80;  // 64 B of data + 16 B pad per staged row (spreads banks)
+  uint8_t* stage_base = smem + STAGES * kStageBytes + 256;             // 8 warps x 32 rows x 80 B
+  float* bias_base = reinterpret_cast<float*>(stage_base + 8 * 32 * kStagePitch);  // 8 warps x 32 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -517,36 +521,55 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
       if (p.k_splits == 1) {
+        // Each thread owns one pixel row; its 32-column chunk (64 B) is staged in warp-private shared memory and
+        // written out with 4 lanes per row, so every store instruction covers whole 32-byte sectors (8 rows x
+        // 64 contiguous bytes) instead of 32 half-written sectors 1 row apart.
         bf16* orow = p.out + p.cls_out_off[t.cls] + (long long)n * p.out_sn + (long long)a * p.out_sh +
                      (long long)b * p.out_sw;
+        const unsigned long long orow_u = reinterpret_cast<unsigned long long>(orow);
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        uint8_t* stage = stage_base + (warp - 2) * (32 * kStagePitch);
+        float* sbias = bias_base + (warp - 2) * 32;
 #pragma unroll 1
         for (int c0 = half * kHalf; c0 < (half + 1) * kHalf; c0 += 32) {
           const int col0 = t.n_tile * BLOCK_N + c0;
           if (col0 >= p.out_cols) break;  // warp-uniform
           uint32_t v[32];
-          tmem_ld_32x32(tmem_d + c0, v);
-          tmem_ld_wait();
-          if (valid) {
+          if (!(p.debug & 2)) {
+            tmem_ld_32x32(tmem_d + c0, v);
+          } else {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col < p.out_cols) {
-                float f[8];
+            for (int i = 0; i < 32; ++i) v[i] = 0;
+          }
+          const float bl = (p.bias != nullptr && col0 + lane < p.bias_cols) ? __ldg(p.bias + col0 + lane) : 0.f;
+          sbias[lane] = bl;
+          if (!(p.debug & 2)) tmem_ld_wait();
+          __syncwarp();
+          uint4* srow = reinterpret_cast<uint4*>(stage + lane * kStagePitch);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float x = __uint_as_float(v[g * 8 + i]);
-                  if (p.bias != nullptr && col + i < p.bias_cols) x += __ldg(p.bias + col + i);
-                  f[i] = apply_act(x, p.act, p.slope);
-                }
-                uint4 o;
-                o.x = pack_bf16(f[0], f[1]);
-                o.y = pack_bf16(f[2], f[3]);
-                o.z = pack_bf16(f[4], f[5]);
-                o.w = pack_bf16(f[6], f[7]);
-                *reinterpret_cast<uint4*>(orow + col) = o;
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              f[i] = apply_act(__uint_as_float(v[g * 8 + i]) + sbias[g * 8 + i], p.act, p.slope);
+            srow[g] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                 pack_bf16(f[6], f[7]));
+          }
+          __syncwarp();
+          if (!(p.debug & 1)) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int piece = it * 32 + lane;
+              const int rr = piece >> 2, ch = piece & 3;
+              const unsigned long long pr = __shfl_sync(0xffffffffu, orow_u, rr);
+              const int col = col0 + ch * 8;
+              if (((vmask >> rr) & 1u) && col < p.out_cols) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * kStagePitch + ch * 16);
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(pr) + col) = val;
               }
             }
           }
+          __syncwarp();
         }
       } else {
         float* prow = p.partial + p.cls_part_off[t.cls] + (long long)n * p.part_sn + (long long)a * p.part_sh +
@@ -712,6 +735,8 @@ static int fill_gather_taps(GemmGeom& g, int KH, int KW, int stride, int pad) {
   return GCC_OK;
 }
 
+static int g_debug_flags = 0;
+extern "C" void gcc_debug_set_flags(int f) { g_debug_flags = f; }
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -725,7 +750,7 @@ static int num_sms() {
 
 template <int BLOCK_N, int STAGES>
 static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
-  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + 1024 + 256;
+  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + 1024 + 256 + 8 * 32 * 80 + 8 * 32 * 4;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -884,6 +909,7 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
     }
   }
   g.total_tiles = base_tiles * g.k_splits;
+  g.debug = g_debug_flags;
 
   if (BN == 64) rc = launch_conv_persistent<64, 8>(g, st);
   else if (BN == 128) rc = launch_conv_persistent<128, 6>(g, st);

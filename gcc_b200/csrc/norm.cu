@@ -125,42 +125,60 @@ __device__ __forceinline__ void channel_affine(const NormArgs& a, int n, int c, 
 }
 
 // -------------------------------------------------------------------------------------- forward
-// Per-channel coefficients are computed once per block into shared memory (p, q, m):
+// Thread layout as in the statistics kernel: thread = (channel group g of 8, pixel lane); the 8 channels'
+// coefficients live in registers for the whole kernel and the pixel loop has no integer division:
 //   y = act(x*p + q) * m   with p = rstd*gamma*mask, q = (beta - mean*rstd*gamma)*mask, m = 1
 //   (gate_after: p, q without the mask and m = mask).  grid.y = sample index for instance norm.
-__global__ void norm_apply_kernel(NormArgs a, int nimg, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp,
+__global__ void norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp,
                                   int y2_coff, int act2, float* running_mean, float* running_var, float momentum) {
-  extern __shared__ float coef[];  // [3][Cp]
-  float* cp = coef;
-  float* cq = coef + a.Cp;
-  float* cm = coef + 2 * a.Cp;
+  const int tid = threadIdx.x;
+  const int g = tid % a.G, lane = tid / a.G;
   const int n = blockIdx.y;
-  for (int c = threadIdx.x; c < a.Cp; c += blockDim.x) {
-    float mean, rstd, gam, bet, mask;
-    channel_affine(a, n, c, mean, rstd, gam, bet, mask);
-    const float mk = a.gate_after ? 1.f : mask;
-    cp[c] = rstd * gam * mk;
-    cq[c] = (bet - mean * rstd * gam) * mk;
-    cm[c] = a.gate_after ? mask : 1.f;
-  }
-  __syncthreads();
-  const long long pix0 = a.per_sample ? (long long)n * a.npix : 0;
-  const long long nvec = a.npix * a.G;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % a.G);
-    const long long pix = pix0 + i / a.G;
-    const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
-    Vec8 o, o2;
+  if (lane < lanes) {
+    float cp[8], cq[8], cm[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = g * 8 + k;
-      const float z = xv.v[k] * cp[c] + cq[c];
-      o.v[k] = act_fwd(z, a.act, a.slope) * cm[c];
-      o2.v[k] = act_fwd(z, act2, a.slope) * cm[c];
+      float mean, rstd, gam, bet, mask;
+      channel_affine(a, n, g * 8 + k, mean, rstd, gam, bet, mask);
+      const float mk = a.gate_after ? 1.f : mask;
+      cp[k] = rstd * gam * mk;
+      cq[k] = (bet - mean * rstd * gam) * mk;
+      cm[k] = a.gate_after ? mask : 1.f;
     }
-    if (y != nullptr) store8(y + pix * a.Cp + g * 8, o);
-    if (y2 != nullptr) store8(y2 + pix * y2_Cp + y2_coff + g * 8, o2);
+    const long long pix0 = a.per_sample ? (long long)n * a.npix : 0;
+    const long long step = (long long)gridDim.x * lanes;
+    const bf16* xb = a.x + pix0 * a.Cp + g * 8;
+    bf16* yb = y ? y + pix0 * a.Cp + g * 8 : nullptr;
+    bf16* y2b = y2 ? y2 + pix0 * y2_Cp + y2_coff + g * 8 : nullptr;
+    long long p = (long long)blockIdx.x * lanes + lane;
+    // two pixels per iteration: two independent 16-byte loads in flight per thread
+    for (; p + step < a.npix; p += 2 * step) {
+      const Vec8 x0 = load8(xb + p * a.Cp);
+      const Vec8 x1 = load8(xb + (p + step) * a.Cp);
+      Vec8 o0, o1, s0, s1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z0 = x0.v[k] * cp[k] + cq[k], z1 = x1.v[k] * cp[k] + cq[k];
+        o0.v[k] = act_fwd(z0, a.act, a.slope) * cm[k];
+        o1.v[k] = act_fwd(z1, a.act, a.slope) * cm[k];
+        s0.v[k] = act_fwd(z0, act2, a.slope) * cm[k];
+        s1.v[k] = act_fwd(z1, act2, a.slope) * cm[k];
+      }
+      if (yb) { store8(yb + p * a.Cp, o0); store8(yb + (p + step) * a.Cp, o1); }
+      if (y2b) { store8(y2b + p * y2_Cp, s0); store8(y2b + (p + step) * y2_Cp, s1); }
+    }
+    for (; p < a.npix; p += step) {
+      const Vec8 x0 = load8(xb + p * a.Cp);
+      Vec8 o0, s0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z0 = x0.v[k] * cp[k] + cq[k];
+        o0.v[k] = act_fwd(z0, a.act, a.slope) * cm[k];
+        s0.v[k] = act_fwd(z0, act2, a.slope) * cm[k];
+      }
+      if (yb) store8(yb + p * a.Cp, o0);
+      if (y2b) store8(y2b + p * y2_Cp, s0);
+    }
   }
   // running statistics (train-mode BatchNorm2d side effect; momentum 0.1, unbiased variance)
   if (running_mean != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && a.sums != nullptr) {
@@ -267,59 +285,57 @@ __global__ void norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __rest
 }
 
 // dx = gamma*rstd*mask * (dg - (S1 + xhat*S2)/M)   [norm]   or   dx = mask*dg [identity]
-// rewritten with per-channel shared-memory coefficients: gg = x*p + q, dx = c1*dg - c2 - c3*x.
+// with per-thread register coefficients: gg = x*p + q, dx = c1*dg - c2 - c3*x  (thread = channel group x lane).
 // block (0,0) also accumulates dgamma += mask*S2, dbeta += mask*S1, dalpha += gamma*S2 + beta*S1 (summed over n).
-__global__ void norm_bwd_apply_kernel(NormArgs a, int nimg, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
-                                      const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
+__global__ void norm_bwd_apply_kernel(NormArgs a, int nimg, int lanes, const bf16* __restrict__ dy, int dy_Cp,
+                                      int dy_coff, const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
                                       const float* __restrict__ red, bf16* __restrict__ dx, float* dgamma,
                                       float* dbeta, float* dalpha) {
-  extern __shared__ float coef[];  // [5][Cp]
-  float* cp = coef;
-  float* cq = coef + a.Cp;
-  float* c1 = coef + 2 * a.Cp;
-  float* c2 = coef + 3 * a.Cp;
-  float* c3 = coef + 4 * a.Cp;
+  const int tid = threadIdx.x;
+  const int g = tid % a.G, lane = tid / a.G;
   const int n = blockIdx.y;
   const float invM = 1.f / (float)a.npix;
-  if (dx != nullptr) {
+  if (dx != nullptr && lane < lanes) {
     const float* rb = red + (long long)n * 2 * a.Cp;
-    for (int c = threadIdx.x; c < a.Cp; c += blockDim.x) {
+    float cp[8], cq[8], c1[8], c2[8], c3[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g * 8 + k;
       float mean, rstd, gam, bet, mask;
       channel_affine(a, n, c, mean, rstd, gam, bet, mask);
       const float mk = a.gate_after ? 1.f : mask;
-      cp[c] = rstd * gam * mk;
-      cq[c] = (bet - mean * rstd * gam) * mk;
+      cp[k] = rstd * gam * mk;
+      cq[k] = (bet - mean * rstd * gam) * mk;
       const float k1 = gam * rstd * mask;
-      c1[c] = (c < a.C) ? k1 : 0.f;
+      c1[k] = (c < a.C) ? k1 : 0.f;
       if (a.sums != nullptr && c < a.C) {
-        c2[c] = k1 * invM * (rb[c] - rb[a.Cp + c] * rstd * mean);
-        c3[c] = k1 * invM * rb[a.Cp + c] * rstd;
+        c2[k] = k1 * invM * (rb[c] - rb[a.Cp + c] * rstd * mean);
+        c3[k] = k1 * invM * rb[a.Cp + c] * rstd;
       } else {
-        c2[c] = 0.f;
-        c3[c] = 0.f;
+        c2[k] = 0.f;
+        c3[k] = 0.f;
       }
     }
-    __syncthreads();
     const long long pix0 = a.per_sample ? (long long)n * a.npix : 0;
-    const long long nvec = a.npix * a.G;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
-         i += (long long)gridDim.x * blockDim.x) {
-      const int g = (int)(i % a.G);
-      const long long pix = pix0 + i / a.G;
-      const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
+    const long long step = (long long)gridDim.x * lanes;
+    const bf16* xb = a.x + pix0 * a.Cp + g * 8;
+    const bf16* d1b = dy ? dy + pix0 * dy_Cp + dy_coff + g * 8 : nullptr;
+    const bf16* d2b = dy2 ? dy2 + pix0 * dy2_Cp + dy2_coff + g * 8 : nullptr;
+    bf16* ob = dx + pix0 * a.Cp + g * 8;
+    for (long long p = (long long)blockIdx.x * lanes + lane; p < a.npix; p += step) {
+      const Vec8 xv = load8(xb + p * a.Cp);
       Vec8 d1, d2, o;
-      if (dy != nullptr) d1 = load8(dy + pix * dy_Cp + dy_coff + g * 8);
-      if (dy2 != nullptr) d2 = load8(dy2 + pix * dy2_Cp + dy2_coff + g * 8);
+      if (d1b) d1 = load8(d1b + p * dy_Cp);
+      if (d2b) d2 = load8(d2b + p * dy2_Cp);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int c = g * 8 + k;
-        const float gg = xv.v[k] * cp[c] + cq[c];
+        const float gg = xv.v[k] * cp[k] + cq[k];
         float dg = 0.f;
-        if (dy != nullptr) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
-        if (dy2 != nullptr) dg += d2.v[k] * act_grad(gg, act2, a.slope);
-        o.v[k] = c1[c] * dg - c2[c] - c3[c] * xv.v[k];
+        if (d1b) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
+        if (d2b) dg += d2.v[k] * act_grad(gg, act2, a.slope);
+        o.v[k] = c1[k] * dg - c2[k] - c3[k] * xv.v[k];
       }
-      store8(dx + pix * a.Cp + g * 8, o);
+      store8(ob + p * a.Cp, o);
     }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr || dalpha != nullptr)) {
@@ -374,9 +390,9 @@ static int fill_args(NormArgs& a, const void* x, int N, long long HW, int Cp, in
   return GCC_OK;
 }
 
-// blocks per statistics group so that the whole grid stays around 16 CTAs per SM
-static int group_blocks(long long nvec_per_group, int groups) {
-  long long b = (nvec_per_group + 255) / 256;
+// blocks for a (group, lane) kernel: each thread visits >= `per` pixels, whole grid <= ~16 CTAs per SM
+static int lane_blocks(long long npix, int lanes, int groups, int per) {
+  long long b = (npix + (long long)lanes * per * 4 - 1) / ((long long)lanes * per * 4);
   long long cap = (148LL * 16 + groups - 1) / groups;
   if (cap < 1) cap = 1;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -403,7 +419,7 @@ extern "C" int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, i
   int lanes;
   const int threads = stats_threads(G, &lanes);
   long long bx = (npix + lanes * 8 - 1) / (lanes * 8);
-  const long long cap = (148LL * 8 + groups - 1) / groups;
+  const long long cap = (148LL * 16 + groups - 1) / groups;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   norm_stats_kernel<<<dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * G * 16, st>>>(
@@ -426,10 +442,11 @@ extern "C" int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, 
     return GCC_ERR_ARG;
   }
   const int groups = per_sample ? N : 1;
-  const long long nvec = a.npix * a.G;
-  const int bx = group_blocks(nvec, groups);
-  norm_apply_kernel<<<dim3(bx, groups), 256, sizeof(float) * 3 * Cp, st>>>(a, N, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff,
-                                                                          act2, running_mean, running_var, momentum);
+  int lanes;
+  const int threads = stats_threads(a.G, &lanes);
+  const int bx = lane_blocks(a.npix, lanes, groups, 2);
+  norm_apply_kernel<<<dim3(bx, groups), threads, 0, st>>>(a, lanes, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff, act2,
+                                                         running_mean, running_var, momentum);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -471,18 +488,19 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
     int lanes;
     const int threads = stats_threads(a.G, &lanes);
     long long bx = (a.npix + lanes * 8 - 1) / (lanes * 8);
-    const long long cap = (148LL * 8 + groups - 1) / groups;
+    const long long cap = (148LL * 16 + groups - 1) / groups;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     norm_bwd_reduce_kernel<<<dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st>>>(
         a, lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
     GCC_CHECK_LAUNCH();
   }
-  const long long nvec = a.npix * a.G;
-  const int bx = dx ? group_blocks(nvec, groups) : 1;
-  norm_bwd_apply_kernel<<<dim3(bx, dx ? groups : 1), 256, sizeof(float) * 5 * Cp, st>>>(
-      a, N, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, (bf16*)dx, dgamma, dbeta,
-      dalpha);
+  int alanes;
+  const int athreads = stats_threads(a.G, &alanes);
+  const int bx = dx ? lane_blocks(a.npix, alanes, groups, 1) : 1;
+  norm_bwd_apply_kernel<<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
+      a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, (bf16*)dx, dgamma,
+      dbeta, dalpha);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

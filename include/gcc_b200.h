@@ -57,6 +57,7 @@ int gcc_wgrad_direct_bf16(const void* p, int N, int OH, int OW, int Cp, const vo
                           float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched, int accumulate,
                           float scale, void* stream);
 void gcc_debug_force_block_n(int bn);
+void gcc_debug_set_flags(int f); /* timing experiments: bit0 skip conv epilogue stores, bit1 skip TMEM loads */
 
 /* ---- norm / gate / activation blocks (norm.cu) ----
  * One block = [BatchNorm2d | InstanceNorm2d | identity] -> [DifferentiableOP gate] -> [(Leaky)ReLU]
