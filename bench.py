@@ -41,7 +41,7 @@ def parse_args():
     p.add_argument("--skip_cpu_baseline", action="store_true")
     p.add_argument("--skip_e2e", action="store_true", help="profiling runs only")
     p.add_argument("--skip_roofline", action="store_true", help="profiling runs only")
-    p.add_argument("--graph", type=int, default=0, help="reserved")
+    p.add_argument("--graph", type=int, default=0, help="1: capture the whole iteration in a CUDA graph and replay it")
     return p.parse_args()
 
 
@@ -233,7 +233,12 @@ def run_b200(args):
             for _ in range(nbatch)]
     devb = [{k: v.cuda() for k, v in h.items()} for h in host]
 
+    graphed = None
+
     def step(d, read_losses):
+        if graphed is not None:
+            graphed.run(d)
+            return model.get_current_losses() if read_losses else None
         model.set_input({"A": d["A"], "B": d["B"], "A_paths": "", "B_paths": ""})
         model.optimize_parameters()
         model.set_input({"A": d["vA"], "B": d["vB"], "A_paths": "", "B_paths": ""})
@@ -266,9 +271,19 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # sampled from the warm-up on: the GPU is under the same load as in the timed region
+    launches_per_step = None
+    if args.graph:
+        from gcc_b200.graph import GraphedIteration
+        step(devb[0], False)
+        l0 = _lib.lib().gcc_launch_count()
+        step(devb[1], False)
+        launches_per_step = _lib.lib().gcc_launch_count() - l0  # the captured graph replays exactly these launches
+        graphed = GraphedIteration(model, B).capture(devb[0], warmup=1)
     for i in range(args.warmup):
         step(devb[i % nbatch], False)
     ms, launches = timed(args.steps, devb, False)
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     if args.skip_e2e:
         ms_e2e = float("nan")
@@ -292,6 +307,7 @@ def run_b200(args):
         "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (activations of 15 net passes at batch %d, several GB) >> 126 MB L2; "
                          "two alternating input batches" % B,
+                   "cuda_graph": bool(args.graph),
                    "algorithmic_gmac_per_image": gmacs,
                    "step_tensor_tflops_per_gpu": step_tflops,
                    "step_frac_of_sustained_bf16_peak": step_tflops / pk["bf16_sustained"]},

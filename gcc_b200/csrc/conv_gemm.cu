@@ -974,8 +974,9 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
   const int total_pb = g.tiles_w * g.tiles_h * (batched ? 1 : g.tiles_n);
   const int base_ctas = r_tiles * c_tiles * g.num_taps * (batched ? N : 1);
   int splits = 1;
-  // aim for >= 2 waves of CTAs while keeping >= 8 pixel blocks per CTA
-  while (base_ctas * splits < 2 * kNumSMs && total_pb / (splits * 2) >= 8) splits *= 2;
+  // fill the machine (~2 CTAs per SM) but keep >= 16 pixel blocks per CTA: every split adds a full tile of
+  // fp32 atomics to the same addresses
+  while (base_ctas * splits * 2 <= 2 * kNumSMs && total_pb / (splits * 2) >= 16) splits *= 2;
   g.splits = splits;
   g.batched = batched;
   g.atomic_out = (splits > 1 || accumulate) ? 1 : 0;

@@ -101,21 +101,33 @@ __global__ void diff_reduce_bf16_kernel(const bf16* __restrict__ a, const bf16* 
 }
 // mode 0 (L1 mean):      da = gout * sign(a-b) * inv_count
 // mode 1 (RMSE = sqrt(mean sq)): da = gout * (a-b) * inv_count / rmse,  rmse = sqrt(*msq)
+// one thread per 8-channel vector (Cp % 8 == 0); the pad-channel test needs no division when C == Cp
 __global__ void diff_bwd_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long npix, int Cp,
                                      int C, int mode, float inv_count, const float* __restrict__ gout,
                                      const float* __restrict__ msq, bf16* __restrict__ da) {
   float go = *gout * inv_count;
   if (mode == 1) go /= fmaxf(sqrtf(*msq), 1e-20f);
-  const long long total = npix * Cp;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+  const int G = Cp / 8;
+  const long long nvec = npix * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % Cp);
-    float r = 0.f;
-    if (c < C) {
-      const float d = __bfloat162float(a[i]) - __bfloat162float(b[i]);
-      r = mode ? d * go : (d > 0.f ? go : (d < 0.f ? -go : 0.f));
+    const int c0 = (C == Cp) ? 0 : (int)(i % G) * 8;
+    const uint4 u = reinterpret_cast<const uint4*>(a)[i];
+    const uint4 v = reinterpret_cast<const uint4*>(b)[i];
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, vw[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float d0 = bf16_lo(uw[k]) - bf16_lo(vw[k]), d1 = bf16_hi(uw[k]) - bf16_hi(vw[k]);
+      float r0 = mode ? d0 * go : (d0 > 0.f ? go : (d0 < 0.f ? -go : 0.f));
+      float r1 = mode ? d1 * go : (d1 > 0.f ? go : (d1 < 0.f ? -go : 0.f));
+      if (C != Cp) {
+        if (c0 + 2 * k >= C) r0 = 0.f;
+        if (c0 + 2 * k + 1 >= C) r1 = 0.f;
+      }
+      o[k] = pack_bf16(r0, r1);
     }
-    da[i] = __float2bfloat16(r);
+    reinterpret_cast<uint4*>(da)[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -131,23 +143,32 @@ __global__ void sqdiff_reduce_f32_kernel(const float* __restrict__ a, const floa
 }
 // Gram RMSE backward: m[b][i][j] = bf16( coef * ((Gs-Gt)[i][j] + (Gs-Gt)[j][i]) ),
 // coef = gout * inv_count / rmse * gram_scale, so that dF = F m (one 1x1 conv_gemm per sample).
+// grid = (j tiles, i, b): no integer division; the transposed read (j, i) goes through a 32x32 smem tile.
 __global__ void gram_bwd_matrix_kernel(const float* __restrict__ gs, const float* __restrict__ gt, int B, int C,
                                        int Cp, float inv_count, float gram_scale, const float* __restrict__ gout,
                                        const float* __restrict__ msq, bf16* __restrict__ m) {
+  __shared__ float tile[32][33];
   const float coef = *gout * inv_count / fmaxf(sqrtf(*msq), 1e-20f) * gram_scale;
-  const long long total = (long long)B * C * Cp;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % Cp);
-    const long long bi = i / Cp;
-    const int r = (int)(bi % C);
-    const long long b = bi / C;
-    float v = 0.f;
-    if (j < C) {
-      const long long e1 = (b * C + r) * C + j, e2 = (b * C + j) * C + r;
-      v = coef * ((gs[e1] - gt[e1]) + (gs[e2] - gt[e2]));
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* ds = gs + (long long)b * C * C;
+  const float* dt = gt + (long long)b * C * C;
+  // tile[jj][ii] = D[j0+jj][i0+ii]  (rows j, coalesced along i)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int jj = ty + k * 8, j = j0 + jj, i = i0 + tx;
+    tile[jj][tx] = (j < C && i < C) ? ds[(long long)j * C + i] - dt[(long long)j * C + i] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ii = ty + k * 8, i = i0 + ii, j = j0 + tx;
+    if (i < C && j < Cp) {
+      float v = 0.f;
+      if (j < C) v = coef * ((ds[(long long)i * C + j] - dt[(long long)i * C + j]) + tile[tx][ii]);
+      m[((long long)b * C + i) * Cp + j] = __float2bfloat16(v);
     }
-    m[i] = __float2bfloat16(v);
   }
 }
 
@@ -192,8 +213,12 @@ extern "C" int gcc_diff_reduce_bf16(const void* a, const void* b, long long npix
 extern "C" int gcc_diff_bwd_bf16(const void* a, const void* b, long long npix, int Cp, int C, int mode,
                                  const float* gout, const float* msq, void* da, void* stream) {
   const float inv = 1.f / (float)(npix * C);
-  diff_bwd_bf16_kernel<<<rblocks(npix * Cp), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, npix, Cp,
-                                                                            C, mode, inv, gout, msq, (bf16*)da);
+  if (Cp % 8) { gcc_set_error(__FILE__, __LINE__, "diff_bwd: Cp must be a multiple of 8"); return GCC_ERR_ARG; }
+  long long nb = (npix * (Cp / 8) + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  diff_bwd_bf16_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, npix, Cp, C, mode,
+                                                                      inv, gout, msq, (bf16*)da);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -205,9 +230,8 @@ extern "C" int gcc_sqdiff_reduce_f32(const float* a, const float* b, long long n
 extern "C" int gcc_gram_bwd_matrix(const float* gs, const float* gt, int B, int C, int Cp, float gram_scale,
                                    const float* gout, const float* msq, void* m, void* stream) {
   const float inv = 1.f / ((float)B * C * C);
-  gram_bwd_matrix_kernel<<<rblocks((long long)B * C * Cp), 256, 0, (cudaStream_t)stream>>>(gs, gt, B, C, Cp, inv,
-                                                                                          gram_scale, gout, msq,
-                                                                                          (bf16*)m);
+  gram_bwd_matrix_kernel<<<dim3((Cp + 31) / 32, (C + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(
+      gs, gt, B, C, Cp, inv, gram_scale, gout, msq, (bf16*)m);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
