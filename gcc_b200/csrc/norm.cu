@@ -27,6 +27,14 @@ __device__ __forceinline__ Vec8 load8(const bf16* p) {
   r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
   return r;
 }
+__device__ __forceinline__ Vec8 unpack8(const uint4 u) {
+  Vec8 r;
+  r.v[0] = bf16_lo(u.x); r.v[1] = bf16_hi(u.x);
+  r.v[2] = bf16_lo(u.y); r.v[3] = bf16_hi(u.y);
+  r.v[4] = bf16_lo(u.z); r.v[5] = bf16_hi(u.z);
+  r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
+  return r;
+}
 __device__ __forceinline__ void store8(bf16* p, const Vec8& r) {
   uint4 u;
   u.x = pack_bf16(r.v[0], r.v[1]);
@@ -55,19 +63,36 @@ __device__ __forceinline__ float gate_value(const float* alpha, float thr, int c
 
 // ---------------------------------------------------------------------------------- statistics
 // sums[(n)][0:Cp) += sum x ; sums[(n)][Cp:2Cp) += sum x^2   (grid.y = n when per_sample)
-__global__ void norm_stats_kernel(const bf16* __restrict__ x, long long npix, int Cp, int G, int lanes,
-                                  float* __restrict__ sums) {
+__global__ void __launch_bounds__(256, 4) norm_stats_kernel(const bf16* __restrict__ x, long long npix, int Cp, int G,
+                                                            int lanes, float* __restrict__ sums) {
   extern __shared__ float red[];  // [lanes][G][16]
   const int tid = threadIdx.x;
   const int g = tid % G, lane = tid / G;
-  const bf16* xb = x + (long long)blockIdx.y * npix * Cp;
+  const bf16* xb = x + (long long)blockIdx.y * npix * Cp + g * 8;
   float* sb = sums + (long long)blockIdx.y * 2 * Cp;
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (lane < lanes) {
-    for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
-      const Vec8 a = load8(xb + p * Cp + g * 8);
+    const long long step = (long long)gridDim.x * lanes;
+    long long p = (long long)blockIdx.x * lanes + lane;
+    // four independent 16-byte loads in flight per thread
+    for (; p + 3 * step < npix; p += 4 * step) {
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = *reinterpret_cast<const uint4*>(xb + (p + j * step) * Cp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const Vec8 a = unpack8(u[j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += a.v[i];
+          q[i] += a.v[i] * a.v[i];
+        }
+      }
+    }
+    for (; p < npix; p += step) {
+      const Vec8 a = load8(xb + p * Cp);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += a.v[i];
@@ -129,8 +154,10 @@ __device__ __forceinline__ void channel_affine(const NormArgs& a, int n, int c, 
 // coefficients live in registers for the whole kernel and the pixel loop has no integer division:
 //   y = act(x*p + q) * m   with p = rstd*gamma*mask, q = (beta - mean*rstd*gamma)*mask, m = 1
 //   (gate_after: p, q without the mask and m = mask).  grid.y = sample index for instance norm.
-__global__ void norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp,
-                                  int y2_coff, int act2, float* running_mean, float* running_var, float momentum) {
+template <bool DUAL>
+__global__ void __launch_bounds__(256, DUAL ? 2 : 4)
+norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp, int y2_coff, int act2,
+                  float* running_mean, float* running_var, float momentum) {
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
   const int n = blockIdx.y;
@@ -149,36 +176,28 @@ __global__ void norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, b
     const long long step = (long long)gridDim.x * lanes;
     const bf16* xb = a.x + pix0 * a.Cp + g * 8;
     bf16* yb = y ? y + pix0 * a.Cp + g * 8 : nullptr;
-    bf16* y2b = y2 ? y2 + pix0 * y2_Cp + y2_coff + g * 8 : nullptr;
+    bf16* y2b = DUAL ? y2 + pix0 * y2_Cp + y2_coff + g * 8 : nullptr;
+    auto emit = [&](const uint4 u, long long p) {
+      const Vec8 xv = unpack8(u);
+      Vec8 o, o2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z = xv.v[k] * cp[k] + cq[k];
+        o.v[k] = act_fwd(z, a.act, a.slope) * cm[k];
+        if (DUAL) o2.v[k] = act_fwd(z, act2, a.slope) * cm[k];
+      }
+      if (yb) store8(yb + p * a.Cp, o);
+      if (DUAL) store8(y2b + p * y2_Cp, o2);
+    };
     long long p = (long long)blockIdx.x * lanes + lane;
-    // two pixels per iteration: two independent 16-byte loads in flight per thread
-    for (; p + step < a.npix; p += 2 * step) {
-      const Vec8 x0 = load8(xb + p * a.Cp);
-      const Vec8 x1 = load8(xb + (p + step) * a.Cp);
-      Vec8 o0, o1, s0, s1;
+    for (; p + 3 * step < a.npix; p += 4 * step) {  // four independent 16-byte loads in flight per thread
+      uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float z0 = x0.v[k] * cp[k] + cq[k], z1 = x1.v[k] * cp[k] + cq[k];
-        o0.v[k] = act_fwd(z0, a.act, a.slope) * cm[k];
-        o1.v[k] = act_fwd(z1, a.act, a.slope) * cm[k];
-        s0.v[k] = act_fwd(z0, act2, a.slope) * cm[k];
-        s1.v[k] = act_fwd(z1, act2, a.slope) * cm[k];
-      }
-      if (yb) { store8(yb + p * a.Cp, o0); store8(yb + (p + step) * a.Cp, o1); }
-      if (y2b) { store8(y2b + p * y2_Cp, s0); store8(y2b + (p + step) * y2_Cp, s1); }
-    }
-    for (; p < a.npix; p += step) {
-      const Vec8 x0 = load8(xb + p * a.Cp);
-      Vec8 o0, s0;
+      for (int j = 0; j < 4; ++j) u[j] = *reinterpret_cast<const uint4*>(xb + (p + j * step) * a.Cp);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float z0 = x0.v[k] * cp[k] + cq[k];
-        o0.v[k] = act_fwd(z0, a.act, a.slope) * cm[k];
-        s0.v[k] = act_fwd(z0, act2, a.slope) * cm[k];
-      }
-      if (yb) store8(yb + p * a.Cp, o0);
-      if (y2b) store8(y2b + p * y2_Cp, s0);
+      for (int j = 0; j < 4; ++j) emit(u[j], p + j * step);
     }
+    for (; p < a.npix; p += step) emit(*reinterpret_cast<const uint4*>(xb + p * a.Cp), p);
   }
   // running statistics (train-mode BatchNorm2d side effect; momentum 0.1, unbiased variance)
   if (running_mean != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && a.sums != nullptr) {
@@ -229,9 +248,9 @@ __global__ void norm_apply_eval_kernel(NormArgs a, const float* __restrict__ rme
 
 // ------------------------------------------------------------------------------------- backward
 // red[(n)][0:Cp) += sum dg ; red[(n)][Cp:2Cp) += sum dg * xhat      dg = dy*act'(g) + dy2*act2'(g)
-__global__ void norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
-                                       const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
-                                       float* __restrict__ red) {
+__global__ void __launch_bounds__(256, 2)
+norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
+                       const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2, float* __restrict__ red) {
   extern __shared__ float sred[];  // [lanes][G][16]
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
@@ -241,31 +260,57 @@ __global__ void norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __rest
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
   if (lane < lanes) {
-    float mean[8], rstd[8], gam[8], bet[8], mask[8];
+    // xhat = x*rs + ms ;  z = xhat*gam + bet ;  gg = gate_after ? z : z*mask
+    float rs[8], ms[8], cg[8], cb[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) channel_affine(a, n, g * 8 + k, mean[k], rstd[k], gam[k], bet[k], mask[k]);
-    for (long long p = (long long)blockIdx.x * lanes + lane; p < a.npix; p += (long long)gridDim.x * lanes) {
-      const long long pix = pix0 + p;
-      const Vec8 xv = load8(a.x + pix * a.Cp + g * 8);
-      Vec8 d1, d2;
-      if (dy != nullptr) d1 = load8(dy + pix * dy_Cp + dy_coff + g * 8);
-      if (dy2 != nullptr) d2 = load8(dy2 + pix * dy2_Cp + dy2_coff + g * 8);
+    for (int k = 0; k < 8; ++k) {
+      float mean, rstd, gam, bet, mask;
+      channel_affine(a, n, g * 8 + k, mean, rstd, gam, bet, mask);
+      const float mk = a.gate_after ? 1.f : mask;
+      rs[k] = rstd;
+      ms[k] = -mean * rstd;
+      cg[k] = gam * mk;
+      cb[k] = bet * mk;
+    }
+    const bf16* xb = a.x + pix0 * a.Cp + g * 8;
+    const bf16* d1b = dy ? dy + pix0 * dy_Cp + dy_coff + g * 8 : nullptr;
+    const bf16* d2b = dy2 ? dy2 + pix0 * dy2_Cp + dy2_coff + g * 8 : nullptr;
+    auto accum = [&](const uint4 ux, const uint4 u1, const uint4 u2) {
+      const Vec8 xv = unpack8(ux), d1 = unpack8(u1), d2 = unpack8(u2);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float xh = (xv.v[k] - mean[k]) * rstd[k];
-        const float z = xh * gam[k] + bet[k];
-        const float gg = a.gate_after ? z : z * mask[k];
+        const float xh = xv.v[k] * rs[k] + ms[k];
+        const float gg = xh * cg[k] + cb[k];
         float dg = 0.f;
-        if (dy != nullptr) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
-        if (dy2 != nullptr) dg += d2.v[k] * act_grad(gg, act2, a.slope);
+        if (d1b) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
+        if (d2b) dg += d2.v[k] * act_grad(gg, act2, a.slope);
         s1[k] += dg;
         if (a.gate_after) {  // S2 = sum dy * act(z): the gate gradient of y = mask * act(z)
-          if (dy != nullptr) s2[k] += d1.v[k] * act_fwd(z, a.act, a.slope);
-          if (dy2 != nullptr) s2[k] += d2.v[k] * act_fwd(z, act2, a.slope);
+          if (d1b) s2[k] += d1.v[k] * act_fwd(gg, a.act, a.slope);
+          if (d2b) s2[k] += d2.v[k] * act_fwd(gg, act2, a.slope);
         } else {
           s2[k] += dg * xh;
         }
       }
+    };
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    const long long step = (long long)gridDim.x * lanes;
+    long long p = (long long)blockIdx.x * lanes + lane;
+    for (; p + step < a.npix; p += 2 * step) {  // two pixels = up to six independent 16-byte loads in flight
+      const uint4 xa = *reinterpret_cast<const uint4*>(xb + p * a.Cp);
+      const uint4 xc = *reinterpret_cast<const uint4*>(xb + (p + step) * a.Cp);
+      const uint4 a1 = d1b ? *reinterpret_cast<const uint4*>(d1b + p * dy_Cp) : zero;
+      const uint4 c1 = d1b ? *reinterpret_cast<const uint4*>(d1b + (p + step) * dy_Cp) : zero;
+      const uint4 a2 = d2b ? *reinterpret_cast<const uint4*>(d2b + p * dy2_Cp) : zero;
+      const uint4 c2 = d2b ? *reinterpret_cast<const uint4*>(d2b + (p + step) * dy2_Cp) : zero;
+      accum(xa, a1, a2);
+      accum(xc, c1, c2);
+    }
+    for (; p < a.npix; p += step) {
+      const uint4 xa = *reinterpret_cast<const uint4*>(xb + p * a.Cp);
+      const uint4 a1 = d1b ? *reinterpret_cast<const uint4*>(d1b + p * dy_Cp) : zero;
+      const uint4 a2 = d2b ? *reinterpret_cast<const uint4*>(d2b + p * dy2_Cp) : zero;
+      accum(xa, a1, a2);
     }
     float* r = sred + ((long long)lane * a.G + g) * 16;
 #pragma unroll
@@ -287,7 +332,7 @@ __global__ void norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __rest
 // dx = gamma*rstd*mask * (dg - (S1 + xhat*S2)/M)   [norm]   or   dx = mask*dg [identity]
 // with per-thread register coefficients: gg = x*p + q, dx = c1*dg - c2 - c3*x  (thread = channel group x lane).
 // block (0,0) also accumulates dgamma += mask*S2, dbeta += mask*S1, dalpha += gamma*S2 + beta*S1 (summed over n).
-__global__ void norm_bwd_apply_kernel(NormArgs a, int nimg, int lanes, const bf16* __restrict__ dy, int dy_Cp,
+__global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int nimg, int lanes, const bf16* __restrict__ dy, int dy_Cp,
                                       int dy_coff, const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
                                       const float* __restrict__ red, bf16* __restrict__ dx, float* dgamma,
                                       float* dbeta, float* dalpha) {
@@ -322,11 +367,9 @@ __global__ void norm_bwd_apply_kernel(NormArgs a, int nimg, int lanes, const bf1
     const bf16* d1b = dy ? dy + pix0 * dy_Cp + dy_coff + g * 8 : nullptr;
     const bf16* d2b = dy2 ? dy2 + pix0 * dy2_Cp + dy2_coff + g * 8 : nullptr;
     bf16* ob = dx + pix0 * a.Cp + g * 8;
-    for (long long p = (long long)blockIdx.x * lanes + lane; p < a.npix; p += step) {
-      const Vec8 xv = load8(xb + p * a.Cp);
-      Vec8 d1, d2, o;
-      if (d1b) d1 = load8(d1b + p * dy_Cp);
-      if (d2b) d2 = load8(d2b + p * dy2_Cp);
+    auto emit = [&](const uint4 ux, const uint4 u1, const uint4 u2, long long p) {
+      const Vec8 xv = unpack8(ux), d1 = unpack8(u1), d2 = unpack8(u2);
+      Vec8 o;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float gg = xv.v[k] * cp[k] + cq[k];
@@ -336,6 +379,24 @@ __global__ void norm_bwd_apply_kernel(NormArgs a, int nimg, int lanes, const bf1
         o.v[k] = c1[k] * dg - c2[k] - c3[k] * xv.v[k];
       }
       store8(ob + p * a.Cp, o);
+    };
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    long long p = (long long)blockIdx.x * lanes + lane;
+    for (; p + step < a.npix; p += 2 * step) {
+      const uint4 xa = *reinterpret_cast<const uint4*>(xb + p * a.Cp);
+      const uint4 xc = *reinterpret_cast<const uint4*>(xb + (p + step) * a.Cp);
+      const uint4 a1 = d1b ? *reinterpret_cast<const uint4*>(d1b + p * dy_Cp) : zero;
+      const uint4 e1 = d1b ? *reinterpret_cast<const uint4*>(d1b + (p + step) * dy_Cp) : zero;
+      const uint4 a2 = d2b ? *reinterpret_cast<const uint4*>(d2b + p * dy2_Cp) : zero;
+      const uint4 e2 = d2b ? *reinterpret_cast<const uint4*>(d2b + (p + step) * dy2_Cp) : zero;
+      emit(xa, a1, a2, p);
+      emit(xc, e1, e2, p + step);
+    }
+    for (; p < a.npix; p += step) {
+      const uint4 xa = *reinterpret_cast<const uint4*>(xb + p * a.Cp);
+      const uint4 a1 = d1b ? *reinterpret_cast<const uint4*>(d1b + p * dy_Cp) : zero;
+      const uint4 a2 = d2b ? *reinterpret_cast<const uint4*>(d2b + p * dy2_Cp) : zero;
+      emit(xa, a1, a2, p);
     }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr || dalpha != nullptr)) {
@@ -444,9 +505,13 @@ extern "C" int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, 
   const int groups = per_sample ? N : 1;
   int lanes;
   const int threads = stats_threads(a.G, &lanes);
-  const int bx = lane_blocks(a.npix, lanes, groups, 2);
-  norm_apply_kernel<<<dim3(bx, groups), threads, 0, st>>>(a, lanes, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff, act2,
-                                                         running_mean, running_var, momentum);
+  const int bx = lane_blocks(a.npix, lanes, groups, 4);
+  if (y2 != nullptr)
+    norm_apply_kernel<true><<<dim3(bx, groups), threads, 0, st>>>(a, lanes, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff, act2,
+                                                                 running_mean, running_var, momentum);
+  else
+    norm_apply_kernel<false><<<dim3(bx, groups), threads, 0, st>>>(a, lanes, (bf16*)y, nullptr, 0, 0, 0, running_mean,
+                                                                  running_var, momentum);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -497,7 +562,7 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
   }
   int alanes;
   const int athreads = stats_threads(a.G, &alanes);
-  const int bx = dx ? lane_blocks(a.npix, alanes, groups, 1) : 1;
+  const int bx = dx ? lane_blocks(a.npix, alanes, groups, 2) : 1;
   norm_bwd_apply_kernel<<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
       a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, (bf16*)dx, dgamma,
       dbeta, dalpha);
