@@ -318,6 +318,20 @@ class Pix2PixModel(nn.Module):
                     ops.call("gcc_l1_sparsity_f32", self.arena_G.P[off:].data_ptr(), self.arena_G.G[off:].data_ptr(), n,
                              o.lambda_scale, st)
 
+    def _release_graphs(self):
+        """Detach every tensor attribute that still references an autograd graph.  The reference keeps them
+        attached but never uses them again; releasing them lets the AccumulateGrad nodes of the parameters expire
+        between iterations, which CUDA-graph capture needs (a stale node pins the stream it was created on)."""
+        for k, v in list(vars(self).items()):
+            if isinstance(v, torch.Tensor) and v.grad_fn is not None:
+                object.__setattr__(self, k, v.detach())
+        for name in ("g_taps", "d_taps"):
+            taps = getattr(self, name, None)
+            if taps:
+                setattr(self, name, [(f.detach(), c) for f, c in taps])
+        self.netG.taps = []
+        self.netD.taps = []
+
     def optimize_parameters(self):
         if self.opt.online_distillation:
             T = self.teacher_model
@@ -337,6 +351,7 @@ class Pix2PixModel(nn.Module):
         self.optimizer_G.zero_grad()
         self.backward_G()
         self.optimizer_G.step()
+        self._release_graphs()
 
     def optimizer_netD_arch(self):
         self.forward()
@@ -347,6 +362,8 @@ class Pix2PixModel(nn.Module):
         self.optimizer_arch.zero_grad()
         self.backward_D_arch()
         self.optimizer_arch.step()
+        self._release_graphs()
+        self.teacher_model._release_graphs()
 
     # ------------------------------------------------------------------ bookkeeping (reference surface)
     def print_sparse_info(self, logger):
