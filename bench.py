@@ -41,7 +41,7 @@ def parse_args():
     p.add_argument("--skip_cpu_baseline", action="store_true")
     p.add_argument("--skip_e2e", action="store_true", help="profiling runs only")
     p.add_argument("--skip_roofline", action="store_true", help="profiling runs only")
-    p.add_argument("--graph", type=int, default=0, help="1: capture the whole iteration in a CUDA graph and replay it")
+    p.add_argument("--graph", type=int, default=1, help="1 (default): capture the whole iteration in a CUDA graph and replay it; 0: eager launches")
     return p.parse_args()
 
 
@@ -175,7 +175,7 @@ def dominant_kernel_roofline(batch, pk):
 
     def launch():
         _lib.call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cin, wt.data_ptr(), cout, k * k, cin, None, y.data_ptr(),
-                  31, 31, cout, 0, 0, k, k, 1, 1, 0, 0.0, 0, None, 0, st)
+                  31, 31, cout, 0, 0, k, k, 1, 1, 0, 0.0, 0, None, 0, None, 0, st)
 
     for _ in range(3):
         launch()

@@ -93,7 +93,7 @@ __global__ void wgrad_direct_kernel(const bf16* __restrict__ pm, int N, int OH, 
 extern "C" int gcc_conv_direct_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                                     const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
                                     int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
-                                    float* splitk_ws, long long ws_elems, void* stream) {
+                                    float* splitk_ws, long long ws_elems, float* stats, int stats_ld, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (w_per_image) { gcc_set_error(__FILE__, __LINE__, "direct conv: per-image weights unsupported"); return GCC_ERR_ARG; }
   const int Rp = (R + 7) / 8 * 8;

@@ -57,6 +57,7 @@ struct GemmGeom {
   int batched;           // 1: one output matrix per image n (Gram)
   int atomic_out;        // 1: red.add into dw, 0: plain store
   float scale;
+  int debug;             // timing experiments: bit2 skip TMA loads, bit3 skip MMAs, bit0 skip epilogue stores
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -258,30 +259,41 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-      const CUtensorMap* qmap = &p.a_maps[p.tap_map[tap]];
-      for (int pb = pb_begin; pb < pb_end; ++pb) {
-        int t = pb;
-        const int tw = t % p.tiles_w;
-        t /= p.tiles_w;
-        const int th = t % p.tiles_h;
-        const int tn = t / p.tiles_h;
-        const int b0 = tw << p.log_wt, a0 = th << p.log_ht;
-        const int n0 = p.batched ? img : (tn << p.log_nt);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], kStageBytes);
-        uint8_t* sa = smem + stage * kStageBytes;
-        tma_load_4d(sa, &p.p_map, &full_bar[stage], r_tile * 128, b0, a0, n0);
-        tma_load_4d(sa + kBoxBytes, &p.p_map, &full_bar[stage], r_tile * 128 + 64, b0, a0, n0);
-#pragma unroll
-        for (int j = 0; j < BLOCK_N / 64; ++j)
-          tma_load_4d(sa + kABytes + j * kBoxBytes, qmap, &full_bar[stage], c_tile * BLOCK_N + j * 64, b0 + dw,
-                      a0 + dh, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    // The whole producer warp stays converged: lane 0 waits for the slot and arms the barrier, then lanes
+    // 0 .. (2 + BLOCK_N/64 - 1) each issue ONE of the 64-channel boxes, so the per-thread TMA issue latency of
+    // up to six boxes per k-block overlaps instead of serialising.
+    int stage = 0;
+    uint32_t phase = 0;
+    const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+    const CUtensorMap* qmap = &p.a_maps[p.tap_map[tap]];
+    constexpr int kBoxes = 2 + BLOCK_N / 64;
+    // pixel-block coordinates advance incrementally (no integer division in the steady state)
+    int tw = pb_begin % p.tiles_w;
+    int th = (pb_begin / p.tiles_w) % p.tiles_h;
+    int tn = pb_begin / (p.tiles_w * p.tiles_h);
+    for (int pb = pb_begin; pb < pb_end; ++pb) {
+      const int b0 = tw << p.log_wt, a0 = th << p.log_ht;
+      const int n0 = p.batched ? img : (tn << p.log_nt);
+      if (++tw == p.tiles_w) {
+        tw = 0;
+        if (++th == p.tiles_h) { th = 0; ++tn; }
       }
+      if (lane == 0) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.debug & 4) mbar_arrive(&full_bar[stage]);
+        else mbar_expect_tx(&full_bar[stage], kStageBytes);
+      }
+      __syncwarp();
+      uint8_t* sa = smem + stage * kStageBytes;
+      if (p.debug & 4) {
+      } else if (lane < 2) {
+        tma_load_4d(sa + lane * kBoxBytes, &p.p_map, &full_bar[stage], r_tile * 128 + lane * 64, b0, a0, n0);
+      } else if (lane < kBoxes) {
+        const int j = lane - 2;
+        tma_load_4d(sa + kABytes + j * kBoxBytes, qmap, &full_bar[stage], c_tile * BLOCK_N + j * 64, b0 + dw, a0 + dh,
+                    n0);
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
           // MN-major SW128: 8-pixel groups are 1024 B apart (SBO), 64-channel atoms 8192 B apart (LBO)
           const uint64_t da = make_smem_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
           const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
-          umma_bf16(tmem_base, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          if (!(p.debug & 8)) umma_bf16(tmem_base, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -325,6 +337,7 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
           const int col = col0 + i;
           if (col < p.C) {
             const float x = __uint_as_float(v[i]) * p.scale;
+            if (p.debug & 1) continue;
             if (p.atomic_out)
               atomicAdd(orow + col, x);
             else
@@ -374,6 +387,8 @@ struct ConvGeom2 {
   float* partial;
   long long part_sn, part_sh, part_sw;
   int debug;  // bit0: skip global stores, bit1: skip TMEM loads (timing experiments only)
+  float* stats;  // optional fp32 [2][stats_ld]: per-output-channel sum / sum of squares of the bf16 outputs
+  int stats_ld;
 };
 
 struct TileInfo {
@@ -427,6 +442,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   constexpr int kStagePitch = 80;  // 64 B of data + 16 B pad per staged row (spreads banks)
   uint8_t* stage_base = smem + STAGES * kStageBytes + 256;             // 8 warps x 32 rows x 80 B
   float* bias_base = reinterpret_cast<float*>(stage_base + 8 * 32 * kStagePitch);  // 8 warps x 32 floats
+  float* sstat = bias_base + 8 * 32;                                                // [2][BLOCK_N] BN statistics
+  if (p.stats != nullptr)
+    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sstat[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -510,9 +528,26 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
     const int wt_mask = (1 << p.log_wt) - 1, ht_mask = (1 << p.log_ht) - 1;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cur_nt = -1;
+    const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
+    // per-CTA statistics live in smem and are flushed (one global atomic per channel) when the CTA moves on to
+    // another block of output channels; tiles are visited with non-decreasing n_tile
+    auto flush_stats = [&](int nt) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < 2 * BLOCK_N; i += 256) {
+        const int col = nt * BLOCK_N + (i % BLOCK_N);
+        if (col < p.out_cols) atomicAdd(p.stats + (i / BLOCK_N) * p.stats_ld + col, sstat[i]);
+        sstat[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(p, tile);
       if (t.kb1 <= t.kb0) continue;
+      if (p.stats != nullptr && t.n_tile != cur_nt) {
+        if (cur_nt >= 0) flush_stats(cur_nt);
+        cur_nt = t.n_tile;
+      }
       const int b = t.b0 + (r & wt_mask);
       const int a = t.a0 + ((r >> p.log_wt) & ht_mask);
       const int n = t.n0 + (r >> (p.log_wt + p.log_ht));
@@ -556,6 +591,21 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
                                  pack_bf16(f[6], f[7]));
           }
           __syncwarp();
+          if (p.stats != nullptr && col0 + lane < p.out_cols) {
+            // lane j sums column j of the warp's 32 staged rows (the bf16 values that are stored)
+            float s1 = 0.f, s2 = 0.f;
+            const bf16* colp = reinterpret_cast<const bf16*>(stage) + lane;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              if ((vmask >> rr) & 1u) {
+                const float xv = __bfloat162float(colp[rr * (kStagePitch / 2)]);
+                s1 += xv;
+                s2 += xv * xv;
+              }
+            }
+            atomicAdd(&sstat[c0 + lane], s1);
+            atomicAdd(&sstat[BLOCK_N + c0 + lane], s2);
+          }
           if (!(p.debug & 1)) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
@@ -595,6 +645,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.stats != nullptr && cur_nt >= 0) flush_stats(cur_nt);
   }
   tc_fence_before();
   __syncthreads();
@@ -750,7 +801,7 @@ static int num_sms() {
 
 template <int BLOCK_N, int STAGES>
 static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
-  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + 1024 + 256 + 8 * 32 * 80 + 8 * 32 * 4;
+  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + 1024 + 256 + 8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -771,8 +822,12 @@ static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
 extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                                   const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
                                   int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
-                                  float* splitk_ws, long long ws_elems, void* stream) {
+                                  float* splitk_ws, long long ws_elems, float* stats, int stats_ld, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (stats != nullptr && (splitk_ws != nullptr || stats_ld < ((R + 7) / 8 * 8))) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: fused statistics exclude split-K and need stats_ld >= round8(R)");
+    return GCC_ERR_ARG;
+  }
   if (w_per_image && (KH != 1 || KW != 1 || stride != 1 || pad != 0 || transposed)) {
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: per-image weights need a 1x1 stride-1 conv");
     return GCC_ERR_ARG;
@@ -910,6 +965,8 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   }
   g.total_tiles = base_tiles * g.k_splits;
   g.debug = g_debug_flags;
+  g.stats = stats;
+  g.stats_ld = stats_ld;
 
   if (BN == 64) rc = launch_conv_persistent<64, 8>(g, st);
   else if (BN == 128) rc = launch_conv_persistent<128, 6>(g, st);
@@ -981,6 +1038,7 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
   g.batched = batched;
   g.atomic_out = (splits > 1 || accumulate) ? 1 : 0;
   g.scale = scale;
+  g.debug = g_debug_flags;
   g.dw = dw;
   g.R = R;
   g.C = C;

@@ -59,6 +59,16 @@ class ConvLayer:
         fn = ops.ColConvFn if self.colpath else (ops.HeadConvFn if self.headpath else ops.ConvFn)
         return fn.apply(x, self.weight, self.bias, self, act, slope)
 
+    def with_stats(self, x):
+        """Conv whose epilogue also accumulates the per-channel sum / sum of squares a following BatchNorm needs.
+        Returns (y, sums) with sums = None when the layer shape does not take the fused path."""
+        n, h, w, _ = x.shape
+        oh, ow = ops.conv_out_hw(h, w, self.k, self.stride, self.pad, self.kind == "convT", self.outpad)
+        if self.colpath or self.headpath or n * oh * ow <= 16384 or not x.is_cuda:
+            return self(x), None
+        sums = torch.zeros(2 * rp8(self.cout), dtype=torch.float32, device=x.device)
+        return ops.ConvFn.apply(x, self.weight, self.bias, self, ACT_NONE, 0.2, sums), sums
+
 
 class DwConvLayer:
     def __init__(self, arena, name, c):
@@ -99,8 +109,8 @@ class NormLayer:
         self.beta = self.arena.params[self.name + ".bias"] if self.mode == "bn" else None
         self.alpha = self.gate_arena.params[self.gate_name + ".alpha"] if self.gate_name else None
 
-    def __call__(self, x, act=ACT_NONE, act2=None):
-        return ops.NormActFn.apply(x, self.gamma, self.beta, self.alpha, self, act, act2)
+    def __call__(self, x, act=ACT_NONE, act2=None, sums=None):
+        return ops.NormActFn.apply(x, self.gamma, self.beta, self.alpha, self, act, act2, sums)
 
 
 class _Net(nn.Module):
@@ -262,11 +272,12 @@ class UnetGenertor(_Net):
         """a = lrelu(parent activation) with ca logical channels, a_relu = relu of the same.
         Returns relu(cat[a, up_i]) and its logical channel count."""
         di, do, ui, uo = self.lv[i]
-        d = self.down[i](a)
         if i == 7:
+            d = self.down[i](a)
             rc, crc = ops.ActFn.apply(d, ACT_RELU, 0.0), do
         else:
-            y, y2 = self.dnorm[i](d, ACT_LRELU, ACT_RELU)
+            d, dsums = self.down[i].with_stats(a)
+            y, y2 = self.dnorm[i](d, ACT_LRELU, ACT_RELU, dsums)
             if i + 1 < 8 and self.present[i + 1]:
                 rc, crc = self._block(i + 1, y, y2, do)
                 feat = y
@@ -276,8 +287,8 @@ class UnetGenertor(_Net):
                 self.taps[0], self.taps[3] = (feat, do), (rc, crc)
             if i == 3:
                 self.taps[1], self.taps[2] = (feat, do), (rc, crc)
-        u = self.up[i](rc)
-        ub = self.unorm[i](u, ACT_RELU)
+        u, usums = self.up[i].with_stats(rc)
+        ub = self.unorm[i](u, ACT_RELU, None, usums)
         if self.use_dropout and i in (4, 5, 6) and self.training:
             self.seed_salt += 1
             ub = ops.DropoutFn.apply(ub, 0.5, self.seed, self.seed_salt)
@@ -466,7 +477,11 @@ class NLayerDiscriminator(_Net):
         self.taps = []
         h = x
         for li in range(4):
-            h = self.norms[li](self.convs[li](h), ACT_LRELU)
+            if li == 0:
+                h = self.norms[0](self.convs[0](h), ACT_LRELU)
+            else:
+                c, csums = self.convs[li].with_stats(h)
+                h = self.norms[li](c, ACT_LRELU, None, csums)
             if li in (1, 3) and not self.gated:
                 self.taps.append((h, self.ch[li + 1]))
         return self.convs[4](h)

@@ -59,7 +59,7 @@ class ConvFn(torch.autograd.Function):
     """nn.Conv2d / nn.ConvTranspose2d (+ bias, + fused LeakyReLU/Tanh epilogue) on tcgen05."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, layer, act, slope):
+    def forward(ctx, x, weight, bias, layer, act, slope, stats=None):
         _check(x)
         x = x.contiguous()
         layer.arena.ensure_packed()
@@ -71,10 +71,11 @@ class ConvFn(torch.autograd.Function):
         pk = layer.packs
         wp = pk.direct if not tr else pk.transposed  # [cout][T][cin_p]
         epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
-        wsp, wse, _keep = _splitk_ws(n, oh, ow, layer.cout, x.device)
+        wsp, wse, _keep = (None, 0, None) if stats is not None else _splitk_ws(n, oh, ow, layer.cout, x.device)
         call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), layer.cout, layer.k * layer.k,
              wp.shape[2], None if bias is None else bias.data_ptr(), y.data_ptr(), oh, ow, cop, 0, tr, layer.k,
-             layer.k, layer.stride, layer.pad, epi, slope, 0, wsp, wse, _st())
+             layer.k, layer.stride, layer.pad, epi, slope, 0, wsp, wse,
+             None if stats is None else stats.data_ptr(), cop, _st())
         ctx.layer, ctx.act, ctx.slope = layer, act, slope
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, y if act != ACT_NONE else None)
@@ -105,7 +106,7 @@ class ConvFn(torch.autograd.Function):
             wsp, wse, _keep = _splitk_ws(n, h, w, layer.cin, x.device)
             call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin, T, wp.shape[2], None,
                  dx.data_ptr(), h, w, dx.shape[3], 0, 0 if tr else 1, layer.k, layer.k, layer.stride, layer.pad, 0,
-                 0.0, 0, wsp, wse, st)
+                 0.0, 0, wsp, wse, None, 0, st)
             if dx.shape[3] != cx:
                 raise _lib.GccB200Error("conv input channel padding mismatch")
         if ctx.needs_input_grad[1]:
@@ -119,7 +120,7 @@ class ConvFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = layer.arena.flat_grad[layer.bname]
             call("gcc_bias_grad_bf16", dpre.data_ptr(), n * oh * ow, cop, 0, layer.cout, gb.data_ptr(), 1, st)
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
 class ColConvFn(torch.autograd.Function):
@@ -144,14 +145,14 @@ class ColConvFn(torch.autograd.Function):
             y = torch.empty(n, oh, ow, cop, dtype=torch.bfloat16, device=x.device)
             epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
             call("gcc_conv_gemm_bf16", xcol.data_ptr(), n, oh, ow, 128, pk.direct.data_ptr(), layer.cout, 1, 128, bp,
-                 y.data_ptr(), oh, ow, cop, 0, 0, 1, 1, 1, 0, epi, slope, 0, None, 0, st)
+                 y.data_ptr(), oh, ow, cop, 0, 0, 1, 1, 1, 0, epi, slope, 0, None, 0, None, 0, st)
             saved = xcol
         else:
             oh, ow = 2 * h, 2 * w
             ycol = torch.empty(n, h, w, 128, dtype=torch.bfloat16, device=x.device)
             wp = pk.transposed  # [cout][16][cin_p] viewed as [cout*16][1][cin_p]
             call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), layer.cout * 16, 1, wp.shape[2], None,
-                 ycol.data_ptr(), h, w, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
+                 ycol.data_ptr(), h, w, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
             y = torch.empty(n, oh, ow, 8, dtype=torch.bfloat16, device=x.device)
             if act not in (ACT_NONE, ACT_TANH):
                 raise _lib.GccB200Error("col-path ConvTranspose supports none/tanh epilogues")
@@ -188,7 +189,7 @@ class ColConvFn(torch.autograd.Function):
                 wp = pk.transposed  # [cin][16][cout_p] viewed as [cin*16][1][cout_p]
                 dcol = torch.empty(n, oh, ow, 128, dtype=torch.bfloat16, device=dev)
                 call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin * 16, 1,
-                     wp.shape[2], None, dcol.data_ptr(), oh, ow, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
+                     wp.shape[2], None, dcol.data_ptr(), oh, ow, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
                 dx = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=dev)
                 call("gcc_col2im_k4s2_c8", dcol.data_ptr(), 128, 1, layer.cin, None, 0, dx.data_ptr(), n, h, w, st)
             if ctx.needs_input_grad[1]:
@@ -208,7 +209,7 @@ class ColConvFn(torch.autograd.Function):
                 wp = pk.direct  # [cin][16][8] viewed as [cin][1][128]
                 dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=dev)
                 call("gcc_conv_gemm_bf16", dcol.data_ptr(), n, h, w, 128, wp.data_ptr(), layer.cin, 1, 128, None,
-                     dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
+                     dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
             if ctx.needs_input_grad[1]:
                 tmp = torch.empty(layer.cin, 128, dtype=torch.float32, device=dev)
                 call("gcc_wgrad_gemm_bf16", x.data_ptr(), n, h, w, cx, dcol.data_ptr(), h, w, 128, tmp.data_ptr(),
@@ -241,7 +242,7 @@ class HeadConvFn(torch.autograd.Function):
         ycol = torch.empty(n, h, w, rp8(rows), dtype=torch.bfloat16, device=x.device)
         wp = pk.direct  # [cout][16][cin_p] viewed as [cout*16][1][cin_p]
         call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), rows, 1, wp.shape[2], None, ycol.data_ptr(),
-             h, w, ycol.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
+             h, w, ycol.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
         y = torch.empty(n, h - 1, w - 1, 8, dtype=torch.bfloat16, device=x.device)
         call("gcc_fold_k4s1_c8", ycol.data_ptr(), ycol.shape[3], layer.cout, None if bias is None else bias.data_ptr(),
              y.data_ptr(), n, h, w, st)
@@ -266,7 +267,7 @@ class HeadConvFn(torch.autograd.Function):
             wp = layer.packs.transposed  # [cin][16][8] viewed as [cin][1][128]
             dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=dev)
             call("gcc_conv_gemm_bf16", dcol.data_ptr(), n, h, w, 128, wp.data_ptr(), layer.cin, 1, 128, None,
-                 dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, st)
+                 dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
         if ctx.needs_input_grad[1]:
             tmp = torch.empty(128, layer.cin, dtype=torch.float32, device=dev)
             call("gcc_wgrad_gemm_bf16", dcol.data_ptr(), n, h, w, 128, x.data_ptr(), h, w, cx, tmp.data_ptr(), 128,
@@ -284,7 +285,7 @@ class NormActFn(torch.autograd.Function):
     activation output (the U-Net's relu'd skip copy)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, alpha, layer, act, act2):
+    def forward(ctx, x, gamma, beta, alpha, layer, act, act2, sums_in=None):
         _check(x)
         x = x.contiguous()
         n, h, w, cp = x.shape
@@ -305,8 +306,11 @@ class NormActFn(torch.autograd.Function):
         else:
             ctx.eval_bn = False
             if mode != "id":
-                sums = torch.empty((n if per_sample else 1) * 2 * cp, dtype=torch.float32, device=x.device)
-                call("gcc_norm_stats_bf16", x.data_ptr(), n, h * w, cp, per_sample, sums.data_ptr(), st)
+                if sums_in is not None and not per_sample:
+                    sums = sums_in  # accumulated by the producing conv's epilogue
+                else:
+                    sums = torch.empty((n if per_sample else 1) * 2 * cp, dtype=torch.float32, device=x.device)
+                    call("gcc_norm_stats_bf16", x.data_ptr(), n, h * w, cp, per_sample, sums.data_ptr(), st)
                 if layer.stats_hook is not None:
                     layer.stats_hook(sums)
             rm = rv = None
@@ -353,7 +357,7 @@ class NormActFn(torch.autograd.Function):
              ctx.act, layer.slope, 1 if (layer.mode == "id" and alpha is not None) else 0, p1, c1, 0, p2, c2, 0,
              ctx.act2 or 0, red.data_ptr(),
              None if dx is None else dx.data_ptr(), dgamma, dbeta, dalpha, st)
-        return dx, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None
 
 
 class ActFn(torch.autograd.Function):
@@ -594,7 +598,7 @@ class GramRmseFn(torch.autograd.Function):
              acc.data_ptr(), m.data_ptr(), st)
         df = torch.empty_like(f)
         call("gcc_conv_gemm_bf16", f.data_ptr(), n, h, w, cp, m.data_ptr(), c, 1, cp, None, df.data_ptr(), h, w, cp, 0,
-             0, 1, 1, 1, 0, 0, 0.0, 1, None, 0, st)
+             0, 1, 1, 1, 0, 0, 0.0, 1, None, 0, None, 0, st)
         return df, None, None
 
 

@@ -36,11 +36,13 @@ long long gcc_launch_count(void); /* kernels launched by this library so far (ho
  *   w_per_image=1 (1x1 only): w is [N][R][Cw], one matrix per image (Gram-loss backward dF = F M).
  *   splitk_ws: optional fp32 scratch of >= N*OH*OW*round8(R) elements enabling split-K for layers with very
  *   few output pixels (U-Net inner levels); NULL disables it.
+ *   stats: optional zeroed fp32 [2][stats_ld]; the epilogue adds per-output-channel sum / sum of squares of the
+ *   stored bf16 values (the statistics nn.BatchNorm2d needs next, Pix2Pix.py:34,288) -- excludes split-K.
  */
 int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                        const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
                        int KW, int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
-                       long long ws_elems, void* stream);
+                       long long ws_elems, float* stats, int stats_ld, void* stream);
 /* gcc_wgrad_gemm_bf16: dw[b][r][kh*KW+kw][c] (+)= scale * sum_{n,oy,ox} p[n,oy,ox,r] * q[n,stride*oy+kh-pad,stride*ox+kw-pad,c]
  *   weight gradient of Conv2d (p = dy, q = x) and ConvTranspose2d (p = x, q = dy); with batched=1,
  *   KH=KW=1, p == q it is the per-sample Gram matrix f f^T (models/Pix2Pix.py:733-740).
@@ -52,7 +54,7 @@ int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void
 int gcc_conv_direct_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                          const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
                          int KW, int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
-                         long long ws_elems, void* stream);
+                         long long ws_elems, float* stats, int stats_ld, void* stream);
 int gcc_wgrad_direct_bf16(const void* p, int N, int OH, int OW, int Cp, const void* q, int H, int W, int Cq,
                           float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched, int accumulate,
                           float scale, void* stream);

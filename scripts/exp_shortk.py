@@ -17,7 +17,7 @@ def run(n, h, w, cin, cout, k=1, s=1, p=0, bias=False, bn=0, flags=0, reps=10, l
     L.gcc_debug_set_flags(flags)
     def go():
         _lib.call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cin, wt.data_ptr(), cout, k * k, cin, _lib.ptr(b),
-                  y.data_ptr(), oh, ow, cop, 0, 0, k, k, s, p, 0, 0.0, 0, None, 0, st)
+                  y.data_ptr(), oh, ow, cop, 0, 0, k, k, s, p, 0, 0.0, 0, None, 0, None, 0, st)
     for _ in range(3): go()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
@@ -30,17 +30,34 @@ def run(n, h, w, cin, cout, k=1, s=1, p=0, bias=False, bn=0, flags=0, reps=10, l
     L.gcc_debug_force_block_n(0); L.gcc_debug_set_flags(0)
 
 B = 32
-run(B, 128, 128, 128, 128, label="1x1 K128 N128 (BN128)")
-run(B, 128, 128, 128, 128, bias=True, label="  + bias")
-run(B, 128, 128, 128, 128, flags=1, label="  no stores")
-run(B, 128, 128, 128, 128, flags=3, label="  no stores, no tmem ld")
-run(B, 128, 128, 128, 128, bn=64, label="  BN64")
-run(B, 128, 128, 128, 128, bn=256, label="  BN256")
-run(B, 128, 128, 64, 128, label="1x1 K64 N128")
-run(B, 128, 128, 256, 128, label="1x1 K256 N128")
-run(B, 128, 128, 512, 128, label="1x1 K512 N128")
-run(B, 64, 64, 128, 256, k=4, s=2, p=1, label="D L1: 128->256 k4s2 (64x64->32x32)?")
-run(B, 128, 128, 128, 256, k=4, s=2, p=1, label="D L1 real: 128->256 k4s2 128->64")
-run(B, 64, 64, 256, 512, k=4, s=2, p=1, label="D L2: 256->512 k4s2 64->32")
-run(B, 32, 32, 512, 1024, k=4, s=1, p=1, label="D L3: 512->1024 k4s1")
-run(B, 32, 32, 512, 1024, k=4, s=1, p=1, flags=1, label="  no stores")
+
+def run_wgrad(n, h, w, cin, cout, k, s, p, label, reps=10):
+    oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(n, oh, ow, cout, device="cuda").to(torch.bfloat16)
+    dw = torch.zeros(cout, k * k, cin, device="cuda")
+    def go():
+        _lib.call("gcc_wgrad_gemm_bf16", dy.data_ptr(), n, oh, ow, cout, x.data_ptr(), h, w, cin, dw.data_ptr(), cout,
+                  cin, k, k, s, p, 0, 1, 1.0, st)
+    for _ in range(3): go()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(reps): go()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = 2.0 * n * oh * ow * cout * cin * k * k
+    print("%-44s %8.1f us  %7.1f TFLOP/s" % (label, ms * 1e3, fl / ms / 1e9), flush=True)
+
+run_wgrad(B, 32, 32, 512, 1024, 4, 1, 1, "wgrad D L3 512->1024 k4s1")
+for fl, nm in ((1, "no epilogue stores"), (4, "no TMA loads"), (8, "no MMA"), (12, "no TMA, no MMA"), (5, "no TMA no stores")):
+    L.gcc_debug_set_flags(fl)
+    run_wgrad(B, 32, 32, 512, 1024, 4, 1, 1, "   " + nm)
+    L.gcc_debug_set_flags(0)
+run_wgrad(B, 64, 64, 256, 512, 4, 2, 1, "wgrad D L2 256->512 k4s2")
+run_wgrad(B, 128, 128, 128, 256, 4, 2, 1, "wgrad D L1 128->256 k4s2")
+run_wgrad(B, 128, 128, 128, 128, 1, 1, 0, "wgrad 1x1 128x128 (col path L0)")
+for bn in (128,):
+    L.gcc_debug_force_block_n(bn)
+    run_wgrad(B, 32, 32, 512, 1024, 4, 1, 1, "wgrad D L3 BN%d" % bn)
+    run_wgrad(B, 64, 64, 256, 512, 4, 2, 1, "wgrad D L2 BN%d" % bn)
+    L.gcc_debug_force_block_n(0)

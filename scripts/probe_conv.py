@@ -43,7 +43,7 @@ def run_conv(fn, x, w, bias, OH, OW, R, transposed, KH, KW, stride, pad, act=0, 
     cy = cy or rp8(R)
     y = torch.full((N, OH, OW, cy), 7.0, dtype=torch.bfloat16, device=dev)
     _lib.call(fn, x.data_ptr(), N, H, W, Cx, w.data_ptr(), R, T, Cw, _lib.ptr(bias), y.data_ptr(), OH, OW, cy, coff,
-              transposed, KH, KW, stride, pad, act, slope, 0, None, 0, _lib.current_stream())
+              transposed, KH, KW, stride, pad, act, slope, 0, None, 0, None, 0, _lib.current_stream())
     torch.cuda.synchronize()
     return y
 

@@ -23,7 +23,7 @@ def conv(n, h, w, cin, cout, k, s, p, tr=0):
     y = torch.empty(n, oh, ow, cop, device="cuda", dtype=torch.bfloat16)
     for _ in range(reps):
         _lib.call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cin, wt.data_ptr(), cout, k * k, cin, None, y.data_ptr(),
-                  oh, ow, cop, 0, tr, k, k, s, p, 0, 0.0, 0, None, 0, st)
+                  oh, ow, cop, 0, tr, k, k, s, p, 0, 0.0, 0, None, 0, None, 0, st)
     torch.cuda.synchronize()
 
 
