@@ -165,6 +165,78 @@ def run_step_case(options, P2P, name, argv, small, batch, iters, cfgs=(None, Non
     return out
 
 
+def run_cycle_case(options, name, small, batch, iters, size, cfgs=(None, None)):
+    """MobileCycleGANModel (models/CycleGAN.py) driven exactly like train.py drives it."""
+    import math
+    import models.CycleGAN as CG
+    torch.manual_seed(0)
+    opt = make_opt(options, ["--dataroot", "x/horse2zebra", "--model", "cyclegan", "--darts_discriminator",
+                             "--online_distillation", "--lambda_content", "0.01", "--lambda_gram", "10", "--gpu_ids", "-1"])
+    for k, v in small.items():
+        setattr(opt, k, v)
+    model = CG.MobileCycleGANModel(opt, cfg_AtoB=cfgs[0], cfg_BtoA=cfgs[1])
+    topt = copy.deepcopy(opt)
+    topt.ngf, topt.ndf = opt.teacher_ngf, opt.teacher_ndf
+    topt.darts_discriminator = False
+    topt.online_distillation = False
+    topt.generator_only = False
+    teacher = CG.MobileCycleGANModel(topt)
+    teacher.model_train()
+    setattr(model, "teacher_model", teacher)
+    model.init_distillation()
+    teacher.init_distillation()
+    for m, tag in ((model, "S"), (teacher, "T")):
+        for k in "AB":
+            for kind in ("G", "D"):
+                net = getattr(m, "net%s_%s" % (kind, k))
+                sd = net.state_dict()
+                O.init_like_reference(sd, "%s.net%s_%s." % (tag, kind, k))
+                net.load_state_dict(sd)
+            for i, conv in enumerate(getattr(m, "transform_%s_convs" % k, [])):
+                cin = conv.weight.shape[1]
+                conv.weight.data.copy_(O.det_uniform("%s.transform_%s.%d" % (tag, k, i), conv.weight.shape, 1.0 / math.sqrt(cin)))
+    model.model_train()
+    out = {"config": {"small": small, "batch": batch, "iters": iters, "size": size, "cfgs": cfgs,
+                      "direction": opt.direction}, "iters": []}
+    for it in range(iters):
+        rec = {}
+        A = O.det_image("%s.A.%d" % (name, it), batch, 3, size, size)
+        B = O.det_image("%s.B.%d" % (name, it), batch, 3, size, size)
+        model.set_input({"A": A, "B": B, "A_paths": "", "B_paths": ""})
+        model.optimize_parameters()
+        for n in ("fake_A", "fake_B", "rec_A", "rec_B", "idt_A", "idt_B"):
+            rec[n] = stats(getattr(model, n))
+        rec["Tfake_A"], rec["Tfake_B"] = stats(teacher.fake_A), stats(teacher.fake_B)
+        for k in "AB":
+            for i, f in enumerate(getattr(model, "target_distillation_%s_features" % k)):
+                rec["target_%s.%d" % (k, i)] = stats(f)
+            for kind in ("G", "D"):
+                for tag, m in (("S", model), ("T", teacher)):
+                    net = getattr(m, "net%s_%s" % (kind, k))
+                    for kk, v in net.state_dict().items():
+                        rec["%s.%s_%s.%s" % (tag, kind, k, kk)] = stats(v)
+                    for kk, v in net.named_parameters():
+                        if v.grad is not None:
+                            rec["%s.%s_%s.grad.%s" % (tag, kind, k, kk)] = stats(v.grad)
+            for i, c in enumerate(getattr(model, "transform_%s_convs" % k)):
+                rec["S.transform_%s.%d" % (k, i)] = stats(c.weight)
+                rec["S.transform_%s.grad.%d" % (k, i)] = stats(c.weight.grad)
+        vA = O.det_image("%s.vA.%d" % (name, it), batch, 3, size, size)
+        vB = O.det_image("%s.vB.%d" % (name, it), batch, 3, size, size)
+        model.set_input({"A": vA, "B": vB, "A_paths": "", "B_paths": ""})
+        model.clipping_mask_alpha()
+        model.optimizer_netD_arch()
+        for k in "AB":
+            for kk, v in getattr(model, "netD_" + k).named_parameters():
+                if kk.endswith("alpha"):
+                    rec["arch.alpha_%s.%s" % (k, kk)] = stats(v)
+                    rec["arch.alpha_grad_%s.%s" % (k, kk)] = stats(v.grad)
+        rec["losses"] = {k: float(v) for k, v in model.get_current_losses().items()}
+        out["iters"].append(rec)
+        print(name, "iter", it, {k: round(v, 5) for k, v in rec["losses"].items()}, flush=True)
+    return out
+
+
 def run_prune_case(options, P2P):
     out = {}
     # U-Net scale / norm prune at fixed thresholds on deterministic weights
@@ -234,6 +306,9 @@ def main():
     rcfg = [8, 16, 29, 21, 29, 17, 29, 30, 29, 11, 29, 25, 29, 32, 29, 9, 29, 27, 29, 19, 29, 13, 7]
     torch.save(run_step_case(options, P2P, "resnet_tiny", base + ["--backbone", "resnet"], tiny, batch=1, iters=1,
                              cfgs=(rcfg, None)), os.path.join(gold, "pix2pix_resnet_tiny.pt"))
+    ccfg = [8, 16, 29, 21, 29, 17, 29, 30, 29, 11, 29, 25, 29, 32, 29, 9, 29, 27, 29, 19, 29, 13, 7]
+    torch.save(run_cycle_case(options, "cycle_tiny", tiny, batch=1, iters=2, size=128, cfgs=(ccfg, None)),
+               os.path.join(gold, "cyclegan_tiny.pt"))
     torch.save({"prune": run_prune_case(options, P2P), "gate": run_gate_case(P2P), "ganloss": run_ganloss_case()},
                os.path.join(gold, "pix2pix_small_ops.pt"))
     print("golden fixtures written to", gold)

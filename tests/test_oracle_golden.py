@@ -11,6 +11,13 @@ from oracle.make_golden import stats
 
 
 def _close(name, got, exp, rtol, atol_frac=1e-4, step_atol=0.0):
+    if atol_frac is None:
+        # norms only: used for a 2nd iteration, where Adam's first step (+-lr * sign(g)) has turned fp32-noise-level
+        # gradient signs into 2*lr weight differences and per-element values are chaotic while norms still agree
+        assert got["n"] == exp["n"], name
+        assert abs(got["sq"] - exp["sq"]) <= rtol * exp["sq"] + 1e-12, (name, "sq", got["sq"], exp["sq"])
+        assert abs(got["abs"] - exp["abs"]) <= rtol * exp["abs"] + 1e-9, (name, "abs", got["abs"], exp["abs"])
+        return
     """Compare summary statistics of one tensor.  ``step_atol`` loosens post-Adam parameters by a
     fraction of one optimizer step (Adam's m/sqrt(v) amplifies fp32 rounding of tiny gradients)."""
     n = max(exp["n"], 1)
@@ -152,3 +159,61 @@ def test_adam_matches_torch():
         mine.step()
         ref.step()
     assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+
+
+def test_oracle_cyclegan_matches_reference(golden_dir):
+    """CycleGANOracle vs the fixture recorded from the reference's MobileCycleGANModel (2 iterations)."""
+    gold = torch.load(os.path.join(golden_dir, "cyclegan_tiny.pt"), weights_only=False)
+    cfg = gold["config"]
+    small = cfg["small"]
+    opt = O.CycleOpt(direction=cfg["direction"], **small)
+    S, T = O.build_cycle_pair(opt, cfg["cfgs"][0], cfg["cfgs"][1])
+    b, size = cfg["batch"], cfg["size"]
+    for it, rec in enumerate(gold["iters"]):
+        # iteration 2 starts from post-Adam weights (m/sqrt(v) amplifies fp32 re-association): looser
+        rtol = 2e-3 if it == 0 else 5e-2
+        af = 1e-4 if it == 0 else None   # iteration 2: norms only (see _close)
+        A = O.det_image("cycle_tiny.A.%d" % it, b, 3, size, size)
+        B = O.det_image("cycle_tiny.B.%d" % it, b, 3, size, size)
+        S.set_input(A, B)
+        S.optimize_parameters()
+        for n in ("fake_A", "fake_B", "rec_A", "rec_B", "idt_A", "idt_B"):
+            _close(n, stats(getattr(S, n)), rec[n], rtol, af)
+        _close("Tfake_A", stats(T.fake_A), rec["Tfake_A"], rtol, af)
+        _close("Tfake_B", stats(T.fake_B), rec["Tfake_B"], rtol, af)
+        for k in "AB":
+            for i, f in enumerate(S.targets[k]):
+                _close("target_%s.%d" % (k, i), stats(f), rec["target_%s.%d" % (k, i)], rtol, af)
+            head = {"S": O.resnet_layout(opt.ngf, S.cfgs[k])[-1][1], "T": "model.26"}
+            for tag, M in (("S", S), ("T", T)):
+                for kind, P in (("G", M.G[k]), ("D", M.D[k])):
+                    for kk, v in P.items():
+                        if kk.endswith(".bias") and not (kind == "G" and kk.startswith(head[tag])) and \
+                                not (kind == "D" and (M.gated or kk.startswith("model.11"))):
+                            continue  # conv bias followed by InstanceNorm: zero true gradient, Adam follows rounding noise
+                        _close("%s.%s_%s.%s" % (tag, kind, k, kk), stats(v), rec["%s.%s_%s.%s" % (tag, kind, k, kk)], rtol, af,
+                               step_atol=STEP_ATOL)
+                        if v.dtype == torch.float32 and v.grad is not None and not kk.endswith("alpha"):
+                            _close("grad", stats(v.grad), rec["%s.%s_%s.grad.%s" % (tag, kind, k, kk)], 10 * rtol if it == 0 else 0.2,
+                                   None if af is None else 10 * af)
+            for i, w in enumerate(S.transform[k]):
+                _close("transform", stats(w), rec["S.transform_%s.%d" % (k, i)], rtol, af, step_atol=STEP_ATOL)
+                _close("transform.grad", stats(w.grad), rec["S.transform_%s.grad.%d" % (k, i)], 10 * rtol if it == 0 else 0.2,
+                       None if af is None else 10 * af)
+        vA = O.det_image("cycle_tiny.vA.%d" % it, b, 3, size, size)
+        vB = O.det_image("cycle_tiny.vB.%d" % it, b, 3, size, size)
+        S.set_input(vA, vB)
+        S.clipping_mask_alpha()
+        S.optimizer_netD_arch()
+        for k in "AB":
+            for kk, v in S.D[k].items():
+                if kk.endswith("alpha"):
+                    # the arch loss is |(a - b) - (c - d)| of O(1) lsgan terms that nearly cancel (diff ~0.1): the
+                    # first-gate gradients inherit that conditioning
+                    _close("alpha_grad", stats(v.grad), rec["arch.alpha_grad_%s.%s" % (k, kk)], 0.15 if it == 0 else 0.5,
+                           5e-2 if it == 0 else None)
+                    _close("alpha", stats(v), rec["arch.alpha_%s.%s" % (k, kk)], rtol, af, step_atol=STEP_ATOL)
+        losses = S.get_current_losses()
+        assert set(losses) == set(rec["losses"])
+        for n, v in rec["losses"].items():
+            assert losses[n] == pytest.approx(v, rel=(5 * rtol if "arch" in n else rtol) if it == 0 else 0.25, abs=1e-5), n
