@@ -84,7 +84,7 @@ __global__ void diff_reduce_bf16_kernel(const bf16* __restrict__ a, const bf16* 
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float d0 = bf16_lo(uw[k]) - bf16_lo(vw[k]), d1 = bf16_hi(uw[k]) - bf16_hi(vw[k]);
-        acc += mode ? d0 * d0 + d1 * d1 : fabsf(d0) + fabsf(d1);
+        acc += mode ? d0 * d0 + d1 * d1 : fabsf(d0) + fabsf(d1);  // modes 1, 2: squares
       }
     }
   } else {
@@ -101,12 +101,14 @@ __global__ void diff_reduce_bf16_kernel(const bf16* __restrict__ a, const bf16* 
 }
 // mode 0 (L1 mean):      da = gout * sign(a-b) * inv_count
 // mode 1 (RMSE = sqrt(mean sq)): da = gout * (a-b) * inv_count / rmse,  rmse = sqrt(*msq)
+// mode 2 (MSE, CycleGAN.py:513-514): da = gout * 2 (a-b) * inv_count
 // one thread per 8-channel vector (Cp % 8 == 0); the pad-channel test needs no division when C == Cp
 __global__ void diff_bwd_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long npix, int Cp,
                                      int C, int mode, float inv_count, const float* __restrict__ gout,
                                      const float* __restrict__ msq, bf16* __restrict__ da) {
   float go = *gout * inv_count;
   if (mode == 1) go /= fmaxf(sqrtf(*msq), 1e-20f);
+  if (mode == 2) go *= 2.f;  // plain MSE
   const int G = Cp / 8;
   const long long nvec = npix * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
@@ -146,9 +148,10 @@ __global__ void sqdiff_reduce_f32_kernel(const float* __restrict__ a, const floa
 // grid = (j tiles, i, b): no integer division; the transposed read (j, i) goes through a 32x32 smem tile.
 __global__ void gram_bwd_matrix_kernel(const float* __restrict__ gs, const float* __restrict__ gt, int B, int C,
                                        int Cp, float inv_count, float gram_scale, const float* __restrict__ gout,
-                                       const float* __restrict__ msq, bf16* __restrict__ m) {
+                                       const float* __restrict__ msq, int mse, bf16* __restrict__ m) {
   __shared__ float tile[32][33];
-  const float coef = *gout * inv_count / fmaxf(sqrtf(*msq), 1e-20f) * gram_scale;
+  const float coef = mse ? *gout * inv_count * 2.f * gram_scale
+                         : *gout * inv_count / fmaxf(sqrtf(*msq), 1e-20f) * gram_scale;
   const int b = blockIdx.z;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -228,10 +231,10 @@ extern "C" int gcc_sqdiff_reduce_f32(const float* a, const float* b, long long n
   return GCC_OK;
 }
 extern "C" int gcc_gram_bwd_matrix(const float* gs, const float* gt, int B, int C, int Cp, float gram_scale,
-                                   const float* gout, const float* msq, void* m, void* stream) {
+                                   const float* gout, const float* msq, int mse, void* m, void* stream) {
   const float inv = 1.f / ((float)B * C * C);
   gram_bwd_matrix_kernel<<<dim3((Cp + 31) / 32, (C + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(
-      gs, gt, B, C, Cp, inv, gram_scale, gout, msq, (bf16*)m);
+      gs, gt, B, C, Cp, inv, gram_scale, gout, msq, mse, (bf16*)m);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

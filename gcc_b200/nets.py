@@ -35,11 +35,15 @@ class _Tree(nn.Module):
 
 
 class ConvLayer:
-    def __init__(self, arena, name, kind, cin, cout, k, stride, pad, outpad=0, bias=False):
+    """`name` is the reference state-dict name; `prefix` only disambiguates the arena key when several nets share
+    one optimizer arena (CycleGAN's netG_A / netG_B)."""
+
+    def __init__(self, arena, name, kind, cin, cout, k, stride, pad, outpad=0, bias=False, prefix=""):
         self.arena, self.kind = arena, kind
         self.cin, self.cout, self.k, self.stride, self.pad, self.outpad = cin, cout, k, stride, pad, outpad
-        self.wname = name + ".weight"
-        self.bname = name + ".bias" if bias else None
+        self.tname = name
+        self.wname = prefix + name + ".weight"
+        self.bname = prefix + name + ".bias" if bias else None
         shape = (cout, cin, k, k) if kind == "conv" else (cin, cout, k, k)
         arena.add(self.wname, shape, kind)
         if bias:
@@ -71,9 +75,10 @@ class ConvLayer:
 
 
 class DwConvLayer:
-    def __init__(self, arena, name, c):
+    def __init__(self, arena, name, c, prefix=""):
         self.arena, self.c = arena, c
-        self.wname, self.bname = name + ".weight", name + ".bias"
+        self.tname = name
+        self.wname, self.bname = prefix + name + ".weight", prefix + name + ".bias"
         arena.add(self.wname, (c, 1, 3, 3), "vec")
         arena.add(self.bname, (c,), "vec")
 
@@ -88,8 +93,11 @@ class DwConvLayer:
 class NormLayer:
     """mode 'bn' (affine, running stats), 'in' (InstanceNorm2d affine=False) or 'id'; optional gate."""
 
-    def __init__(self, arena, name, c, mode, device, gate_arena=None, gate_name=None, thr=0.5, slope=0.2):
+    def __init__(self, arena, name, c, mode, device, gate_arena=None, gate_name=None, thr=0.5, slope=0.2, prefix=""):
         self.c, self.mode, self.thr, self.slope = c, mode, float(thr), slope
+        self.tname, self.tgate = name, gate_name
+        name = prefix + name
+        gate_name = prefix + gate_name if gate_name is not None else None
         self.name, self.arena = name, arena
         self.training = True
         self.stats_hook = None
@@ -122,23 +130,23 @@ class _Net(nn.Module):
         for l in layers:
             l.bind()
             if isinstance(l, ConvLayer):
-                tree.put(l.wname, l.weight)
+                tree.put(l.tname + ".weight", l.weight)
                 if l.bias is not None:
-                    tree.put(l.bname, l.bias)
+                    tree.put(l.tname + ".bias", l.bias)
             elif isinstance(l, DwConvLayer):
-                tree.put(l.wname, l.weight)
-                tree.put(l.bname, l.bias)
+                tree.put(l.tname + ".weight", l.weight)
+                tree.put(l.tname + ".bias", l.bias)
             elif isinstance(l, NormLayer):
                 self._norms.append(l)
                 if l.mode == "bn":
-                    tree.put(l.name + ".weight", l.gamma)
-                    tree.put(l.name + ".bias", l.beta)
-                    tree.put(l.name + ".running_mean", l.running_mean, buffer=True)
-                    tree.put(l.name + ".running_var", l.running_var, buffer=True)
+                    tree.put(l.tname + ".weight", l.gamma)
+                    tree.put(l.tname + ".bias", l.beta)
+                    tree.put(l.tname + ".running_mean", l.running_mean, buffer=True)
+                    tree.put(l.tname + ".running_var", l.running_var, buffer=True)
                     l.nbt = torch.zeros((), dtype=torch.long, device=l.running_mean.device)
-                    tree.put(l.name + ".num_batches_tracked", l.nbt, buffer=True)
+                    tree.put(l.tname + ".num_batches_tracked", l.nbt, buffer=True)
                 if l.alpha is not None:
-                    tree.put(l.gate_name + ".alpha", l.alpha)
+                    tree.put(l.tgate + ".alpha", l.alpha)
         # expose the reference's top-level attribute name ("model")
         for k, m in tree._modules.items():
             self.add_module(k, m)
@@ -309,7 +317,7 @@ class UnetGenertor(_Net):
 # -------------------------------------------------------------------------------- MobileResNet
 class MobileResnetGenerator(_Net):
     def __init__(self, input_nc=3, output_nc=3, ngf=64, n_blocks=9, cfg=None, arena=None, device="cuda", opt=None,
-                 dropout_rate=0, padding_type="reflect"):
+                 dropout_rate=0, padding_type="reflect", prefix=""):
         super().__init__()
         if padding_type != "reflect":
             raise NotImplementedError("padding [%s] is not implemented" % padding_type)
@@ -321,8 +329,8 @@ class MobileResnetGenerator(_Net):
         seq = []  # (kind, ...)
         idx = 0
         c0 = ngf if cfg is None else cfg[0]
-        conv = ConvLayer(A, "model.1", "conv", input_nc, c0, 7, 1, 0, bias=True)
-        seq.append(("stem", conv, NormLayer(A, "model.2", c0, "in", device)))
+        conv = ConvLayer(A, "model.1", "conv", input_nc, c0, 7, 1, 0, bias=True, prefix=prefix)
+        seq.append(("stem", conv, NormLayer(A, "model.2", c0, "in", device, prefix=prefix)))
         idx = 1
         for i in range(2):
             mult = 2 ** i
@@ -330,8 +338,8 @@ class MobileResnetGenerator(_Net):
             cout = ngf * mult * 2 if cfg is None else cfg[idx]
             idx += 1
             name = "model.%d" % (4 + 3 * i)
-            seq.append(("down", ConvLayer(A, name, "conv", cin, cout, 3, 2, 1, bias=True),
-                        NormLayer(A, "model.%d" % (5 + 3 * i), cout, "in", device), name))
+            seq.append(("down", ConvLayer(A, name, "conv", cin, cout, 3, 2, 1, bias=True, prefix=prefix),
+                        NormLayer(A, "model.%d" % (5 + 3 * i), cout, "in", device, prefix=prefix), name))
         mi = 10
         for i in range(n_blocks):
             c_in = ngf * 4 if cfg is None else cfg[idx - 1]
@@ -345,9 +353,9 @@ class MobileResnetGenerator(_Net):
             parts = []
             for j, (a, b) in ((1, (c_in, c_mid)), (6, (c_mid, c_out))):
                 q = "%s.conv_block.%d.conv" % (name, j)
-                parts.append((DwConvLayer(A, q + ".0", a), NormLayer(A, q + ".1", a, "in", device),
-                              ConvLayer(A, q + ".2", "conv", a, b, 1, 1, 0, bias=True),
-                              NormLayer(A, "%s.conv_block.%d" % (name, j + 1), b, "in", device)))
+                parts.append((DwConvLayer(A, q + ".0", a, prefix=prefix), NormLayer(A, q + ".1", a, "in", device, prefix=prefix),
+                              ConvLayer(A, q + ".2", "conv", a, b, 1, 1, 0, bias=True, prefix=prefix),
+                              NormLayer(A, "%s.conv_block.%d" % (name, j + 1), b, "in", device, prefix=prefix)))
             seq.append(("block", parts, name, c_out))
             mi += 1
         out_ch = ngf
@@ -356,10 +364,10 @@ class MobileResnetGenerator(_Net):
             cin = ngf * mult if cfg is None else cfg[idx - 1]
             out_ch = int(ngf * mult / 2) if cfg is None else cfg[idx]
             idx += 1
-            seq.append(("up", ConvLayer(A, "model.%d" % mi, "convT", cin, out_ch, 3, 2, 1, outpad=1, bias=True),
-                        NormLayer(A, "model.%d" % (mi + 1), out_ch, "in", device)))
+            seq.append(("up", ConvLayer(A, "model.%d" % mi, "convT", cin, out_ch, 3, 2, 1, outpad=1, bias=True, prefix=prefix),
+                        NormLayer(A, "model.%d" % (mi + 1), out_ch, "in", device, prefix=prefix)))
             mi += 3
-        seq.append(("head", ConvLayer(A, "model.%d" % (mi + 1), "conv", out_ch, output_nc, 7, 1, 0, bias=True)))
+        seq.append(("head", ConvLayer(A, "model.%d" % (mi + 1), "conv", out_ch, output_nc, 7, 1, 0, bias=True, prefix=prefix)))
         self.seq = seq
         for s in seq:
             if s[0] == "block":
@@ -430,7 +438,9 @@ class NLayerDiscriminator(_Net):
     """PatchGAN-70 (models/Pix2Pix.py:267-305); ``gated=True`` gives MaskNLayerDiscriminator (:307-348)."""
     gated = False
 
-    def __init__(self, input_nc=3, ndf=64, n_layers=3, threshold=0.5, arena=None, gate_arena=None, device="cuda"):
+    def __init__(self, input_nc=3, ndf=64, n_layers=3, threshold=0.5, arena=None, gate_arena=None, device="cuda",
+                 norm="bn", prefix=""):
+        """norm='in': CycleGAN's plain discriminator (InstanceNorm2d, every conv has a bias; CycleGAN.py:140-178)."""
         super().__init__()
         assert n_layers == 3
         gated = self.gated
@@ -446,18 +456,18 @@ class NLayerDiscriminator(_Net):
         layers = []
         for li, (ci, bi, gi) in enumerate(idx):
             conv = ConvLayer(A, "model.%d" % ci, "conv", ch[li], ch[li + 1], 4, 2 if li < 3 else 1, 1,
-                             bias=li in (0, 4))
+                             bias=(li in (0, 4)) or norm == "in", prefix=prefix)
             self.convs.append(conv)
             layers.append(conv)
             if li == 4:
                 break
             gname = "model.%d" % gi if gi is not None else None
             if li == 0:
-                norm = NormLayer(A, "model.act0", ch[1], "id", device, GA, gname, threshold)
+                nl = NormLayer(A, "model.act0", ch[1], "id", device, GA, gname, threshold, prefix=prefix)
             else:
-                norm = NormLayer(A, "model.%d" % bi, ch[li + 1], "bn", device, GA, gname, threshold)
-            self.norms.append(norm)
-            layers.append(norm)
+                nl = NormLayer(A, "model.%d" % bi, ch[li + 1], norm, device, GA, gname, threshold, prefix=prefix)
+            self.norms.append(nl)
+            layers.append(nl)
         self._layers = layers
         if arena is None:
             self.finalize()

@@ -531,7 +531,8 @@ class GanLossFn(torch.autograd.Function):
 
 
 class DiffLossFn(torch.autograd.Function):
-    """mode 0: mean |a - b| (nn.L1Loss);  mode 1: sqrt(mean (a - b)^2) (sqrt(nn.MSELoss)).  b is constant."""
+    """mode 0: mean |a - b| (nn.L1Loss);  mode 1: sqrt(mean (a - b)^2) (sqrt(nn.MSELoss));  mode 2: mean (a - b)^2
+    (nn.MSELoss).  b is constant."""
 
     @staticmethod
     def forward(ctx, a, b, c, mode):
@@ -539,7 +540,7 @@ class DiffLossFn(torch.autograd.Function):
         npix = a.numel() // a.shape[-1]
         acc = torch.zeros((), dtype=torch.float32, device=a.device)
         st = _st()
-        call("gcc_diff_reduce_bf16", a.data_ptr(), b.data_ptr(), npix, a.shape[-1], c, mode, acc.data_ptr(), st)
+        call("gcc_diff_reduce_bf16", a.data_ptr(), b.data_ptr(), npix, a.shape[-1], c, 1 if mode else 0, acc.data_ptr(), st)
         if mode == 1:
             out = torch.empty_like(acc)
             call("gcc_scalar_sqrt", acc.data_ptr(), out.data_ptr(), st)
@@ -571,18 +572,22 @@ def gram_matrix(f, c):
 
 
 class GramRmseFn(torch.autograd.Function):
-    """sqrt(MSE(gram(f), gram_target)) (models/Pix2Pix.py:542); gram_target is a constant fp32 [N,c,c]."""
+    """sqrt(MSE(gram(f), gram_target)) (models/Pix2Pix.py:542) or, with mse=True, MSE(gram(f), gram_target)
+    (models/CycleGAN.py:513); gram_target is a constant fp32 [N,c,c]."""
 
     @staticmethod
-    def forward(ctx, f, gt, c):
+    def forward(ctx, f, gt, c, mse=False):
         f = _check(f).contiguous()
         gs = gram_matrix(f, c)
         acc = torch.zeros((), dtype=torch.float32, device=f.device)
-        out = torch.empty_like(acc)
         st = _st()
         call("gcc_sqdiff_reduce_f32", gs.data_ptr(), gt.data_ptr(), gs.numel(), acc.data_ptr(), st)
-        call("gcc_scalar_sqrt", acc.data_ptr(), out.data_ptr(), st)
-        ctx.c = c
+        if mse:
+            out = acc
+        else:
+            out = torch.empty_like(acc)
+            call("gcc_scalar_sqrt", acc.data_ptr(), out.data_ptr(), st)
+        ctx.c, ctx.mse = c, mse
         ctx.save_for_backward(f, gs, gt, acc)
         return out
 
@@ -595,11 +600,11 @@ class GramRmseFn(torch.autograd.Function):
         gout = gout.contiguous().float()
         m = torch.empty(n, c, cp, dtype=torch.bfloat16, device=f.device)
         call("gcc_gram_bwd_matrix", gs.data_ptr(), gt.data_ptr(), n, c, cp, 1.0 / (c * h * w), gout.data_ptr(),
-             acc.data_ptr(), m.data_ptr(), st)
+             acc.data_ptr(), 1 if ctx.mse else 0, m.data_ptr(), st)
         df = torch.empty_like(f)
         call("gcc_conv_gemm_bf16", f.data_ptr(), n, h, w, cp, m.data_ptr(), c, 1, cp, None, df.data_ptr(), h, w, cp, 0,
              0, 1, 1, 1, 0, 0, 0.0, 1, None, 0, None, 0, st)
-        return df, None, None
+        return df, None, None, None
 
 
 # ------------------------------------------------------------------------------- boundary helpers

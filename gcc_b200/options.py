@@ -56,6 +56,10 @@ def parse(argv=None):
         if "maps" in root:
             opt.n_epochs, opt.direction, opt.no_flip, opt.load_size = 100, "BtoA", False, 286
             opt.n_epochs_decay, opt.save_epoch_freq, opt.print_freq, opt.lambda_L1 = 200, 5, 100, 10.0
+    elif "cyclegan" in opt.model:
+        opt.dataset_mode = "unaligned"
+        opt.gan_mode = "lsgan"
+        opt.n_epochs, opt.n_epochs_decay, opt.print_freq = 100, 100, 100
     else:
         raise NotImplementedError("%s not implemented" % opt.model)
     if opt.lambda_weight > 0 or opt.lambda_scale > 0:
@@ -65,8 +69,11 @@ def parse(argv=None):
 
 
 def get_model_class(opt):
-    """models/__init__.py:3-14 (only the pix2pix family is built in this round)."""
+    """models/__init__.py:3-14 (pix2pix and cyclegan are built; srgan / sagan are not yet)."""
     if opt.model == "pix2pix":
         from .pix2pix import Pix2PixModel
         return Pix2PixModel
+    if opt.model == "cyclegan":
+        from .cyclegan import MobileCycleGANModel
+        return MobileCycleGANModel
     raise NotImplementedError("%s not implemented" % opt.model)

@@ -163,3 +163,45 @@ def binarysearch_threshold(model, target_budget, count_macs, tolerance=0.1):
         else:
             lo = mid
     raise NotImplementedError("No appropriate threshold found")
+
+
+# ---- CycleGAN (models/CycleGAN.py:803-885): the residual stream is pruned by the MEAN norm over its ten convs
+def _cyclegan_residual_mean(sd):
+    total = None
+    for n in _RES_RESIDUAL:
+        v = _l1(sd[n + ".weight"], False)
+        total = v.clone() if total is None else total + v
+    return total / len(_RES_RESIDUAL)
+
+
+def cyclegan_prunenet_cfg(sd, threshold):
+    sd = _cpu(sd)
+    alive = _cyclegan_residual_mean(sd) > threshold
+    cfg = []
+    for k, v in sd.items():
+        if not k.endswith(".weight") or v.dim() != 4:
+            continue
+        name = k[:-len(".weight")]
+        if name in _RES_UNPRUNABLE:
+            continue
+        if name in _RES_RESIDUAL:
+            cfg.append(int(alive.sum()))
+        else:
+            cfg.append(int((_l1(v, name in ("model.19", "model.22")) > threshold).sum()))
+    return cfg
+
+
+def cyclegan_max_min_conv_norm(sd):
+    sd = _cpu(sd)
+    mean = _cyclegan_residual_mean(sd)
+    un_max, lo = float("inf"), float("inf")
+    for k, v in sd.items():
+        if not k.endswith(".weight") or v.dim() != 4:
+            continue
+        name = k[:-len(".weight")]
+        if name in _RES_UNPRUNABLE:
+            continue
+        nrm = mean if name in _RES_RESIDUAL else _l1(v, name in ("model.19", "model.22"))
+        un_max = min(float(nrm.max()), un_max)
+        lo = min(float(nrm.min()), lo)
+    return un_max, lo

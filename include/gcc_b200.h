@@ -145,12 +145,13 @@ int gcc_gan_loss_bwd_bf16(const void* pred, long long npix, int Cp, int C, int m
 /* mode 0: out += mean|a-b| (criterionL1, Pix2Pix.py:520); mode 1: out += mean (a-b)^2 (criterionMSE, :543) */
 int gcc_diff_reduce_bf16(const void* a, const void* b, long long npix, int Cp, int C, int mode, float* out,
                          void* stream);
-/* mode 0: da = gout*sign(a-b)/count ; mode 1 (sqrt(MSE)): da = gout*(a-b)/(count*sqrt(*msq)) */
+/* mode 0: da = gout*sign(a-b)/count ; mode 1 (sqrt(MSE)): da = gout*(a-b)/(count*sqrt(*msq)) ;
+ * mode 2 (plain MSE, models/CycleGAN.py:513-514): da = gout*2(a-b)/count */
 int gcc_diff_bwd_bf16(const void* a, const void* b, long long npix, int Cp, int C, int mode, const float* gout,
                       const float* msq, void* da, void* stream);
 int gcc_sqdiff_reduce_f32(const float* a, const float* b, long long n, float* out, void* stream);
 int gcc_gram_bwd_matrix(const float* gs, const float* gt, int B, int C, int Cp, float gram_scale, const float* gout,
-                        const float* msq, void* m, void* stream);
+                        const float* msq, int mse, void* m, void* stream);
 int gcc_scalar_sqrt(const float* in, float* out, void* stream);
 
 /* ---- optimizer (optim.cu) ---- */

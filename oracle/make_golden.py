@@ -237,6 +237,21 @@ def run_cycle_case(options, name, small, batch, iters, size, cfgs=(None, None)):
     return out
 
 
+def run_cycle_prune_case(options):
+    """get_prunenet_cfg / max_min_conv_norm of MobileCycleGANModel (CycleGAN.py:803-885) on deterministic weights."""
+    import models.CycleGAN as CG
+    opt = make_opt(options, ["--dataroot", "x/horse2zebra", "--model", "cyclegan", "--ngf", "16", "--ndf", "16",
+                             "--gpu_ids", "-1", "--norm_prune"])
+    m = CG.MobileCycleGANModel(opt)
+    sd = m.netG_A.state_dict()
+    O.init_like_reference(sd, "P.netG.")
+    m.netG_A.load_state_dict(sd)
+    out = {"cfg@%g" % thr: m.get_prunenet_cfg(m.netG_A, thr) for thr in (0.8, 0.95, 1.05, 1.15)}
+    mx, mn = m.max_min_conv_norm(m.netG_A)
+    out["maxmin"] = (float(mx), float(mn))
+    return out
+
+
 def run_prune_case(options, P2P):
     out = {}
     # U-Net scale / norm prune at fixed thresholds on deterministic weights
@@ -309,6 +324,7 @@ def main():
     ccfg = [8, 16, 29, 21, 29, 17, 29, 30, 29, 11, 29, 25, 29, 32, 29, 9, 29, 27, 29, 19, 29, 13, 7]
     torch.save(run_cycle_case(options, "cycle_tiny", tiny, batch=1, iters=2, size=128, cfgs=(ccfg, None)),
                os.path.join(gold, "cyclegan_tiny.pt"))
+    torch.save(run_cycle_prune_case(options), os.path.join(gold, "cyclegan_prune.pt"))
     torch.save({"prune": run_prune_case(options, P2P), "gate": run_gate_case(P2P), "ganloss": run_ganloss_case()},
                os.path.join(gold, "pix2pix_small_ops.pt"))
     print("golden fixtures written to", gold)

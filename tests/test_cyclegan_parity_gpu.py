@@ -1,0 +1,116 @@
+"""CycleGAN GCC iteration on the B200 (gcc_b200.cyclegan.MobileCycleGANModel) against the CPU oracle
+(oracle.gcc_oracle.CycleGANOracle, pinned to the reference by tests/golden/cyclegan_tiny.pt).  Same tolerances as
+the pix2pix MobileResNet case (41 bf16-rounded InstanceNorm stages per generator pass, 6 passes per forward)."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TINY = {"ngf": 8, "teacher_ngf": 16, "ndf": 16, "teacher_ndf": 16}
+CFG = [8, 16, 29, 21, 29, 17, 29, 30, 29, 11, 29, 25, 29, 32, 29, 9, 29, 27, 29, 19, 29, 13, 7]
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def test_cyclegan_iteration_matches_oracle():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from gcc_b200 import options
+    from gcc_b200.cyclegan import MobileCycleGANModel, build_cycle_teacher
+    from oracle import gcc_oracle as O
+    opt = options.parse(["--dataroot", "x/horse2zebra", "--model", "cyclegan", "--darts_discriminator",
+                         "--online_distillation", "--lambda_content", "0.01", "--lambda_gram", "10", "--gpu_ids", "0"])
+    assert opt.gan_mode == "lsgan" and opt.lambda_L1 == 0.0
+    for k, v in TINY.items():
+        setattr(opt, k, v)
+    model = MobileCycleGANModel(opt, cfg_AtoB=CFG, cfg_BtoA=None)
+    teacher = build_cycle_teacher(model, opt)
+    S, T = O.build_cycle_pair(O.CycleOpt(direction=opt.direction, **TINY), CFG, None)
+    for mine, orc in ((model, S), (teacher, T)):
+        for k in "AB":
+            getattr(mine, "netG_" + k).load_state_dict({n: v.detach() for n, v in orc.G[k].items()})
+            getattr(mine, "netD_" + k).load_state_dict({n: v.detach() for n, v in orc.D[k].items()})
+            with torch.no_grad():
+                for i, w in enumerate(orc.transform[k]):
+                    getattr(mine, "transform_%s_convs" % k)[i].weight.copy_(w.detach())
+        mine.sync_weights()
+        mine.model_train()
+    size = 128
+    A, B = O.det_image("cyc.A", 1, 3, size, size), O.det_image("cyc.B", 1, 3, size, size)
+    S.set_input(A, B)
+    S.optimize_parameters()
+    model.set_input({"A": A, "B": B, "A_paths": "", "B_paths": ""})
+    model.optimize_parameters()
+    torch.cuda.synchronize()
+    rep = {}
+    for n in ("fake_A", "fake_B", "rec_A", "rec_B", "idt_A", "idt_B"):
+        rep[n] = _rel(getattr(model, n).cpu(), getattr(S, n).detach())
+    rep["Tfake_B"] = _rel(teacher.fake_B.cpu(), T.fake_B.detach())
+
+    def grads(arena, named, prefix):
+        a, b = [], []
+        for n, v in named.items():
+            if v.dtype == torch.float32 and v.grad is not None and prefix + n in arena.grads and not n.endswith(".bias"):
+                a.append(arena.grads[prefix + n].detach().float().cpu().flatten())
+                b.append(v.grad.flatten())
+        return torch.cat(a), torch.cat(b)
+
+    for tag, mine, orc in (("S", model, S), ("T", teacher, T)):
+        for k in "AB":
+            a, b = grads(mine.arena_G, orc.G[k], k + ".")
+            rep["%s.G_%s.grad.rel" % (tag, k)], rep["%s.G_%s.grad.cos" % (tag, k)] = _rel(a, b), _cos(a, b)
+            a, b = grads(mine.arena_D, {n: v for n, v in orc.D[k].items() if not n.endswith("alpha")}, k + ".")
+            rep["%s.D_%s.grad.rel" % (tag, k)], rep["%s.D_%s.grad.cos" % (tag, k)] = _rel(a, b), _cos(a, b)
+    losses = {}
+    mine_l = {n: float(getattr(model, "loss_" + n).detach()) for n in ("D_A", "G_A", "cycle_A", "idt_A", "D_B", "G_B",
+                                                                       "cycle_B", "idt_B", "content_A", "content_B",
+                                                                       "gram_A", "gram_B")}
+    for n, v in mine_l.items():
+        losses[n] = (v, float(getattr(S, "loss_" + n)))
+    vA, vB = O.det_image("cyc.vA", 1, 3, size, size), O.det_image("cyc.vB", 1, 3, size, size)
+    S.set_input(vA, vB)
+    S.clipping_mask_alpha()
+    S.optimizer_netD_arch()
+    model.set_input({"A": vA, "B": vB, "A_paths": "", "B_paths": ""})
+    model.clipping_mask_alpha()
+    model.optimizer_netD_arch()
+    torch.cuda.synchronize()
+    got = model.get_current_losses()
+    exp = S.get_current_losses()
+    assert list(got) == list(exp)
+    for n in ("D_arch_A", "D_arch_B", "teacher_netD_A_arch_diff", "teacher_netD_B_arch_diff"):
+        losses[n] = (got[n], exp[n])
+    masks_ok = all(torch.equal(m.cpu(), om) for m, om in
+                   zip(model.netD_A.get_current_masks() + model.netD_B.get_current_masks(), S.current_masks()))
+    rep["losses"] = {k: {"b200": a, "oracle": b} for k, (a, b) in losses.items()}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "step_parity_cyclegan.json"), "w"), indent=1)
+    print(json.dumps(rep, indent=1))
+    bad = []
+    for k, v in rep.items():
+        if k == "losses":
+            continue
+        if k.endswith(".cos"):
+            if v < 0.99:
+                bad.append((k, v))
+        elif k.endswith(".rel"):
+            if v > 0.15:
+                bad.append((k, v))
+        elif v > 5e-2:
+            bad.append((k, v))
+    for k, (a, b) in losses.items():
+        if abs(a - b) > 5e-2 * abs(b) + 1e-2:
+            bad.append(("loss." + k, a, b))
+    assert masks_ok, "gate masks differ from the oracle"
+    assert not bad, bad

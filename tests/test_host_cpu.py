@@ -109,3 +109,12 @@ def test_options_overrides():
     assert (o.n_epochs, o.n_epochs_decay) == (10, 15)
     with pytest.raises(NotImplementedError):
         options.parse(["--dataroot", "x", "--model", "nope"])
+
+
+def test_cyclegan_prune_cfg_bit_exact_vs_golden(golden_dir):
+    from gcc_b200 import prune
+    g = torch.load(os.path.join(golden_dir, "cyclegan_prune.pt"), weights_only=False)
+    R = {k: v.detach() for k, v in O._make_params(O.resnet_param_shapes(16), "P.netG.").items()}
+    for thr in (0.8, 0.95, 1.05, 1.15):
+        assert prune.cyclegan_prunenet_cfg(R, thr) == g["cfg@%g" % thr], thr
+    assert prune.cyclegan_max_min_conv_norm(R) == pytest.approx(g["maxmin"], rel=1e-6)
