@@ -207,13 +207,15 @@ __global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // dW[r][tap][c] (+)= scale * sum_pix P[pix, r] * Q[pix (+) tap, c]
 // grid = (r tiles of 128, c tiles of BLOCK_N, taps * splits [* batch])
-template <int BLOCK_N, int STAGES>
+// MT = number of 128-row accumulators per CTA (MT = 2: a 256 x BLOCK_N tile, one third less L2->SM traffic per
+// flop, which is what bounds this kernel: both operands are activations streamed from L2).
+template <int BLOCK_N, int STAGES, int MT>
 __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__ GemmGeom p) {
   constexpr uint32_t kBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
-  constexpr uint32_t kABytes = 2 * kBoxBytes;
+  constexpr uint32_t kABytes = 2 * MT * kBoxBytes;
   constexpr uint32_t kBBytes = (BLOCK_N / 64) * kBoxBytes;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = BLOCK_N;
+  constexpr uint32_t kTmemCols = MT * BLOCK_N;
   constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);
 
   extern __shared__ uint8_t smem_raw[];
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
     uint32_t phase = 0;
     const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
     const CUtensorMap* qmap = &p.a_maps[p.tap_map[tap]];
-    constexpr int kBoxes = 2 + BLOCK_N / 64;
+    constexpr int kBoxes = 2 * MT + BLOCK_N / 64;
     // pixel-block coordinates advance incrementally (no integer division in the steady state)
     int tw = pb_begin % p.tiles_w;
     int th = (pb_begin / p.tiles_w) % p.tiles_h;
@@ -286,10 +288,10 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
       __syncwarp();
       uint8_t* sa = smem + stage * kStageBytes;
       if (p.debug & 4) {
-      } else if (lane < 2) {
-        tma_load_4d(sa + lane * kBoxBytes, &p.p_map, &full_bar[stage], r_tile * 128 + lane * 64, b0, a0, n0);
+      } else if (lane < 2 * MT) {
+        tma_load_4d(sa + lane * kBoxBytes, &p.p_map, &full_bar[stage], r_tile * (128 * MT) + lane * 64, b0, a0, n0);
       } else if (lane < kBoxes) {
-        const int j = lane - 2;
+        const int j = lane - 2 * MT;
         tma_load_4d(sa + kABytes + j * kBoxBytes, qmap, &full_bar[stage], c_tile * BLOCK_N + j * 64, b0 + dw, a0 + dh,
                     n0);
       }
@@ -305,11 +307,14 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
         const uint32_t sa = smem_u32(smem + stage * kStageBytes);
         const uint32_t sb = sa + kABytes;
 #pragma unroll
-        for (int k = 0; k < 64 / 16; ++k) {
-          // MN-major SW128: 8-pixel groups are 1024 B apart (SBO), 64-channel atoms 8192 B apart (LBO)
-          const uint64_t da = make_smem_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
-          if (!(p.debug & 8)) umma_bf16(tmem_base, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+        for (int m = 0; m < MT; ++m) {
+#pragma unroll
+          for (int k = 0; k < 64 / 16; ++k) {
+            // MN-major SW128: 8-pixel groups are 1024 B apart (SBO), 64-channel atoms 8192 B apart (LBO)
+            const uint64_t da = make_smem_desc_sw128(sa + m * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
+            if (!(p.debug & 8)) umma_bf16(tmem_base + m * BLOCK_N, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -318,30 +323,33 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
     }
   } else if (num_kb > 0) {
     const int q = warp & 3;
-    const int r = r_tile * 128 + q * 32 + lane;
-    const bool valid = r < p.R;
-    float* orow = p.dw + ((long long)(p.batched ? img : 0) * p.R + r) * ((long long)p.T_total * p.C) +
-                  (long long)p.tap_widx[tap] * p.C;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      const int col0 = c_tile * BLOCK_N + c0;
-      if (col0 >= p.C) break;
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      if (valid) {
+    for (int m = 0; m < MT; ++m) {
+      const int r = r_tile * (128 * MT) + m * 128 + q * 32 + lane;
+      const bool valid = r < p.R;
+      float* orow = p.dw + ((long long)(p.batched ? img : 0) * p.R + r) * ((long long)p.T_total * p.C) +
+                    (long long)p.tap_widx[tap] * p.C;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        const int col0 = c_tile * BLOCK_N + c0;
+        if (col0 >= p.C) break;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + m * BLOCK_N + c0, v);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = col0 + i;
-          if (col < p.C) {
-            const float x = __uint_as_float(v[i]) * p.scale;
-            if (p.debug & 1) continue;
-            if (p.atomic_out)
-              atomicAdd(orow + col, x);
-            else
-              orow[col] = x;
+          for (int i = 0; i < 32; ++i) {
+            const int col = col0 + i;
+            if (col < p.C) {
+              const float x = __uint_as_float(v[i]) * p.scale;
+              if (p.debug & 1) continue;
+              if (p.atomic_out)
+                atomicAdd(orow + col, x);
+              else
+                orow[col] = x;
+            }
           }
         }
       }
@@ -735,19 +743,19 @@ static int launch_conv_gemm(const GemmGeom& g, int m_tiles, int n_tiles, cudaStr
   return GCC_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MT>
 static int launch_wgrad_gemm(const GemmGeom& g, dim3 grid, cudaStream_t st) {
-  const int smem = STAGES * (2 * 8192 + (BLOCK_N / 64) * 8192) + 1024 + 256;
+  const int smem = STAGES * (2 * MT * 8192 + (BLOCK_N / 64) * 8192) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem) != cudaSuccess) {
       gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
       return GCC_ERR_CUDA;
     }
     configured = true;
   }
-  wgrad_gemm_kernel<BLOCK_N, STAGES><<<grid, 192, smem, st>>>(g);
+  wgrad_gemm_kernel<BLOCK_N, STAGES, MT><<<grid, 192, smem, st>>>(g);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -1026,7 +1034,9 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
   if (rc) return GCC_ERR_DRIVER;
 
   const int BN = g_force_block_n ? g_force_block_n : (C <= 64 ? 64 : (C <= 128 ? 128 : 256));
-  const int r_tiles = (R + 127) / 128;
+  // 256-row tiles (two accumulators) when there are enough rows: less operand traffic per flop
+  const int MT = (BN == 256 && R > 128 && !(g_debug_flags & 16)) ? 2 : 1;
+  const int r_tiles = (R + 128 * MT - 1) / (128 * MT);
   const int c_tiles = (C + BN - 1) / BN;
   const int total_pb = g.tiles_w * g.tiles_h * (batched ? 1 : g.tiles_n);
   const int base_ctas = r_tiles * c_tiles * g.num_taps * (batched ? N : 1);
@@ -1048,7 +1058,8 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
     if (cudaMemsetAsync(dw, 0, bytes, st) != cudaSuccess) return GCC_ERR_CUDA;
   }
   dim3 grid(r_tiles, c_tiles, g.num_taps * splits * (batched ? N : 1));
-  if (BN == 64) return launch_wgrad_gemm<64, 4>(g, grid, st);
-  if (BN == 128) return launch_wgrad_gemm<128, 3>(g, grid, st);
-  return launch_wgrad_gemm<256, 4>(g, grid, st);
+  if (BN == 64) return launch_wgrad_gemm<64, 4, 1>(g, grid, st);
+  if (BN == 128) return launch_wgrad_gemm<128, 3, 1>(g, grid, st);
+  if (MT == 2) return launch_wgrad_gemm<256, 3, 2>(g, grid, st);
+  return launch_wgrad_gemm<256, 4, 1>(g, grid, st);
 }

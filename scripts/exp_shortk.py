@@ -29,7 +29,6 @@ def run(n, h, w, cin, cout, k=1, s=1, p=0, bias=False, bn=0, flags=0, reps=10, l
     print("%-44s %8.1f us  %7.1f GB/s  %7.1f TFLOP/s" % (label, ms * 1e3, byts / ms / 1e6, fl / ms / 1e9), flush=True)
     L.gcc_debug_force_block_n(0); L.gcc_debug_set_flags(0)
 
-B = 32
 
 def run_wgrad(n, h, w, cin, cout, k, s, p, label, reps=10):
     oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
@@ -48,16 +47,11 @@ def run_wgrad(n, h, w, cin, cout, k, s, p, label, reps=10):
     fl = 2.0 * n * oh * ow * cout * cin * k * k
     print("%-44s %8.1f us  %7.1f TFLOP/s" % (label, ms * 1e3, fl / ms / 1e9), flush=True)
 
-run_wgrad(B, 32, 32, 512, 1024, 4, 1, 1, "wgrad D L3 512->1024 k4s1")
-for fl, nm in ((1, "no epilogue stores"), (4, "no TMA loads"), (8, "no MMA"), (12, "no TMA, no MMA"), (5, "no TMA no stores")):
+B = 32
+for fl, nm in ((16, "MT=1 (128-row tiles)"), (0, "MT=2 (256-row tiles)")):
     L.gcc_debug_set_flags(fl)
-    run_wgrad(B, 32, 32, 512, 1024, 4, 1, 1, "   " + nm)
+    run_wgrad(B, 32, 32, 512, 1024, 4, 1, 1, "wgrad D L3 512->1024 k4s1 " + nm)
+    run_wgrad(B, 64, 64, 256, 512, 4, 2, 1, "wgrad D L2 256->512 k4s2 " + nm)
+    run_wgrad(B, 128, 128, 128, 256, 4, 2, 1, "wgrad D L1 128->256 k4s2 " + nm)
+    run_wgrad(B, 16, 16, 512, 512, 4, 2, 1, "wgrad U-Net 512->512 k4s2 16->8 " + nm)
     L.gcc_debug_set_flags(0)
-run_wgrad(B, 64, 64, 256, 512, 4, 2, 1, "wgrad D L2 256->512 k4s2")
-run_wgrad(B, 128, 128, 128, 256, 4, 2, 1, "wgrad D L1 128->256 k4s2")
-run_wgrad(B, 128, 128, 128, 128, 1, 1, 0, "wgrad 1x1 128x128 (col path L0)")
-for bn in (128,):
-    L.gcc_debug_force_block_n(bn)
-    run_wgrad(B, 32, 32, 512, 1024, 4, 1, 1, "wgrad D L3 BN%d" % bn)
-    run_wgrad(B, 64, 64, 256, 512, 4, 2, 1, "wgrad D L2 BN%d" % bn)
-    L.gcc_debug_force_block_n(0)
