@@ -1035,15 +1035,28 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
 
   const int BN = g_force_block_n ? g_force_block_n : (C <= 64 ? 64 : (C <= 128 ? 128 : 256));
   // 256-row tiles (two accumulators) when there are enough rows: less operand traffic per flop
-  const int MT = (BN == 256 && R > 128 && !(g_debug_flags & 16)) ? 2 : 1;
+  const int MT = (BN >= 128 && R > 128 && !(g_debug_flags & 16)) ? 2 : 1;
   const int r_tiles = (R + 128 * MT - 1) / (128 * MT);
   const int c_tiles = (C + BN - 1) / BN;
   const int total_pb = g.tiles_w * g.tiles_h * (batched ? 1 : g.tiles_n);
   const int base_ctas = r_tiles * c_tiles * g.num_taps * (batched ? N : 1);
+  // split-K factor from a small cost model (cycles): CTAs run one per SM for the big tiles, every split adds a
+  // full tile of fp32 atomics, and a partially filled last wave costs a whole wave
   int splits = 1;
-  // fill the machine (~2 CTAs per SM) but keep >= 16 pixel blocks per CTA: every split adds a full tile of
-  // fp32 atomics to the same addresses
-  while (base_ctas * splits * 2 <= 2 * kNumSMs && total_pb / (splits * 2) >= 16) splits *= 2;
+  {
+    const double t_kb = 2.0 * BN * MT * 1.4;             // MMA cycles per 64-pixel block (x1.4: L2-bound operands)
+    const double t_epi = 40.0 * BN * MT + 6000.0;        // atomics epilogue + prologue
+    const int slots = kNumSMs * ((BN <= 128 && MT == 1) ? 2 : 1);
+    double best = 1e30;
+    for (int sp = 1; sp <= 64; sp *= 2) {
+      const int kb = (total_pb + sp - 1) / sp;
+      if (sp > 1 && kb < 8) break;
+      const long long ctas = (long long)base_ctas * sp;
+      const double waves = (double)((ctas + slots - 1) / slots);
+      const double cost = waves * (kb * t_kb + t_epi);
+      if (cost < best * 0.97) { best = cost; splits = sp; }
+    }
+  }
   g.splits = splits;
   g.batched = batched;
   g.atomic_out = (splits > 1 || accumulate) ? 1 : 0;
@@ -1059,6 +1072,7 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
   }
   dim3 grid(r_tiles, c_tiles, g.num_taps * splits * (batched ? N : 1));
   if (BN == 64) return launch_wgrad_gemm<64, 4, 1>(g, grid, st);
+  if (BN == 128 && MT == 2) return launch_wgrad_gemm<128, 4, 2>(g, grid, st);
   if (BN == 128) return launch_wgrad_gemm<128, 3, 1>(g, grid, st);
   if (MT == 2) return launch_wgrad_gemm<256, 3, 2>(g, grid, st);
   return launch_wgrad_gemm<256, 4, 1>(g, grid, st);
