@@ -1035,7 +1035,12 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
 
   const int BN = g_force_block_n ? g_force_block_n : (C <= 64 ? 64 : (C <= 128 ? 128 : 256));
   // 256-row tiles (two accumulators) when there are enough rows: less operand traffic per flop
-  const int MT = (BN >= 128 && R > 128 && !(g_debug_flags & 16)) ? 2 : 1;
+  // 256-row tiles pay when the K loop is long or there are plenty of tiles anyway; short-K layers (U-Net inner
+  // levels) prefer more, smaller CTAs
+  const int c_tiles_pre = (C + BN - 1) / BN;
+  const int pb_pre = g.tiles_w * g.tiles_h * (batched ? 1 : g.tiles_n);
+  const int base2 = ((R + 255) / 256) * c_tiles_pre * g.num_taps * (batched ? N : 1);
+  const int MT = (BN >= 128 && R > 128 && !(g_debug_flags & 16) && (pb_pre >= 256 || base2 >= 100)) ? 2 : 1;
   const int r_tiles = (R + 128 * MT - 1) / (128 * MT);
   const int c_tiles = (C + BN - 1) / BN;
   const int total_pb = g.tiles_w * g.tiles_h * (batched ? 1 : g.tiles_n);
