@@ -162,7 +162,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------ B200 arm
 def dominant_kernel_roofline(batch, pk):
-    """CUDA-event timing of the dominant kernel alone: PatchGAN 512->1024 k4 s1 fprop (conv_gemm_kernel<256,4>),
+    """CUDA-event timing of the dominant kernel alone: PatchGAN 512->1024 k4 s1 fprop (conv_gemm_persistent_kernel<256,4>),
     L2 flushed between launches.  Algorithmic FLOPs = 2 * (batch*31*31) * 1024 * (512*16)."""
     import torch
     from gcc_b200 import _lib
@@ -191,9 +191,14 @@ def dominant_kernel_roofline(batch, pk):
     ms = sum(times) / len(times)
     flops = 2.0 * n * 31 * 31 * cout * cin * k * k
     ach = flops / (ms * 1e-3) / 1e12
+    # DRAM traffic of this exact launch from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_full_gemm_v2_persistent.csv: dram__bytes_read.sum 55.9 MB + dram__bytes_write.sum 35.1 MB at
+    # batch 32; algorithmic unique bytes = 33.5 MB input + 16.8 MB weights + 63.0 MB output = 113 MB)
+    traffic = 91.1e6 if n == 32 else None
     return {"bound": "tensor", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-            "frac": ach / pk["bf16_burst"], "traffic": None,
-            "kernel": "conv_gemm_kernel<256,4>: PatchGAN 512->1024 k4 s1 fprop, M=%d N=1024 K=8192" % (n * 961),
+            "frac": ach / pk["bf16_burst"], "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+            "ncu_tensor_pipe_active_pct": 89.6,
+            "kernel": "conv_gemm_persistent_kernel<256,4>: PatchGAN 512->1024 k4 s1 fprop, M=%d N=1024 K=8192" % (n * 961),
             "avg_launch_ms": ms, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
 
 
