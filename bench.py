@@ -32,12 +32,14 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    p.add_argument("--trace", type=int, default=0, help="debug: after warm-up run one eager step with per-GEMM-launch "
+                   "event timing logged to stderr (GCCTRACE lines) and exit without a bench line")
     p.add_argument("--ngf", type=int, default=32)
     p.add_argument("--teacher_ngf", type=int, default=64)
     p.add_argument("--ndf", type=int, default=128)
     p.add_argument("--backbone", default="unet")
     p.add_argument("--no_dropout", action="store_true")
-    p.add_argument("--cpu_iters", type=int, default=3, help="timed CPU-baseline iterations (batch 1)")
+    p.add_argument("--cpu_iters", type=int, default=20, help="timed CPU-baseline iterations (batch 1), ~0.5 s each on 16 cores")
     p.add_argument("--skip_cpu_baseline", action="store_true")
     p.add_argument("--skip_e2e", action="store_true", help="profiling runs only")
     p.add_argument("--skip_roofline", action="store_true", help="profiling runs only")
@@ -274,6 +276,15 @@ def run_b200(args):
             ms = float(t)
         return ms, _lib.lib().gcc_launch_count() - l0
 
+    if args.trace:
+        for i in range(3):
+            step(devb[i % nbatch], False)
+        torch.cuda.synchronize()
+        _lib.lib().gcc_debug_set_flags(32)
+        step(devb[0], False)
+        torch.cuda.synchronize()
+        _lib.lib().gcc_debug_set_flags(0)
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # sampled from the warm-up on: the GPU is under the same load as in the timed region

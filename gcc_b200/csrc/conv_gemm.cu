@@ -338,17 +338,29 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + m * BLOCK_N + c0, v);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(p.debug & 1)) {
+          // 16-byte vector reductions / stores where the row segment is aligned (C % 4 == 0), scalar otherwise
+          const bool vec = ((reinterpret_cast<uintptr_t>(orow + col0) & 15) == 0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 32; i += 4) {
             const int col = col0 + i;
-            if (col < p.C) {
-              const float x = __uint_as_float(v[i]) * p.scale;
-              if (p.debug & 1) continue;
+            const float x0 = __uint_as_float(v[i]) * p.scale, x1 = __uint_as_float(v[i + 1]) * p.scale;
+            const float x2 = __uint_as_float(v[i + 2]) * p.scale, x3 = __uint_as_float(v[i + 3]) * p.scale;
+            if (vec && col + 3 < p.C) {
               if (p.atomic_out)
-                atomicAdd(orow + col, x);
+                red_add_v4(orow + col, x0, x1, x2, x3);
               else
-                orow[col] = x;
+                *reinterpret_cast<float4*>(orow + col) = make_float4(x0, x1, x2, x3);
+            } else {
+              const float xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col + j < p.C) {
+                  if (p.atomic_out)
+                    atomicAdd(orow + col + j, xs[j]);
+                  else
+                    orow[col + j] = xs[j];
+                }
             }
           }
         }
@@ -639,10 +651,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
           uint32_t v[32];
           tmem_ld_32x32(tmem_d + c0, v);
           tmem_ld_wait();
-          if (valid) {
+          if (valid) {  // out_cols and the workspace row pitch are multiples of 8: whole 16-byte reductions
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.out_cols) atomicAdd(prow + col0 + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; i += 4)
+              if (col0 + i < p.out_cols)
+                red_add_v4(prow + col0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                           __uint_as_float(v[i + 3]));
           }
         }
       }
@@ -796,6 +810,26 @@ static int fill_gather_taps(GemmGeom& g, int KH, int KW, int stride, int pad) {
 
 static int g_debug_flags = 0;
 extern "C" void gcc_debug_set_flags(int f) { g_debug_flags = f; }
+// bit 5 of the debug flags: time every GEMM launch with events (serialises the stream) and log shape + time
+static cudaEvent_t g_trace_ev[2];
+static void trace_begin(cudaStream_t st) {
+  if (!(g_debug_flags & 32)) return;
+  if (g_trace_ev[0] == nullptr) {
+    cudaEventCreate(&g_trace_ev[0]);
+    cudaEventCreate(&g_trace_ev[1]);
+  }
+  cudaEventRecord(g_trace_ev[0], st);
+}
+static void trace_end(cudaStream_t st, const char* kind, int N, int H, int W, int C, int R, int OH, int OW, int k,
+                      int s, int mode, int BN, int tiles, int ksplit, int kb, int stats, double flop) {
+  if (!(g_debug_flags & 32)) return;
+  cudaEventRecord(g_trace_ev[1], st);
+  cudaEventSynchronize(g_trace_ev[1]);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, g_trace_ev[0], g_trace_ev[1]);
+  fprintf(stderr, "GCCTRACE %s N=%d H=%d W=%d C=%d R=%d OH=%d OW=%d k=%d s=%d mode=%d BN=%d tiles=%d ksplit=%d kb=%d stats=%d us=%.1f tflops=%.0f\n",
+          kind, N, H, W, C, R, OH, OW, k, s, mode, BN, tiles, ksplit, kb, stats, ms * 1e3, flop / (ms * 1e9));
+}
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -976,6 +1010,7 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   g.stats = stats;
   g.stats_ld = stats_ld;
 
+  trace_begin(st);
   if (BN == 64) rc = launch_conv_persistent<64, 8>(g, st);
   else if (BN == 128) rc = launch_conv_persistent<128, 6>(g, st);
   else rc = launch_conv_persistent<256, 4>(g, st);
@@ -987,6 +1022,8 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
                                                        Cy, y_coff, R, bias, act, slope);
     GCC_CHECK_LAUNCH();
   }
+  trace_end(st, "conv", N, H, W, Cx, R, OH, OW, KH, stride, transposed, BN, base_tiles, g.k_splits, max_kb,
+            stats != nullptr, 2.0 * N * OH * OW * (double)R * Ck * KH * KW / (transposed && stride == 2 ? 4 : 1));
   return GCC_OK;
 }
 
@@ -1076,9 +1113,13 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
     if (cudaMemsetAsync(dw, 0, bytes, st) != cudaSuccess) return GCC_ERR_CUDA;
   }
   dim3 grid(r_tiles, c_tiles, g.num_taps * splits * (batched ? N : 1));
-  if (BN == 64) return launch_wgrad_gemm<64, 4, 1>(g, grid, st);
-  if (BN == 128 && MT == 2) return launch_wgrad_gemm<128, 4, 2>(g, grid, st);
-  if (BN == 128) return launch_wgrad_gemm<128, 3, 1>(g, grid, st);
-  if (MT == 2) return launch_wgrad_gemm<256, 3, 2>(g, grid, st);
-  return launch_wgrad_gemm<256, 4, 1>(g, grid, st);
+  trace_begin(st);
+  if (BN == 64) rc = launch_wgrad_gemm<64, 4, 1>(g, grid, st);
+  else if (BN == 128 && MT == 2) rc = launch_wgrad_gemm<128, 4, 2>(g, grid, st);
+  else if (BN == 128) rc = launch_wgrad_gemm<128, 3, 1>(g, grid, st);
+  else if (MT == 2) rc = launch_wgrad_gemm<256, 3, 2>(g, grid, st);
+  else rc = launch_wgrad_gemm<256, 4, 1>(g, grid, st);
+  trace_end(st, "wgrad", N, H, W, C, R, OH, OW, KH, stride, batched, BN * 10 + MT, base_ctas, splits, total_pb, 0,
+            2.0 * N * OH * OW * (double)R * C * KH * KW);
+  return rc;
 }

@@ -75,28 +75,26 @@ __global__ void __launch_bounds__(256, 4) norm_stats_kernel(const bf16* __restri
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (lane < lanes) {
     const long long step = (long long)gridDim.x * lanes;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    auto ld = [&](long long q) { return q < npix ? *reinterpret_cast<const uint4*>(xb + q * Cp) : zero; };
+    // register double buffer: the next four 16-byte loads are issued before the current four are consumed
     long long p = (long long)blockIdx.x * lanes + lane;
-    // four independent 16-byte loads in flight per thread
-    for (; p + 3 * step < npix; p += 4 * step) {
-      uint4 u[4];
+    uint4 cur[4], nxt[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) u[j] = *reinterpret_cast<const uint4*>(xb + (p + j * step) * Cp);
+    for (int j = 0; j < 4; ++j) cur[j] = ld(p + j * step);
+    while (p < npix) {
+      p += 4 * step;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nxt[j] = ld(p + j * step);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const Vec8 a = unpack8(u[j]);
+        const Vec8 a = unpack8(cur[j]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           s[i] += a.v[i];
           q[i] += a.v[i] * a.v[i];
         }
-      }
-    }
-    for (; p < npix; p += step) {
-      const Vec8 a = load8(xb + p * Cp);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += a.v[i];
-        q[i] += a.v[i] * a.v[i];
+        cur[j] = nxt[j];
       }
     }
     float* r = red + ((long long)lane * G + g) * 16;
@@ -295,22 +293,23 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
     };
     const uint4 zero = make_uint4(0, 0, 0, 0);
     const long long step = (long long)gridDim.x * lanes;
+    auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * a.Cp) : zero; };
+    auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * dy_Cp) : zero; };
+    auto ld2 = [&](long long q) { return (d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
+    // register double buffer over pairs of pixels (out-of-range pixels load zeros and contribute nothing)
     long long p = (long long)blockIdx.x * lanes + lane;
-    for (; p + step < a.npix; p += 2 * step) {  // two pixels = up to six independent 16-byte loads in flight
-      const uint4 xa = *reinterpret_cast<const uint4*>(xb + p * a.Cp);
-      const uint4 xc = *reinterpret_cast<const uint4*>(xb + (p + step) * a.Cp);
-      const uint4 a1 = d1b ? *reinterpret_cast<const uint4*>(d1b + p * dy_Cp) : zero;
-      const uint4 c1 = d1b ? *reinterpret_cast<const uint4*>(d1b + (p + step) * dy_Cp) : zero;
-      const uint4 a2 = d2b ? *reinterpret_cast<const uint4*>(d2b + p * dy2_Cp) : zero;
-      const uint4 c2 = d2b ? *reinterpret_cast<const uint4*>(d2b + (p + step) * dy2_Cp) : zero;
-      accum(xa, a1, a2);
-      accum(xc, c1, c2);
-    }
-    for (; p < a.npix; p += step) {
-      const uint4 xa = *reinterpret_cast<const uint4*>(xb + p * a.Cp);
-      const uint4 a1 = d1b ? *reinterpret_cast<const uint4*>(d1b + p * dy_Cp) : zero;
-      const uint4 a2 = d2b ? *reinterpret_cast<const uint4*>(d2b + p * dy2_Cp) : zero;
-      accum(xa, a1, a2);
+    uint4 cx[2], c1[2], c2[2], nx[2], n1[2], n2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { cx[j] = ldx(p + j * step); c1[j] = ld1(p + j * step); c2[j] = ld2(p + j * step); }
+    while (p < a.npix) {
+      p += 2 * step;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { nx[j] = ldx(p + j * step); n1[j] = ld1(p + j * step); n2[j] = ld2(p + j * step); }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        accum(cx[j], c1[j], c2[j]);
+        cx[j] = nx[j]; c1[j] = n1[j]; c2[j] = n2[j];
+      }
     }
     float* r = sred + ((long long)lane * a.G + g) * 16;
 #pragma unroll
@@ -381,22 +380,24 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
       store8(ob + p * a.Cp, o);
     };
     const uint4 zero = make_uint4(0, 0, 0, 0);
+    auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * a.Cp) : zero; };
+    auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * dy_Cp) : zero; };
+    auto ld2 = [&](long long q) { return (d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
+    // register double buffer over pairs of pixels
     long long p = (long long)blockIdx.x * lanes + lane;
-    for (; p + step < a.npix; p += 2 * step) {
-      const uint4 xa = *reinterpret_cast<const uint4*>(xb + p * a.Cp);
-      const uint4 xc = *reinterpret_cast<const uint4*>(xb + (p + step) * a.Cp);
-      const uint4 a1 = d1b ? *reinterpret_cast<const uint4*>(d1b + p * dy_Cp) : zero;
-      const uint4 e1 = d1b ? *reinterpret_cast<const uint4*>(d1b + (p + step) * dy_Cp) : zero;
-      const uint4 a2 = d2b ? *reinterpret_cast<const uint4*>(d2b + p * dy2_Cp) : zero;
-      const uint4 e2 = d2b ? *reinterpret_cast<const uint4*>(d2b + (p + step) * dy2_Cp) : zero;
-      emit(xa, a1, a2, p);
-      emit(xc, e1, e2, p + step);
-    }
-    for (; p < a.npix; p += step) {
-      const uint4 xa = *reinterpret_cast<const uint4*>(xb + p * a.Cp);
-      const uint4 a1 = d1b ? *reinterpret_cast<const uint4*>(d1b + p * dy_Cp) : zero;
-      const uint4 a2 = d2b ? *reinterpret_cast<const uint4*>(d2b + p * dy2_Cp) : zero;
-      emit(xa, a1, a2, p);
+    uint4 cx[2], e1[2], e2[2], nx[2], n1[2], n2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { cx[j] = ldx(p + j * step); e1[j] = ld1(p + j * step); e2[j] = ld2(p + j * step); }
+    while (p < a.npix) {
+      const long long pn = p + 2 * step;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { nx[j] = ldx(pn + j * step); n1[j] = ld1(pn + j * step); n2[j] = ld2(pn + j * step); }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (p + j * step < a.npix) emit(cx[j], e1[j], e2[j], p + j * step);
+        cx[j] = nx[j]; e1[j] = n1[j]; e2[j] = n2[j];
+      }
+      p = pn;
     }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr || dalpha != nullptr)) {
@@ -480,7 +481,7 @@ extern "C" int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, i
   int lanes;
   const int threads = stats_threads(G, &lanes);
   long long bx = (npix + lanes * 8 - 1) / (lanes * 8);
-  const long long cap = (148LL * 16 + groups - 1) / groups;
+  const long long cap = (148LL * 4 + groups - 1) / groups;  // one resident wave: few same-address reductions
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   norm_stats_kernel<<<dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * G * 16, st>>>(
@@ -553,7 +554,7 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
     int lanes;
     const int threads = stats_threads(a.G, &lanes);
     long long bx = (a.npix + lanes * 8 - 1) / (lanes * 8);
-    const long long cap = (148LL * 16 + groups - 1) / groups;
+    const long long cap = (148LL * 2 + groups - 1) / groups;  // one resident wave (launch bounds: 2 CTAs / SM)
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     norm_bwd_reduce_kernel<<<dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st>>>(
