@@ -112,6 +112,22 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const void* desc, uint64
       : "memory");
 }
 
+// TMA store of a 4-D box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA store source)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -182,6 +198,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Un-swizzled ("interleave") operand: core matrices of 8 rows x 16 bytes stored as 128 contiguous bytes;
+// lbo = byte distance between core matrices adjacent along K, sbo = along M/N.
+__device__ __forceinline__ uint64_t make_smem_desc_plain(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 inputs, fp32 accumulate.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                      // c_format = F32
@@ -225,3 +251,5 @@ PFN_encodeTiled gcc_get_encode_tiled();
 // strides[i] is the byte stride of dim i+1 (dim 0 is contiguous).
 int gcc_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_bytes, const uint32_t* box);
+int gcc_make_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);

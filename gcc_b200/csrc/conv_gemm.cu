@@ -58,6 +58,7 @@ struct GemmGeom {
   int atomic_out;        // 1: red.add into dw, 0: plain store
   float scale;
   int debug;             // timing experiments: bit2 skip TMA loads, bit3 skip MMAs, bit0 skip epilogue stores
+  int c8;                // wgrad: 1 = Q is an 8-channel image, the N dimension is (tap, channel) = T * 8 columns
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -266,9 +267,15 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
     // up to six boxes per k-block overlaps instead of serialising.
     int stage = 0;
     uint32_t phase = 0;
-    const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+    int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
     const CUtensorMap* qmap = &p.a_maps[p.tap_map[tap]];
     constexpr int kBoxes = 2 * MT + BLOCK_N / 64;
+    if (p.c8 && lane >= 2 * MT && lane < 2 * MT + BLOCK_N / 8) {  // image mode: this lane owns tap (lane - 2 MT)
+      const int tq = lane - 2 * MT;
+      dh = p.tap_dh[tq];
+      dw = p.tap_dw[tq];
+      qmap = &p.a_maps[p.tap_map[tq]];
+    }
     // pixel-block coordinates advance incrementally (no integer division in the steady state)
     int tw = pb_begin % p.tiles_w;
     int th = (pb_begin / p.tiles_w) % p.tiles_h;
@@ -290,6 +297,10 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
       if (p.debug & 4) {
       } else if (lane < 2 * MT) {
         tma_load_4d(sa + lane * kBoxBytes, &p.p_map, &full_bar[stage], r_tile * (128 * MT) + lane * 64, b0, a0, n0);
+      } else if (p.c8) {
+        // one 1 KB box (64 pixels x 8 channels, un-swizzled) per tap: canonical MN-major core matrices
+        if (lane < 2 * MT + BLOCK_N / 8)
+          tma_load_4d(sa + kABytes + (lane - 2 * MT) * 1024, qmap, &full_bar[stage], 0, b0 + dw, a0 + dh, n0);
       } else if (lane < kBoxes) {
         const int j = lane - 2 * MT;
         tma_load_4d(sa + kABytes + j * kBoxBytes, qmap, &full_bar[stage], c_tile * BLOCK_N + j * 64, b0 + dw, a0 + dh,
@@ -312,7 +323,10 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
           for (int k = 0; k < 64 / 16; ++k) {
             // MN-major SW128: 8-pixel groups are 1024 B apart (SBO), 64-channel atoms 8192 B apart (LBO)
             const uint64_t da = make_smem_desc_sw128(sa + m * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
+            // image mode: a k-step = 16 pixels = two 8-pixel core-matrix rows 128 B apart (LBO); the taps
+            // (8-column groups of N) are 1 KB apart (SBO)
+            const uint64_t db = p.c8 ? make_smem_desc_plain(sb + k * 256, 128, 1024)
+                                     : make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
             if (!(p.debug & 8)) umma_bf16(tmem_base + m * BLOCK_N, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
           }
         }
@@ -384,6 +398,7 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
 struct ConvGeom2 {
   CUtensorMap a_maps[4];
   CUtensorMap b_map;
+  CUtensorMap out_maps[4];  // per sub-pixel class: bf16 output view (BLOCK_N <= 128 kernels store tiles by TMA)
   int num_classes;
   int cls_tap_begin[5];
   int cls_GH[4], cls_GW[4];
@@ -409,6 +424,10 @@ struct ConvGeom2 {
   int debug;  // bit0: skip global stores, bit1: skip TMEM loads (timing experiments only)
   float* stats;  // optional fp32 [2][stats_ld]: per-output-channel sum / sum of squares of the bf16 outputs
   int stats_ld;
+  // 1: "image" mode for 8-channel inputs (first conv of the U-Net / PatchGAN).  One k-block = 8 taps x 8 channels:
+  // eight 2 KB boxes (128 pixels x 16 B, un-swizzled) land as canonical core matrices, K index = tap * 8 + c,
+  // which is exactly the order of the packed weights [R][T][8] read as [R][T * 8].
+  int c8;
 };
 
 struct TileInfo {
@@ -435,7 +454,8 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvGeom2& p, int tile_id)
   t.a0 = th << p.log_ht;
   t.n0 = tn << p.log_nt;
   t.tap0 = p.cls_tap_begin[cls];
-  const int num_kb = (p.cls_tap_begin[cls + 1] - t.tap0) * p.k_chunks;
+  const int ntap = p.cls_tap_begin[cls + 1] - t.tap0;
+  const int num_kb = p.c8 ? ntap / 8 : ntap * p.k_chunks;
   const int per = (num_kb + p.k_splits - 1) / p.k_splits;
   t.kb0 = split * per;
   t.kb1 = min(num_kb, t.kb0 + per);
@@ -454,13 +474,19 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  // BLOCK_N <= 128 (short-K, store-bound layers): the bf16 tile is staged in 128B-swizzled 64-column units
+  // (128 rows x 128 B = 16 KB each, double buffered) and written by TMA; otherwise warp-private staging below.
+  constexpr bool kTmaStore = BLOCK_N <= 128;
+  constexpr int kUnits = BLOCK_N / 64;
+  constexpr uint32_t kOutBytes = kTmaStore ? 2 * kUnits * 16384 : 0;
+  uint8_t* out_base = smem + STAGES * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_base + kOutBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;    // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   constexpr int kStagePitch = 80;  // 64 B of data + 16 B pad per staged row (spreads banks)
-  uint8_t* stage_base = smem + STAGES * kStageBytes + 256;             // 8 warps x 32 rows x 80 B
+  uint8_t* stage_base = out_base + kOutBytes + 256;                    // 8 warps x 32 rows x 80 B
   float* bias_base = reinterpret_cast<float*>(stage_base + 8 * 32 * kStagePitch);  // 8 warps x 32 floats
   float* sstat = bias_base + 8 * 32;                                                // [2][BLOCK_N] BN statistics
   if (p.stats != nullptr)
@@ -472,6 +498,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_maps[0]);
     tma_prefetch_desc(&p.b_map);
+    if (kTmaStore) tma_prefetch_desc(&p.out_maps[0]);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -495,16 +522,26 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(p, tile);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          const int tl = kb / p.k_chunks;
-          const int kc = kb - tl * p.k_chunks;
-          const int tap = t.tap0 + tl;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kStageBytes);
           uint8_t* sa = smem + stage * kStageBytes;
-          tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, t.b0 + p.tap_dw[tap],
-                      t.a0 + p.tap_dh[tap], t.n0);
-          tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK,
-                      p.w_per_image ? t.n0 : (int)p.tap_widx[tap], t.n_tile * BLOCK_N);
+          if (p.c8) {
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+              const int tap = t.tap0 + kb * 8 + j;
+              tma_load_4d(sa + j * (kBlockM * 16), &p.a_maps[p.tap_map[tap]], &full_bar[stage], 0, t.b0 + p.tap_dw[tap],
+                          t.a0 + p.tap_dh[tap], t.n0);
+            }
+            tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kb * kBlockK, 0, t.n_tile * BLOCK_N);
+          } else {
+            const int tl = kb / p.k_chunks;
+            const int kc = kb - tl * p.k_chunks;
+            const int tap = t.tap0 + tl;
+            tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, t.b0 + p.tap_dw[tap],
+                        t.a0 + p.tap_dh[tap], t.n0);
+            tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK,
+                        p.w_per_image ? t.n0 : (int)p.tap_widx[tap], t.n_tile * BLOCK_N);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -528,7 +565,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
           const uint32_t sb = sa + kABytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            // image mode: one MMA (K = 16) spans two taps = two core-matrix columns 2 KB apart (LBO); the 8-pixel
+            // row groups of a tap are 128 B apart (SBO)
+            const uint64_t da = p.c8 ? make_smem_desc_plain(sa + k * (2 * kBlockM * 16), kBlockM * 16, 128)
+                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
             umma_bf16(tmem_d, da, db, kIdesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
           }
@@ -549,6 +589,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
     int acc = 0;
     uint32_t acc_phase = 0;
     int cur_nt = -1;
+    int tile_iter = 0;
     const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
     // per-CTA statistics live in smem and are flushed (one global atomic per channel) when the CTA moves on to
     // another block of output channels; tiles are visited with non-decreasing n_tile
@@ -575,6 +616,72 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      if (kTmaStore && p.k_splits == 1) {
+        uint8_t* obuf = out_base + (uint32_t)(tile_iter & 1) * (kUnits * 16384);
+        // the store issued two tiles ago read this buffer: wait for it, then tell everybody
+        if (et == 0) tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        float* sbias = bias_base + (warp - 2) * 32;
+#pragma unroll 1
+        for (int c0 = half * kHalf; c0 < (half + 1) * kHalf; c0 += 32) {
+          const int col0 = t.n_tile * BLOCK_N + c0;
+          if (col0 >= p.out_cols) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_d + c0, v);
+          const float bl = (p.bias != nullptr && col0 + lane < p.bias_cols) ? __ldg(p.bias + col0 + lane) : 0.f;
+          sbias[lane] = bl;
+          tmem_ld_wait();
+          __syncwarp();
+          // row r of unit (c0 / 64): 128 B, 16-byte chunks XOR-swizzled with (r & 7) (= CU_TENSOR_MAP_SWIZZLE_128B)
+          uint8_t* urow = obuf + (c0 >> 6) * 16384 + r * 128;
+          const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              f[i] = apply_act(__uint_as_float(v[g * 8 + i]) + sbias[g * 8 + i], p.act, p.slope);
+            *reinterpret_cast<uint4*>(urow + (((ch0 + g) ^ (r & 7)) << 4)) =
+                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          }
+          __syncwarp();
+          if (p.stats != nullptr && col0 + lane < p.out_cols) {
+            // lane j sums column j of the warp's 32 staged rows (the bf16 values that are stored)
+            float s1 = 0.f, s2 = 0.f;
+            const uint8_t* ubase = obuf + (c0 >> 6) * 16384 + (q * 32) * 128 + (lane & 7) * 2;
+            const int chl = ch0 + (lane >> 3);
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              if ((vmask >> rr) & 1u) {
+                const float xv = __bfloat162float(
+                    *reinterpret_cast<const bf16*>(ubase + rr * 128 + ((chl ^ (rr & 7)) << 4)));
+                s1 += xv;
+                s2 += xv * xv;
+              }
+            }
+            atomicAdd(&sstat[c0 + lane], s1);
+            atomicAdd(&sstat[BLOCK_N + c0 + lane], s2);
+          }
+        }
+        // TMEM reads done: hand the accumulator stage back before the (slower) store hand-off
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0 && !(p.debug & 1)) {
+#pragma unroll
+          for (int u = 0; u < kUnits; ++u)
+            if (t.n_tile * BLOCK_N + u * 64 < p.out_cols)
+              tma_store_4d(&p.out_maps[t.cls], obuf + u * 16384, t.n_tile * BLOCK_N + u * 64, t.b0, t.a0, t.n0);
+          tma_store_commit();
+        }
+        ++tile_iter;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       if (p.k_splits == 1) {
         // Each thread owns one pixel row; its 32-column chunk (64 B) is staged in warp-private shared memory and
         // written out with 4 lanes per row, so every store instruction covers whole 32-byte sectors (8 rows x
@@ -668,6 +775,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.stats != nullptr && cur_nt >= 0) flush_stats(cur_nt);
+    if (kTmaStore && et == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -716,7 +824,7 @@ static void choose_tile(int pixels, int GN, int GH, int GW, int* lw, int* lh, in
 // 4-D activation view: dims (C, W', H', N) over an NHWC bf16 tensor, optionally the stride-2
 // parity sub-grid (ph, pw).  box = (64, 2^lw, 2^lh, 2^ln).
 static int make_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int C, int sub, int ph, int pw,
-                        int lw, int lh, int ln) {
+                        int lw, int lh, int ln, int c8 = 0) {
   const bf16* base = reinterpret_cast<const bf16*>(x);
   uint64_t dims[4], strides[3];
   if (sub == 1) {
@@ -734,8 +842,8 @@ static int make_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int 
     strides[1] = (uint64_t)W * C * 4;
     strides[2] = (uint64_t)H * W * C * 2;
   }
-  uint32_t box[4] = {64u, 1u << lw, 1u << lh, 1u << ln};
-  return gcc_make_tmap_bf16(m, base, 4, dims, strides, box);
+  uint32_t box[4] = {c8 ? 8u : 64u, 1u << lw, 1u << lh, 1u << ln};
+  return gcc_make_tmap_bf16_sw(m, base, 4, dims, strides, box, c8 ? 0 : 1);
 }
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -843,7 +951,8 @@ static int num_sms() {
 
 template <int BLOCK_N, int STAGES>
 static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
-  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + 1024 + 256 + 8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
+  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + (BLOCK_N <= 128 ? 2 * (BLOCK_N / 64) * 16384 : 0) + 1024 +
+                   256 + 8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -891,8 +1000,11 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   const int BN = pick_block_n(Rp);
   const int Ck = Cx < Cw ? Cx : Cw;  // contraction extent (both are zero padded to their physical size)
 
+  // 8-channel image input with a multiple of 8 taps (k4 convs): gather taps x channels into K = T * 8
+  const int c8 = (!transposed && !w_per_image && Cx == 8 && Cw == 8 && (T % 8) == 0 && !(g_debug_flags & 128)) ? 1 : 0;
   ConvGeom2 g;
   memset(&g, 0, sizeof(g));
+  g.c8 = c8;
   g.n_tiles = (Rp + BN - 1) / BN;
   g.k_chunks = (Ck + kBlockK - 1) / kBlockK;
   g.GN = N;
@@ -954,7 +1066,7 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
     g.cls_mtile_begin[ncls + 1] = g.cls_mtile_begin[ncls] + g.cls_tiles_w[ncls] * g.cls_tiles_h[ncls] * tiles_n;
     g.cls_out_off[ncls] = ((long long)qh * OW + qw) * Cy;
     g.cls_part_off[ncls] = ((long long)qh * OW + qw) * Rp;
-    const int kb = (ntap - tap_begin) * g.k_chunks;
+    const int kb = c8 ? (ntap - tap_begin) / 8 : (ntap - tap_begin) * g.k_chunks;
     if (kb > max_kb) max_kb = kb;
     ++ncls;
   }
@@ -966,11 +1078,16 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   if (!transposed && stride == 2) {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
-        rc |= make_act_map(&g.a_maps[ph * 2 + pw], x, N, H, W, Cx, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt);
+        rc |= make_act_map(&g.a_maps[ph * 2 + pw], x, N, H, W, Cx, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt, c8);
   } else {
-    rc |= make_act_map(&g.a_maps[0], x, N, H, W, Cx, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
+    rc |= make_act_map(&g.a_maps[0], x, N, H, W, Cx, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt, c8);
   }
-  {
+  if (c8) {  // weights [R][T][8] read as a K-major [R][T * 8] matrix
+    uint64_t dims[3] = {(uint64_t)T * 8, 1, (uint64_t)R};
+    uint64_t strides[2] = {(uint64_t)T * 16, (uint64_t)T * 16};
+    uint32_t box[3] = {64u, 1u, (uint32_t)BN};
+    rc |= gcc_make_tmap_bf16(&g.b_map, w, 3, dims, strides, box);
+  } else {
     uint64_t dims[3] = {(uint64_t)Cw, (uint64_t)(w_per_image ? N : T), (uint64_t)R};
     uint64_t strides[2] = {(uint64_t)Cw * 2 * (w_per_image ? R : 1), (uint64_t)Cw * 2 * (w_per_image ? 1 : T)};
     uint32_t box[3] = {64u, 1u, (uint32_t)BN};
@@ -978,6 +1095,16 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   }
   if (rc) return GCC_ERR_DRIVER;
 
+  if (BN <= 128) {  // TMA-store views of the output, one per sub-pixel class
+    for (int cls = 0; cls < ncls; ++cls) {
+      const bf16* ob = reinterpret_cast<const bf16*>(y) + y_coff + g.cls_out_off[cls];
+      uint64_t dims[4] = {(uint64_t)Rp, (uint64_t)g.cls_GW[cls], (uint64_t)g.cls_GH[cls], (uint64_t)N};
+      uint64_t strides[3] = {(uint64_t)Cy * 2 * os, (uint64_t)OW * Cy * 2 * os, (uint64_t)OH * OW * Cy * 2};
+      uint32_t box[4] = {64u, 1u << g.log_wt, 1u << g.log_ht, 1u << g.log_nt};
+      rc |= gcc_make_tmap_bf16(&g.out_maps[cls], ob, 4, dims, strides, box);
+    }
+    if (rc) return GCC_ERR_DRIVER;
+  }
   g.out = reinterpret_cast<bf16*>(y) + y_coff;
   g.out_sn = (long long)OH * OW * Cy;
   g.out_sh = (long long)OW * Cy * os;
@@ -1011,8 +1138,8 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   g.stats_ld = stats_ld;
 
   trace_begin(st);
-  if (BN == 64) rc = launch_conv_persistent<64, 8>(g, st);
-  else if (BN == 128) rc = launch_conv_persistent<128, 6>(g, st);
+  if (BN == 64) rc = launch_conv_persistent<64, 6>(g, st);
+  else if (BN == 128) rc = launch_conv_persistent<128, 4>(g, st);
   else rc = launch_conv_persistent<256, 4>(g, st);
   if (rc) return rc;
   if (g.k_splits > 1) {
@@ -1060,17 +1187,26 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
   g.tiles_h = (OH + (1 << g.log_ht) - 1) >> g.log_ht;
   g.tiles_n = (N + (1 << g.log_nt) - 1) >> g.log_nt;
 
+  // 8-channel image on the Q side of a 16-tap conv: all taps become columns of ONE 128-wide tile
+  // (dw is then the dense [R][16 * 8] matrix; the caller drops the padded channels)
+  const int c8 = (!batched && Cq == 8 && C == 8 && KH * KW == 16 && !(g_debug_flags & 128)) ? 1 : 0;
+  g.c8 = c8;
   rc = make_act_map(&g.p_map, pmat, N, OH, OW, Cp, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
   if (stride == 2) {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
-        rc |= make_act_map(&g.a_maps[ph * 2 + pw], qmat, N, H, W, Cq, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt);
+        rc |= make_act_map(&g.a_maps[ph * 2 + pw], qmat, N, H, W, Cq, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt, c8);
   } else {
-    rc |= make_act_map(&g.a_maps[0], qmat, N, H, W, Cq, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
+    rc |= make_act_map(&g.a_maps[0], qmat, N, H, W, Cq, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt, c8);
   }
   if (rc) return GCC_ERR_DRIVER;
+  if (c8) {  // one "tap" (the whole receptive field), 128 output columns
+    g.num_taps = 1;
+    C = 128;
+    KH = KW = 1;
+  }
 
-  const int BN = g_force_block_n ? g_force_block_n : (C <= 64 ? 64 : (C <= 128 ? 128 : 256));
+  const int BN = c8 ? 128 : (g_force_block_n ? g_force_block_n : (C <= 64 ? 64 : (C <= 128 ? 128 : 256)));
   // 256-row tiles (two accumulators) when there are enough rows: less operand traffic per flop
   // 256-row tiles pay when the K loop is long or there are plenty of tiles anyway; short-K layers (U-Net inner
   // levels) prefer more, smaller CTAs
@@ -1090,7 +1226,7 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
     const double t_epi = 40.0 * BN * MT + 6000.0;        // atomics epilogue + prologue
     const int slots = kNumSMs * ((BN <= 128 && MT == 1) ? 2 : 1);
     double best = 1e30;
-    for (int sp = 1; sp <= 64; sp *= 2) {
+    for (int sp = 1; sp <= (c8 ? 256 : 64); sp *= 2) {
       const int kb = (total_pb + sp - 1) / sp;
       if (sp > 1 && kb < 8) break;
       const long long ctas = (long long)base_ctas * sp;

@@ -438,6 +438,10 @@ __global__ void col2im_k4s2_c8_kernel(const bf16* __restrict__ col, int Ccol, in
           acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
           acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z);
           acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+        } else if (order == 2) {  // tap-major, 4 channels per tap: one 8-byte load
+          const uint2 u = *reinterpret_cast<const uint2*>(row + tap * 4);
+          acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x);
+          acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
         } else {
           for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(row[c * 16 + tap]);
         }
@@ -686,7 +690,10 @@ extern "C" int gcc_im2col_k4s2_c8(const void* img, void* col, int N, int H, int 
 }
 extern "C" int gcc_col2im_k4s2_c8(const void* col, int Ccol, int order, int C, const float* bias, int act, void* img,
                                   int N, int H, int W, void* stream) {
-  if ((H % 2) || (W % 2) || C > 8 || (Ccol % 8)) { gcc_set_error(__FILE__, __LINE__, "col2im: bad arguments"); return GCC_ERR_ARG; }
+  if ((H % 2) || (W % 2) || C > 8 || (Ccol % 8) || order < 0 || order > 2 || (order == 2 && C > 4)) {
+    gcc_set_error(__FILE__, __LINE__, "col2im: bad arguments");
+    return GCC_ERR_ARG;
+  }
   col2im_k4s2_c8_kernel<<<blocks_for((long long)N * H * W), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)col, Ccol, order, C, bias, act, (uint4*)img, N, H, W);
   GCC_CHECK_LAUNCH();

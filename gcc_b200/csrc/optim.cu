@@ -62,19 +62,38 @@ __global__ void clamp_kernel(float* __restrict__ x, long long n, float lo, float
 }
 
 // table entry (8 x int64): src, direct, transposed, D0, T, D1, D1p, D0p
-// One CTA handles 32 x 32 (d0 x d1) tiles of one tap: coalesced fp32 reads along d1, coalesced bf16 writes of
-// the direct pack along d1 and, through a shared-memory transpose, of the transposed pack along d0.
-__global__ void pack_table_kernel(const long long* __restrict__ table) {
+// The 32 x 32 (d0 x d1) tiles of ALL entries form one flat index space walked grid-stride (layers differ in size
+// by four orders of magnitude: a per-layer grid leaves most CTAs idle).  Per tile: coalesced fp32 reads along d1,
+// coalesced bf16 writes of the direct pack along d1 and, through a shared-memory transpose, of the transposed
+// pack along d0.
+__global__ void pack_table_kernel(const long long* __restrict__ table, int count) {
   __shared__ float tile[32][33];
-  const long long* e = table + (long long)blockIdx.y * 8;
-  const float* src = reinterpret_cast<const float*>(e[0]);
-  bf16* direct = reinterpret_cast<bf16*>(e[1]);
-  bf16* transposed = reinterpret_cast<bf16*>(e[2]);
-  const int D0 = (int)e[3], T = (int)e[4], D1 = (int)e[5], D1p = (int)e[6], D0p = (int)e[7];
-  const int t0 = (D0 + 31) / 32, t1 = (D1 + 31) / 32;
-  const long long ntiles = (long long)t0 * t1 * T;
+  extern __shared__ long long cum[];  // [count + 1] running tile counts
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const long long* e = table + (long long)i * 8;
+    cum[i + 1] = ((e[3] + 31) / 32) * ((e[5] + 31) / 32) * e[4];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cum[0] = 0;
+    for (int i = 0; i < count; ++i) cum[i + 1] += cum[i];
+  }
+  __syncthreads();
+  const long long total = cum[count];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
-  for (long long tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+  for (long long flat = blockIdx.x; flat < total; flat += gridDim.x) {
+    int lo = 0, hi = count - 1;  // last entry with cum[entry] <= flat
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (cum[mid] <= flat) lo = mid; else hi = mid - 1;
+    }
+    const long long* e = table + (long long)lo * 8;
+    const float* src = reinterpret_cast<const float*>(e[0]);
+    bf16* direct = reinterpret_cast<bf16*>(e[1]);
+    bf16* transposed = reinterpret_cast<bf16*>(e[2]);
+    const int D0 = (int)e[3], T = (int)e[4], D1 = (int)e[5], D1p = (int)e[6], D0p = (int)e[7];
+    const int t1 = (D1 + 31) / 32;
+    const long long tile_id = flat - cum[lo];
     const int b1 = (int)(tile_id % t1);
     const long long r = tile_id / t1;
     const int t = (int)(r % T);
@@ -134,7 +153,8 @@ extern "C" int gcc_clamp_f32(float* x, long long n, float lo, float hi, void* st
 // table: device int64 [count][8] = {src fp32 ptr, direct bf16 ptr, transposed bf16 ptr, D0, T, D1, D1p, D0p}
 extern "C" int gcc_pack_weights_table(const void* table_dev, int count, void* stream) {
   if (count <= 0) return GCC_OK;
-  pack_table_kernel<<<dim3(128, count), 256, 0, (cudaStream_t)stream>>>((const long long*)table_dev);
+  pack_table_kernel<<<148 * 8, 256, sizeof(long long) * (count + 1), (cudaStream_t)stream>>>(
+      (const long long*)table_dev, count);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

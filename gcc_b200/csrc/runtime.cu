@@ -59,6 +59,13 @@ PFN_encodeTiled gcc_get_encode_tiled() {
 
 int gcc_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_bytes, const uint32_t* box) {
+  return gcc_make_tmap_bf16_sw(map, base, rank, dims, strides_bytes, box, 1);
+}
+
+// swizzle128 = 0: plain (un-swizzled) box, used for the 8-channel image operand whose 16-byte pixels land as
+// canonical no-swizzle core matrices
+int gcc_make_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
   PFN_encodeTiled enc = gcc_get_encode_tiled();
   if (!enc) return GCC_ERR_DRIVER;
   cuuint64_t gdims[5];
@@ -72,7 +79,8 @@ int gcc_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint6
     if (i + 1 < rank) gstrides[i] = strides_bytes[i];
   }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides,
-                   gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];

@@ -123,6 +123,19 @@ class ConvFn(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+def _tap_major_weight(layer, pack, c):
+    """Rows of ``pack`` ([c][16 taps][K] bf16) re-ordered tap-major with the channels padded to a group of 4
+    or 8 (zero rows): the GEMM then writes columns col2im can read with one 8/16-byte load per tap.  The
+    buffer lives on the layer (allocated once, refreshed from the current pack on every call)."""
+    cg = 4 if c <= 4 else 8
+    buf = getattr(layer, "_tapw", None)
+    if buf is None or buf.shape[2] != pack.shape[2] or buf.device != pack.device:
+        buf = torch.zeros(16, cg, pack.shape[2], dtype=torch.bfloat16, device=pack.device)
+        layer._tapw = buf
+    buf[:, :c].copy_(pack[:c].permute(1, 0, 2))
+    return buf, cg, (2 if cg == 4 else 0)
+
+
 class ColConvFn(torch.autograd.Function):
     """k4 s2 p1 Conv2d with <= 8 input channels / ConvTranspose2d with <= 8 output channels: the image side is
     expanded by im2col / folded by col2im (16 taps x 8 channels = one 128-wide GEMM dimension) and the
@@ -140,23 +153,22 @@ class ColConvFn(torch.autograd.Function):
         if layer.kind == "conv":
             oh, ow = h // 2, w // 2
             cop = rp8(layer.cout)
-            xcol = torch.empty(n, oh, ow, 128, dtype=torch.bfloat16, device=x.device)
-            call("gcc_im2col_k4s2_c8", x.data_ptr(), xcol.data_ptr(), n, h, w, st)
+            # the GEMM kernel gathers the 16 taps x 8 channels itself (image mode: K = 128 straight from the image)
             y = torch.empty(n, oh, ow, cop, dtype=torch.bfloat16, device=x.device)
             epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
-            call("gcc_conv_gemm_bf16", xcol.data_ptr(), n, oh, ow, 128, pk.direct.data_ptr(), layer.cout, 1, 128, bp,
-                 y.data_ptr(), oh, ow, cop, 0, 0, 1, 1, 1, 0, epi, slope, 0, None, 0, None, 0, st)
-            saved = xcol
+            call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, 8, pk.direct.data_ptr(), layer.cout, 16, 8, bp,
+                 y.data_ptr(), oh, ow, cop, 0, 0, 4, 4, 2, 1, epi, slope, 0, None, 0, None, 0, st)
+            saved = x
         else:
             oh, ow = 2 * h, 2 * w
-            ycol = torch.empty(n, h, w, 128, dtype=torch.bfloat16, device=x.device)
-            wp = pk.transposed  # [cout][16][cin_p] viewed as [cout*16][1][cin_p]
-            call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), layer.cout * 16, 1, wp.shape[2], None,
-                 ycol.data_ptr(), h, w, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
+            wp, cg, order = _tap_major_weight(layer, pk.transposed, layer.cout)  # [16*cg][cin_p]
+            ycol = torch.empty(n, h, w, 16 * cg, dtype=torch.bfloat16, device=x.device)
+            call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), 16 * cg, 1, wp.shape[2], None,
+                 ycol.data_ptr(), h, w, 16 * cg, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
             y = torch.empty(n, oh, ow, 8, dtype=torch.bfloat16, device=x.device)
             if act not in (ACT_NONE, ACT_TANH):
                 raise _lib.GccB200Error("col-path ConvTranspose supports none/tanh epilogues")
-            call("gcc_col2im_k4s2_c8", ycol.data_ptr(), 128, 1, layer.cout, bp, 2 if act == ACT_TANH else 0,
+            call("gcc_col2im_k4s2_c8", ycol.data_ptr(), 16 * cg, order, layer.cout, bp, 2 if act == ACT_TANH else 0,
                  y.data_ptr(), n, oh, ow, st)
             saved = x
         ctx.layer, ctx.act, ctx.slope = layer, act, slope
@@ -183,19 +195,20 @@ class ColConvFn(torch.autograd.Function):
         dx = None
         if layer.kind == "conv":
             _, oh, ow, cop = dpre.shape
-            xcol = saved
             if ctx.needs_input_grad[0]:
                 layer.arena.ensure_packed()
-                wp = pk.transposed  # [cin][16][cout_p] viewed as [cin*16][1][cout_p]
-                dcol = torch.empty(n, oh, ow, 128, dtype=torch.bfloat16, device=dev)
-                call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin * 16, 1,
-                     wp.shape[2], None, dcol.data_ptr(), oh, ow, 128, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
+                wp, cg, order = _tap_major_weight(layer, pk.transposed, layer.cin)  # [16*cg][cout_p]
+                dcol = torch.empty(n, oh, ow, 16 * cg, dtype=torch.bfloat16, device=dev)
+                call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), 16 * cg, 1,
+                     wp.shape[2], None, dcol.data_ptr(), oh, ow, 16 * cg, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0,
+                     st)
                 dx = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=dev)
-                call("gcc_col2im_k4s2_c8", dcol.data_ptr(), 128, 1, layer.cin, None, 0, dx.data_ptr(), n, h, w, st)
+                call("gcc_col2im_k4s2_c8", dcol.data_ptr(), 16 * cg, order, layer.cin, None, 0, dx.data_ptr(), n, h, w,
+                     st)
             if ctx.needs_input_grad[1]:
                 tmp = torch.empty(layer.cout, 128, dtype=torch.float32, device=dev)
-                call("gcc_wgrad_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, xcol.data_ptr(), oh, ow, 128,
-                     tmp.data_ptr(), layer.cout, 128, 1, 1, 1, 0, 0, 0, 1.0, st)
+                call("gcc_wgrad_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, saved.data_ptr(), h, w, 8,
+                     tmp.data_ptr(), layer.cout, 8, 4, 4, 2, 1, 0, 0, 1.0, st)
                 call("gcc_unpad_wgrad_c8", tmp.data_ptr(), layer.arena.flat_grad[layer.wname].data_ptr(), layer.cout,
                      layer.cin, st)
             npix_out = n * oh * ow

@@ -120,7 +120,8 @@ int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w, void* dxp,
 /* k4 s2 p1 layers with <= 8 image-side channels (first conv of PatchGAN / U-Net, Pix2Pix.py:31,280,320; last
  * ConvTranspose of the U-Net, Pix2Pix.py:40): 16 taps x 8 channels become one 128-wide GEMM dimension.
  * im2col: col[n,oh,ow,(kh*4+kw)*8+c] = img[n,2oh+kh-1,2ow+kw-1,c]; img [N,H,W,8], col [N,H/2,W/2,128].
- * col2im: img[n,iy,ix,c] = act(bias[c] + sum_taps col[...]) (order 0: tap-major index, 1: c*16+tap); act 2 = tanh.
+ * col2im: img[n,iy,ix,c] = act(bias[c] + sum_taps col[...]) (order 0: index tap*8+c, 1: c*16+tap, 2: tap*4+c with C <= 4);
+ * act 2 = tanh.
  * unpad_wgrad: g[r][tap][c] += tmp[r][tap*8+c] for c < C. */
 int gcc_im2col_k4s2_c8(const void* img, void* col, int N, int H, int W, void* stream);
 int gcc_col2im_k4s2_c8(const void* col, int Ccol, int order, int C, const float* bias, int act, void* img, int N,
