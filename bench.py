@@ -34,6 +34,7 @@ def parse_args():
     p.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     p.add_argument("--trace", type=int, default=0, help="debug: after warm-up run one eager step with per-GEMM-launch "
                    "event timing logged to stderr (GCCTRACE lines) and exit without a bench line")
+    p.add_argument("--watchdog_s", type=int, default=600, help="abort the whole process after this many seconds")
     p.add_argument("--ngf", type=int, default=32)
     p.add_argument("--teacher_ngf", type=int, default=64)
     p.add_argument("--ndf", type=int, default=128)
@@ -204,8 +205,23 @@ def dominant_kernel_roofline(batch, pk):
             "avg_launch_ms": ms, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
 
 
+def _watchdog(seconds):
+    """A hung collective or kernel must not hold the GPU box: give up loudly after `seconds`."""
+    import threading
+
+    def bark():
+        sys.stderr.write("bench.py: watchdog expired after %d s, aborting\n" % seconds)
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, bark)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def run_b200(args):
     import torch
+    _watchdog(args.watchdog_s)
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

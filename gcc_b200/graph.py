@@ -31,6 +31,7 @@ class GraphedIteration:
             t.copy_(data[k], non_blocking=True)
 
     def capture(self, data, warmup=3):
+        from . import pix2pix
         self.load(data)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -39,12 +40,48 @@ class GraphedIteration:
                 self._iteration()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=side):
-            self._iteration()
+        if not pix2pix._dist_on():
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self._iteration()
+            self.segments = [(self.graph, None)]
+            return self
+        # Data parallel: the iteration is captured as a chain of graphs cut at every gradient exchange (five per
+        # iteration); run() replays a segment, launches the NCCL all-reduce of that optimizer group's flat
+        # gradient arena eagerly on the same stream, replays the next segment (which starts with the Adam step).
+        # All segments share one memory pool and are always replayed in capture order.
+        self.segments = []
+        pool = torch.cuda.graph_pool_handle()
+        state = {"g": None}
+
+        def begin():
+            state["g"] = torch.cuda.CUDAGraph()
+            state["g"].capture_begin(pool=pool)
+
+        def cut(arena):
+            state["g"].capture_end()
+            self.segments.append((state["g"], arena))
+            begin()
+
+        with torch.cuda.stream(side):
+            begin()
+            pix2pix._graph_segmenter = cut
+            try:
+                self._iteration()
+            finally:
+                pix2pix._graph_segmenter = None
+            state["g"].capture_end()
+            self.segments.append((state["g"], None))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = self.segments[0][0]
         return self
 
     def run(self, data):
+        from . import pix2pix
         self.load(data)
-        self.graph.replay()
+        for g, arena in self.segments:
+            g.replay()
+            if arena is not None:
+                pix2pix._allreduce_grads(arena)
         self.replays += 1

@@ -48,11 +48,24 @@ def _dist_on():
         torch.distributed.get_world_size() > 1
 
 
+# Set by gcc_b200.graph.GraphedIteration while it captures a data-parallel iteration: the gradient exchange is a
+# cut point between two CUDA graphs (the collective itself is launched eagerly between the replays).
+_graph_segmenter = None
+
+
 def _allreduce_grads(arena):
     """Data parallel: average the flat gradient arena over ranks (NCCL over NVLink) before the step."""
-    if _dist_on():
-        torch.distributed.all_reduce(arena.G, op=torch.distributed.ReduceOp.SUM)
-        arena.G.mul_(1.0 / torch.distributed.get_world_size())
+    if not _dist_on():
+        return
+    if _graph_segmenter is not None:
+        _graph_segmenter(arena)
+        return
+    dist = torch.distributed
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(arena.G, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(arena.G, op=dist.ReduceOp.SUM)
+        arena.G.mul_(1.0 / dist.get_world_size())
 
 
 class _LambdaLR:
