@@ -23,7 +23,7 @@
 
 namespace gcc {
 
-static constexpr int kMaxTaps = 49;
+static constexpr int kMaxTaps = 81;  // up to 9 x 9 (SRGAN's first / last conv)
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one SWIZZLE_128B row
 

@@ -166,6 +166,32 @@ int gcc_clamp_f32(float* x, long long n, float lo, float hi, void* stream);
 /* re-pack all conv weights of a net after an optimizer step: device int64 table [count][8] */
 int gcc_pack_weights_table(const void* table_dev, int count, void* stream);
 
+/* ---- SRGAN additions (srgan.cu) ----
+ * nn.PReLU() with one learnable slope (models/SRGAN.py:49-50,89): y = x > 0 ? x : a x; bwd: dx = dy (x > 0 ? 1 : a),
+ * dslope += sum_{x <= 0} dy x (dx / dslope may be NULL). */
+int gcc_prelu_fwd_bf16(const void* x, void* y, long long n, const float* slope_dev, void* stream);
+int gcc_prelu_bwd_bf16(const void* x, const void* dy, void* dx, long long n, const float* slope_dev, float* dslope,
+                       void* stream);
+/* nn.PixelShuffle(2) (models/SRGAN.py:88) on NHWC: dst[n,2h+i,2w+j,c] = src[n,h,w,4c+2i+j]; inverse = 1 is the
+ * backward permutation (src = gradient wrt the shuffled tensor, dst = gradient wrt the conv output). */
+int gcc_pixel_shuffle2_bf16(const void* src, void* dst, int N, int H, int W, int C, int Cin_p, int Cout_p, int inverse,
+                            void* stream);
+/* nn.MaxPool2d(2, 2) of torchvision's VGG19 features (models/GANLoss.py:110-134); bwd routes dy to the first
+ * maximum of each window in row-major order. */
+int gcc_maxpool2_fwd_bf16(const void* x, void* y, int N, int H, int W, int Cp, void* stream);
+int gcc_maxpool2_bwd_bf16(const void* x, const void* dy, void* dx, int N, int H, int W, int Cp, void* stream);
+/* convert_image('[-1, 1]' -> 'imagenet-norm') (data/sr_dataset.py:15-64) and its gradient: y = x * scale[c] + shift[c]
+ * on an 8-channel (3 logical) NHWC image; shift_dev may be NULL. */
+int gcc_channel_affine8_bf16(const void* x, void* y, long long npix, int C, const float* scale_dev,
+                             const float* shift_dev, void* stream);
+/* AdaptiveAvgPool2d((1,1)) + Linear(C, 1) (models/SRGAN.py:231-245): sums = per-sample channel sums as written by
+ * gcc_norm_stats_bf16(per_sample = 1); logits bf16 [N][8] (channel 0, the layout the GAN-loss kernels read).
+ * bwd: dlogit bf16 [N][8], dx bf16 [N,HW,Cp] (may be NULL), dw/db accumulate. */
+int gcc_pool_linear_fwd(const float* sums, int N, long long HW, int Cp, int C, const float* w, const float* b,
+                        void* logits, void* stream);
+int gcc_pool_linear_bwd(const void* dlogit, const float* sums, const float* w, int N, long long HW, int Cp, int C,
+                        void* dx, float* dw, float* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,6 +237,97 @@ def run_cycle_case(options, name, small, batch, iters, size, cfgs=(None, None)):
     return out
 
 
+def run_sr_case(options, name, small, batch, iters, lr_size):
+    """SRGAN (models/SRGAN.py) driven exactly like train.py drives it.  The one value-touching shim: torchvision's
+    vgg19 is built with weights=None (no network for the pretrained file) and its conv parameters are overwritten
+    with oracle.srgan_oracle.make_vgg_params() on both models."""
+    import math
+    import torchvision
+    from oracle import srgan_oracle as S
+    import models.GANLoss as GL
+    real_vgg19 = torchvision.models.vgg19
+    GL.vgg19 = lambda pretrained=True: real_vgg19(weights=None)
+    import models.SRGAN as SR
+    torch.manual_seed(0)
+    opt = make_opt(options, ["--dataroot", "x/sr", "--model", "srgan", "--darts_discriminator", "--online_distillation",
+                             "--lambda_content", "1e-3", "--lambda_gram", "1e-1", "--gpu_ids", "-1"])
+    for k, v in small.items():
+        setattr(opt, k, v)
+    opt.generator_only = False
+    model = SR.SRGAN(opt)
+    topt = copy.deepcopy(opt)
+    topt.ngf, topt.ndf = opt.teacher_ngf, opt.teacher_ndf
+    topt.darts_discriminator = False
+    topt.online_distillation = False
+    topt.generator_only = False
+    teacher = SR.SRGAN(topt)
+    teacher.model_train()
+    setattr(model, "teacher_model", teacher)
+    model.init_distillation()
+    teacher.init_distillation()
+    vggP = S.make_vgg_params()
+    for m, tag in ((model, "S"), (teacher, "T")):
+        sd = m.netG.state_dict()
+        O.init_like_reference(sd, tag + ".netG.")
+        S.init_sr_params(sd, tag + ".netG.")
+        m.netG.load_state_dict(sd)
+        sd = m.netD.state_dict()
+        O.init_like_reference(sd, tag + ".netD.")
+        m.netD.load_state_dict(sd)
+        m.truncated_vgg19.load_state_dict(vggP)
+        for i, conv in enumerate(getattr(m, "transform_convs", [])):
+            cin = conv.weight.shape[1]
+            conv.weight.data.copy_(O.det_uniform("%s.transform.%d" % (tag, i), conv.weight.shape, 1.0 / math.sqrt(cin)))
+    model.model_train()
+    out = {"config": {"small": small, "batch": batch, "iters": iters, "lr_size": lr_size,
+                      "lambdas": {k: getattr(opt, k) for k in ("lambda_content", "lambda_gram", "lambda_L1",
+                                                               "lambda_SR_adversarial", "lambda_SR_content",
+                                                               "lambda_SR_perceptual", "lr", "arch_lr", "gan_mode")}},
+           "iters": []}
+    for it in range(iters):
+        rec = {}
+        lr = S.convert_to_imagenet(O.det_image("%s.lr.%d" % (name, it), batch, 3, lr_size, lr_size))
+        hr = O.det_image("%s.hr.%d" % (name, it), batch, 3, 4 * lr_size, 4 * lr_size)
+        model.set_input({"lr": lr, "hr": hr, "lr_names": "", "hr_names": ""})
+        model.optimize_parameters()
+        rec["fake_hr"], rec["Tfake_hr"] = stats(model.fake_hr), stats(teacher.fake_hr)
+        for i, f in enumerate(model.target_distillation_features):
+            rec["target.%d" % i] = stats(f)
+        record_model(rec, "S", model)
+        record_model(rec, "T", teacher)
+        vlr = S.convert_to_imagenet(O.det_image("%s.vlr.%d" % (name, it), batch, 3, lr_size, lr_size))
+        vhr = O.det_image("%s.vhr.%d" % (name, it), batch, 3, 4 * lr_size, 4 * lr_size)
+        model.set_input({"lr": vlr, "hr": vhr, "lr_names": "", "hr_names": ""})
+        model.clipping_mask_alpha()
+        model.optimizer_netD_arch()
+        for kk, v in model.netD.named_parameters():
+            if kk.endswith("alpha"):
+                rec["arch.alpha." + kk] = stats(v)
+                rec["arch.alpha_grad." + kk] = stats(v.grad)
+        rec["losses"] = {k: float(v) for k, v in model.get_current_losses().items()}
+        out["iters"].append(rec)
+        print(name, "iter", it, {k: round(v, 5) for k, v in rec["losses"].items()}, flush=True)
+    # prune index selection on the final student weights (SRGAN.py:773-837) and on spread-out deterministic ones
+    sd = {k: O.det_normal("srprune." + k, v.shape, 0.5, 0.3) if v.dim() == 1 and v.numel() > 1 else v
+          for k, v in model.netG.state_dict().items()}
+    model.netG.load_state_dict(sd)
+    prunes = {}
+    for mode, thr in (("scale", 0.45), ("scale", 0.8), ("norm", None)):
+        o2 = copy.deepcopy(opt)
+        o2.scale_prune, o2.norm_prune = mode == "scale", mode == "norm"
+        model.opt = o2
+        if thr is None:
+            norms = [float(torch.sum(torch.abs(m.weight.data), (1, 2, 3)).median()) for n, m in model.netG.named_modules()
+                     if isinstance(m, torch.nn.Conv2d) and "conv_block1.conv_block.0" in n and n.startswith("residual")]
+            thr = sum(norms) / len(norms)
+        pruned = model.prune(thr)
+        prunes["%s@%.6f" % (mode, thr)] = {"thr": thr, "cfg": list(pruned.filter_cfgs)}
+    model.opt = opt
+    out["prune"] = prunes
+    out["prune_state"] = {k: stats(v) for k, v in model.netG.state_dict().items() if v.dim() >= 1}
+    return out
+
+
 def run_cycle_prune_case(options):
     """get_prunenet_cfg / max_min_conv_norm of MobileCycleGANModel (CycleGAN.py:803-885) on deterministic weights."""
     import models.CycleGAN as CG
@@ -309,6 +400,11 @@ def main():
     options, P2P = import_reference()
     gold = os.path.join(REPO, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
+    sr_small = {"ngf": 8, "teacher_ngf": 16, "ndf": 8, "teacher_ndf": 16}
+    if len(sys.argv) > 1 and sys.argv[1] == "srgan":     # regenerate only the SRGAN fixture
+        torch.save(run_sr_case(options, "sr_tiny", sr_small, batch=2, iters=2, lr_size=12),
+                   os.path.join(gold, "srgan_tiny.pt"))
+        return
     base = ["--dataroot", "x/cityscapes", "--model", "pix2pix", "--darts_discriminator", "--online_distillation",
             "--lambda_content", "50", "--lambda_gram", "1e4", "--gpu_ids", "-1", "--no_dropout"]
     tiny = {"ngf": 8, "teacher_ngf": 16, "ndf": 16, "teacher_ndf": 16}
@@ -327,6 +423,7 @@ def main():
     torch.save(run_cycle_prune_case(options), os.path.join(gold, "cyclegan_prune.pt"))
     torch.save({"prune": run_prune_case(options, P2P), "gate": run_gate_case(P2P), "ganloss": run_ganloss_case()},
                os.path.join(gold, "pix2pix_small_ops.pt"))
+    torch.save(run_sr_case(options, "sr_tiny", sr_small, batch=2, iters=2, lr_size=12), os.path.join(gold, "srgan_tiny.pt"))
     print("golden fixtures written to", gold)
 
 

@@ -217,3 +217,79 @@ def test_oracle_cyclegan_matches_reference(golden_dir):
         assert set(losses) == set(rec["losses"])
         for n, v in rec["losses"].items():
             assert losses[n] == pytest.approx(v, rel=(5 * rtol if "arch" in n else rtol) if it == 0 else 0.25, abs=1e-5), n
+
+
+def _is_prelu(P, k):
+    return k.endswith(".weight") and P[k].dim() == 1 and P[k].numel() == 1 and (k[:-6] + "running_mean") not in P
+
+
+def test_oracle_srgan_matches_reference(golden_dir):
+    """SRGAN: oracle/srgan_oracle.py against the fixture recorded from the reference
+    (models/SRGAN.py driven like train.py:144-151; VGG branch with name-seeded random weights on both sides)."""
+    from oracle import srgan_oracle as SR
+    gold = torch.load(os.path.join(golden_dir, "srgan_tiny.pt"), weights_only=False)
+    cfg = gold["config"]
+    lam = cfg["lambdas"]
+    assert lam["gan_mode"] == "vanilla" and lam["lr"] == 1e-4
+    opt = SR.SROpt(**cfg["small"], lambda_content=lam["lambda_content"], lambda_gram=lam["lambda_gram"],
+                   lambda_L1=lam["lambda_L1"], arch_lr=lam["arch_lr"])
+    S, T = SR.build_sr_pair(opt)
+    b, ls = cfg["batch"], cfg["lr_size"]
+    rtol = 2e-3
+    step_atol = 0.05 * 1e-4 / 50
+    for it, rec in enumerate(gold["iters"]):
+        first = it == 0
+        lr = SR.convert_to_imagenet(O.det_image("sr_tiny.lr.%d" % it, b, 3, ls, ls))
+        hr = O.det_image("sr_tiny.hr.%d" % it, b, 3, 4 * ls, 4 * ls)
+        S.set_input(lr, hr)
+        S.optimize_parameters()
+        frac = 1e-4 if first else None       # 2nd iteration: norms only (Adam's first step amplifies fp32 noise)
+        r = rtol if first else 2e-2
+        _close("fake_hr", stats(S.fake_hr), rec["fake_hr"], r, frac)
+        _close("Tfake_hr", stats(T.fake_hr), rec["Tfake_hr"], r, frac)
+        for i, f in enumerate(S.target_features):
+            _close("target.%d" % i, stats(f), rec["target.%d" % i], r, frac)
+        if first:
+            for tag, M in (("S", S), ("T", T)):
+                for kind, P in (("G", M.G), ("D", M.D)):
+                    for k, v in P.items():
+                        if k.endswith("conv_block.0.bias") and (k[:-len("0.bias")] + "1.running_mean") in P:
+                            # conv bias followed by BatchNorm: the true gradient is exactly zero, the reference's is
+                            # fp32 rounding noise whose sign drives Adam (same finding as the InstanceNorm biases)
+                            continue
+                        # running means inherit the +-lr random walk of the (excluded) conv bias in front of the BN
+                        _close("%s.%s.%s" % (tag, kind, k), stats(v), rec["%s.%s.%s" % (tag, kind, k)],
+                               2e-2 if k.endswith("running_mean") else rtol,
+                               step_atol=(1e-4 if k.endswith("running_mean") else step_atol))
+                        key = "%s.%s.grad.%s" % (tag, kind, k)
+                        if v.dtype != torch.float32 or v.grad is None or k.endswith("alpha"):
+                            continue
+                        if _is_prelu(P, k):
+                            # one scalar summed over the whole activation with mixed signs: absolute tolerance
+                            assert float(v.grad) == pytest.approx(rec[key]["samples"][0], rel=2e-2, abs=5e-6), key
+                        else:
+                            _close(key, stats(v.grad), rec[key], 10 * rtol, 1e-3)
+            for i, w in enumerate(S.transform):
+                _close("transform.%d" % i, stats(w), rec["S.transform.%d" % i], rtol, step_atol=step_atol)
+                _close("transform.grad.%d" % i, stats(w.grad), rec["S.transform.grad.%d" % i], 10 * rtol, 1e-3)
+        vlr = SR.convert_to_imagenet(O.det_image("sr_tiny.vlr.%d" % it, b, 3, ls, ls))
+        vhr = O.det_image("sr_tiny.vhr.%d" % it, b, 3, 4 * ls, 4 * ls)
+        S.set_input(vlr, vhr)
+        S.clipping_mask_alpha()
+        S.optimizer_netD_arch()
+        for k, v in S.D.items():
+            if k.endswith("alpha"):
+                if first:
+                    _close("alpha_grad." + k, stats(v.grad), rec["arch.alpha_grad." + k], 10 * rtol, 1e-3)
+                _close("alpha." + k, stats(v), rec["arch.alpha." + k], rtol, step_atol=step_atol)
+        losses = S.get_current_losses()
+        for k, v in rec["losses"].items():
+            assert losses[k] == pytest.approx(v, rel=rtol if first else 3e-2, abs=1e-5), (it, k)
+    # prune index selection (SRGAN.py:773-837): bit-exact channel counts at the recorded thresholds
+    G = {k: (O.det_normal("srprune." + k, v.shape, 0.5, 0.3) if v.dim() == 1 and v.numel() > 1 and v.dtype == torch.float32
+             else v.detach()) for k, v in S.G.items()}
+    for key, ent in gold["prune"].items():
+        fn = SR.sr_scale_prune_cfg if key.startswith("scale") else SR.sr_norm_prune_cfg
+        if key.startswith("norm"):
+            continue  # depends on the trained conv weights of the reference run (covered by the scale variants + unit test)
+        assert fn(G, ent["thr"]) == ent["cfg"], key
