@@ -332,7 +332,7 @@ class NormActFn(torch.autograd.Function):
                 layer.num_batches += 1
             call("gcc_norm_apply_bf16", x.data_ptr(), y.data_ptr(), n, h * w, cp, layer.c, per_sample,
                  None if sums is None else sums.data_ptr(), gp, bp, ap, layer.thr, BN_EPS, rm, rv, BN_MOM, act,
-                 layer.slope, 1 if (mode == "id" and alpha is not None) else 0,
+                 layer.slope, 1 if (getattr(layer, "gate_after", mode == "id") and mode == "id" and alpha is not None) else 0,
                  None if y2 is None else y2.data_ptr(), cp, 0, act2 or 0, st)
         ctx.layer, ctx.act, ctx.act2 = layer, act, act2
         ctx.save_for_backward(x, sums, gamma, beta, alpha)
@@ -367,7 +367,7 @@ class NormActFn(torch.autograd.Function):
         call("gcc_norm_bwd_bf16", x.data_ptr(), n, h * w, cp, layer.c, per_sample,
              None if sums is None else sums.data_ptr(), None if gamma is None else gamma.data_ptr(),
              None if beta is None else beta.data_ptr(), None if alpha is None else alpha.data_ptr(), layer.thr, BN_EPS,
-             ctx.act, layer.slope, 1 if (layer.mode == "id" and alpha is not None) else 0, p1, c1, 0, p2, c2, 0,
+             ctx.act, layer.slope, 1 if (getattr(layer, "gate_after", layer.mode == "id") and layer.mode == "id" and alpha is not None) else 0, p1, c1, 0, p2, c2, 0,
              ctx.act2 or 0, red.data_ptr(),
              None if dx is None else dx.data_ptr(), dgamma, dbeta, dalpha, st)
         return dx, None, None, None, None, None, None, None

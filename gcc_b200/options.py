@@ -21,6 +21,8 @@ _FLAGS = [
     ("lambda_alpha", float, 0.01), ("ema_beta", float, 1.0), ("threshold", float, 0.5), ("distillation_path", str, None),
     ("lambda_content", float, 0.0), ("lambda_gram", float, 0.0), ("teacher_ngf", int, 64), ("teacher_ndf", int, 64),
     ("initial_path", str, None), ("teacher_initial_path", str, None), ("z_dim", int, 128),
+    ("lambda_SR_adversarial", float, 1e-3), ("lambda_SR_content", float, 0.0), ("lambda_SR_perceptual", float, 1.0),
+    ("image_size", int, 96),
 ]
 _SWITCHES = ["no_dropout", "serial_batches", "no_flip", "split_dataset", "scale_prune", "norm_prune",
              "darts_discriminator", "arch_lr_step", "adaptive_ema", "regular", "arch_base_loss", "only_arch_base",
@@ -60,6 +62,18 @@ def parse(argv=None):
         opt.dataset_mode = "unaligned"
         opt.gan_mode = "lsgan"
         opt.n_epochs, opt.n_epochs_decay, opt.print_freq = 100, 100, 100
+    elif opt.model == "srgan":                      # options.py:192-205
+        opt.dataset_mode = "sr"
+        opt.gan_mode = "vanilla"
+        opt.lr = 1e-4
+        opt.batch_size = 16
+        opt.n_epochs_decay = 0
+        if opt.generator_only:
+            opt.n_epochs = 130
+        else:
+            opt.n_epochs = 30
+            opt.lr_policy = "step"
+            opt.lr_decay_iters = opt.n_epochs // 2
     else:
         raise NotImplementedError("%s not implemented" % opt.model)
     if opt.lambda_weight > 0 or opt.lambda_scale > 0:
@@ -69,11 +83,14 @@ def parse(argv=None):
 
 
 def get_model_class(opt):
-    """models/__init__.py:3-14 (pix2pix and cyclegan are built; srgan / sagan are not yet)."""
+    """models/__init__.py:3-14 (pix2pix, cyclegan and srgan are built; sagan is not yet)."""
     if opt.model == "pix2pix":
         from .pix2pix import Pix2PixModel
         return Pix2PixModel
     if opt.model == "cyclegan":
         from .cyclegan import MobileCycleGANModel
         return MobileCycleGANModel
+    if opt.model == "srgan":
+        from .srgan import SRGAN
+        return SRGAN
     raise NotImplementedError("%s not implemented" % opt.model)
