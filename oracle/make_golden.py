@@ -328,6 +328,84 @@ def run_sr_case(options, name, small, batch, iters, lr_size):
     return out
 
 
+def run_sa_case(options, name, small, batch, iters):
+    """SAGANModel (models/SAGAN.py) driven exactly like train.py drives it (image size 64, the only one it supports).
+    Shim: the integer Adam betas (0, 0.9) of SAGAN.py:302,327,346,356 are coerced to floats."""
+    import math
+    from oracle import sagan_oracle as SA
+    import models.SAGAN as SG
+    torch.manual_seed(0)
+    opt = make_opt(options, ["--dataroot", "x/celeb", "--model", "sagan", "--darts_discriminator", "--online_distillation",
+                             "--lambda_content", "1e-3", "--lambda_gram", "1e-1", "--gpu_ids", "-1"])
+    for k, v in small.items():
+        setattr(opt, k, v)
+    # shim (SURVEY 8c.4): this torch rejects integer betas (0, 0.9): coerce to floats, nothing else changes
+    real_adam = torch.optim.Adam
+
+    class _FloatBetasAdam(real_adam):
+        def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), **kw):
+            super().__init__(params, lr=lr, betas=(float(betas[0]), float(betas[1])), **kw)
+    torch.optim.Adam = _FloatBetasAdam
+    try:
+        model = SG.SAGANModel(opt)
+        topt = copy.deepcopy(opt)
+        topt.ngf, topt.ndf = opt.teacher_ngf, opt.teacher_ndf
+        topt.darts_discriminator = False
+        topt.online_distillation = False
+        topt.generator_only = False
+        teacher = SG.SAGANModel(topt)
+    finally:
+        torch.optim.Adam = real_adam
+    teacher.model_train()
+    setattr(model, "teacher_model", teacher)
+    model.init_distillation()
+    teacher.init_distillation()
+    sopt = SA.SAOpt(**small)
+    S, T = SA.build_sa_pair(sopt)
+    for m, orc, tag in ((model, S, "S"), (teacher, T, "T")):
+        m.netG.load_state_dict({k: v.detach().clone() for k, v in orc.G.items()})
+        m.netD.load_state_dict({k: v.detach().clone() for k, v in orc.D.items()})
+        for i, conv in enumerate(getattr(m, "transform_convs", [])):
+            conv.weight.data.copy_(orc.transform[i].detach())
+    model.model_train()
+    out = {"config": {"small": small, "batch": batch, "iters": iters,
+                      "opts": {k: getattr(opt, k) for k in ("lambda_content", "lambda_gram", "lambda_L1", "lr", "arch_lr",
+                                                            "gan_mode", "z_dim", "crop_size")}}, "iters": []}
+    for it in range(iters):
+        rec = {}
+        z = O.det_normal("%s.z.%d" % (name, it), (batch, opt.z_dim))
+        real = O.det_image("%s.real.%d" % (name, it), batch, 3, 64, 64)
+        model.set_input({"z": z, "real_img": real, "img_path": ""})
+        model.optimize_parameters()
+        rec["fake_img"], rec["Tfake_img"] = stats(model.fake_img), stats(teacher.fake_img)
+        for i, f in enumerate(model.target_distillation_features):
+            rec["target.%d" % i] = stats(f)
+        record_model(rec, "S", model)
+        record_model(rec, "T", teacher)
+        vz = O.det_normal("%s.vz.%d" % (name, it), (batch, opt.z_dim))
+        vreal = O.det_image("%s.vreal.%d" % (name, it), batch, 3, 64, 64)
+        model.set_input({"z": vz, "real_img": vreal, "img_path": ""})
+        model.clipping_mask_alpha()
+        model.optimizer_netD_arch()
+        for kk, v in model.netD.named_parameters():
+            if kk.endswith("alpha"):
+                rec["arch.alpha." + kk] = stats(v)
+                rec["arch.alpha_grad." + kk] = stats(v.grad)
+        rec["losses"] = {k: float(v) for k, v in model.get_current_losses().items()}
+        out["iters"].append(rec)
+        print(name, "iter", it, {k: round(v, 5) for k, v in rec["losses"].items()}, flush=True)
+    o2 = copy.deepcopy(opt)
+    o2.scale_prune = True
+    model.opt = o2
+    torch.optim.Adam = _FloatBetasAdam
+    try:
+        out["prune"] = {"%g" % thr: list(model.prune(thr).filter_cfgs) for thr in (0.98, 1.0, 1.02)}
+    finally:
+        torch.optim.Adam = real_adam
+    out["prune_state"] = {k: v.clone() for k, v in model.netG.state_dict().items() if k.endswith(".1.weight")}
+    return out
+
+
 def run_cycle_prune_case(options):
     """get_prunenet_cfg / max_min_conv_norm of MobileCycleGANModel (CycleGAN.py:803-885) on deterministic weights."""
     import models.CycleGAN as CG
@@ -401,6 +479,10 @@ def main():
     gold = os.path.join(REPO, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
     sr_small = {"ngf": 8, "teacher_ngf": 16, "ndf": 8, "teacher_ndf": 16}
+    sa_small = {"ngf": 16, "teacher_ngf": 32, "ndf": 16, "teacher_ndf": 32}
+    if len(sys.argv) > 1 and sys.argv[1] == "sagan":     # regenerate only the SAGAN fixture
+        torch.save(run_sa_case(options, "sa_tiny", sa_small, batch=4, iters=2), os.path.join(gold, "sagan_tiny.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "srgan":     # regenerate only the SRGAN fixture
         torch.save(run_sr_case(options, "sr_tiny", sr_small, batch=2, iters=2, lr_size=12),
                    os.path.join(gold, "srgan_tiny.pt"))
@@ -424,6 +506,7 @@ def main():
     torch.save({"prune": run_prune_case(options, P2P), "gate": run_gate_case(P2P), "ganloss": run_ganloss_case()},
                os.path.join(gold, "pix2pix_small_ops.pt"))
     torch.save(run_sr_case(options, "sr_tiny", sr_small, batch=2, iters=2, lr_size=12), os.path.join(gold, "srgan_tiny.pt"))
+    torch.save(run_sa_case(options, "sa_tiny", sa_small, batch=4, iters=2), os.path.join(gold, "sagan_tiny.pt"))
     print("golden fixtures written to", gold)
 
 

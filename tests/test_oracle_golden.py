@@ -293,3 +293,70 @@ def test_oracle_srgan_matches_reference(golden_dir):
         if key.startswith("norm"):
             continue  # depends on the trained conv weights of the reference run (covered by the scale variants + unit test)
         assert fn(G, ent["thr"]) == ent["cfg"], key
+
+
+def test_oracle_sagan_matches_reference(golden_dir):
+    """SAGAN: oracle/sagan_oracle.py against the fixture recorded from the reference
+    (models/SAGAN.py driven like train.py:144-151), incl. the spectral-norm vectors that optimizer_D steps and the
+    parameters the student's optimizers hold twice."""
+    from oracle import sagan_oracle as SA
+    gold = torch.load(os.path.join(golden_dir, "sagan_tiny.pt"), weights_only=False)
+    cfg = gold["config"]
+    o = cfg["opts"]
+    assert o["gan_mode"] == "hinge" and o["lr"] == 1e-4 and o["crop_size"] == 64
+    opt = SA.SAOpt(**cfg["small"], lambda_content=o["lambda_content"], lambda_gram=o["lambda_gram"],
+                   lambda_L1=o["lambda_L1"], arch_lr=o["arch_lr"], z_dim=o["z_dim"])
+    S, T = SA.build_sa_pair(opt)
+    b = cfg["batch"]
+    rtol = 2e-3
+    step_atol = 0.05 * 1e-4 / 50
+    for it, rec in enumerate(gold["iters"]):
+        first = it == 0
+        z = O.det_normal("sa_tiny.z.%d" % it, (b, opt.z_dim))
+        real = O.det_image("sa_tiny.real.%d" % it, b, 3, 64, 64)
+        S.set_input(z, real)
+        S.optimize_parameters()
+        frac = 1e-4 if first else None
+        r = rtol if first else 3e-2
+        _close("fake_img", stats(S.fake_img), rec["fake_img"], r, frac)
+        _close("Tfake_img", stats(T.fake_img), rec["Tfake_img"], r, frac)
+        for i, f in enumerate(S.target_features):
+            _close("target.%d" % i, stats(f), rec["target.%d" % i], r, frac)
+        if first:
+            for tag, M in (("S", S), ("T", T)):
+                for kind, P in (("G", M.G), ("D", M.D)):
+                    for k, v in P.items():
+                        key = "%s.%s.grad.%s" % (tag, kind, k)
+                        if key in rec and math.sqrt(rec[key]["sq"] / max(rec[key]["n"], 1)) < 1e-7:
+                            # exactly-zero true gradient, the reference's value is fp32 rounding noise whose sign
+                            # drives Adam: conv bias in front of a BatchNorm, attention key bias (softmax over keys
+                            # is invariant to it), the last attention's value bias under an all-active hinge loss
+                            # (real and fake passes cancel)
+                            continue
+                        _close("%s.%s.%s" % (tag, kind, k), stats(v), rec["%s.%s.%s" % (tag, kind, k)],
+                               2e-2 if k.endswith("running_mean") else rtol,
+                               step_atol=(4e-4 if k.endswith("running_mean") else 4 * step_atol))
+                        key = "%s.%s.grad.%s" % (tag, kind, k)
+                        if v.dtype == torch.float32 and v.grad is not None and key in rec and not k.endswith("alpha"):
+                            # (attention biases: sums over all positions of near-cancelling terms -> wider sample atol)
+                            _close(key, stats(v.grad), rec[key], 10 * rtol, 5e-3 if "attn" in k else 1e-3)
+            for i, w in enumerate(S.transform):
+                _close("transform.%d" % i, stats(w), rec["S.transform.%d" % i], rtol, step_atol=step_atol)
+                _close("transform.grad.%d" % i, stats(w.grad), rec["S.transform.grad.%d" % i], 10 * rtol, 1e-3)
+        vz = O.det_normal("sa_tiny.vz.%d" % it, (b, opt.z_dim))
+        vreal = O.det_image("sa_tiny.vreal.%d" % it, b, 3, 64, 64)
+        S.set_input(vz, vreal)
+        S.clipping_mask_alpha()
+        S.optimizer_netD_arch()
+        for k, v in S.D.items():
+            if k.endswith("alpha"):
+                if first:
+                    _close("alpha_grad." + k, stats(v.grad), rec["arch.alpha_grad." + k], 10 * rtol, 1e-3)
+                _close("alpha." + k, stats(v), rec["arch.alpha." + k], rtol, step_atol=step_atol)
+        losses = S.get_current_losses()
+        for k, v in rec["losses"].items():
+            assert losses[k] == pytest.approx(v, rel=rtol if first else 5e-2, abs=1e-5), (it, k)
+    G = {k: v for k, v in S.G.items()}
+    G.update(gold["prune_state"])
+    for thr, cfgl in gold["prune"].items():
+        assert SA.scale_prune_cfg(G, float(thr)) == cfgl, thr
