@@ -40,7 +40,9 @@ class ParamArena:
         self.dirty = True
 
     def add(self, name, shape, kind="vec"):
-        """kind: 'conv' (O,I,KH,KW), 'convT' (I,O,KH,KW) or 'vec' (anything, stored contiguous)."""
+        """kind: 'conv' (O,I,KH,KW), 'convT' (I,O,KH,KW) or 'vec' (anything, stored contiguous); 'conv_nopack' /
+        'convT_nopack' store like conv / convT but keep no bf16 operand packs (spectral-normed weights are packed
+        per forward, scaled by 1 / sigma)."""
         assert not self.finalized
         self.specs.append((name, tuple(int(s) for s in shape), kind))
         return len(self.specs) - 1
@@ -88,7 +90,7 @@ class ParamArena:
     @staticmethod
     def _view(flat, o, n, shape, kind):
         seg = flat[o:o + n]
-        if kind in ("conv", "convT"):
+        if kind.startswith("conv"):
             d0, d1, kh, kw = shape
             return seg.view(d0, kh, kw, d1).permute(0, 3, 1, 2)
         return seg.view(shape)

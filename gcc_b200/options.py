@@ -74,6 +74,17 @@ def parse(argv=None):
             opt.n_epochs = 30
             opt.lr_policy = "step"
             opt.lr_decay_iters = opt.n_epochs // 2
+    elif opt.model == "sagan":                      # options.py:206-218
+        opt.dataset_mode = "sa"
+        opt.crop_size = 64
+        opt.batch_size = 64
+        opt.lr = 1e-4
+        opt.n_epochs_decay = 0
+        opt.save_epoch_freq = 5
+        if "church" in root:
+            opt.n_epochs, opt.center_crop = 300, False
+        else:
+            opt.n_epochs, opt.center_crop = 100, True
     else:
         raise NotImplementedError("%s not implemented" % opt.model)
     if opt.lambda_weight > 0 or opt.lambda_scale > 0:
@@ -83,7 +94,7 @@ def parse(argv=None):
 
 
 def get_model_class(opt):
-    """models/__init__.py:3-14 (pix2pix, cyclegan and srgan are built; sagan is not yet)."""
+    """models/__init__.py:3-14."""
     if opt.model == "pix2pix":
         from .pix2pix import Pix2PixModel
         return Pix2PixModel
@@ -93,4 +104,7 @@ def get_model_class(opt):
     if opt.model == "srgan":
         from .srgan import SRGAN
         return SRGAN
+    if opt.model == "sagan":
+        from .sagan import SAGANModel
+        return SAGANModel
     raise NotImplementedError("%s not implemented" % opt.model)

@@ -192,6 +192,32 @@ int gcc_pool_linear_fwd(const float* sums, int N, long long HW, int Cp, int C, c
 int gcc_pool_linear_bwd(const void* dlogit, const float* sums, const float* w, int N, long long HW, int Cp, int C,
                         void* dx, float* dw, float* db, void* stream);
 
+/* ---- SAGAN additions (sagan.cu) ----
+ * SpectralNorm._update_u_v (models/SAGAN.py:25-38): one power iteration IN PLACE on u [height], v [width] over the
+ * fp32 weight w_bar [height][width] (the arena's channels-last conv weight, height = weight.shape[0]);
+ * t_out [height] = w_bar v (saved for the u gradient), *sigma_out = u . (w_bar v); scratch2: 2 floats. */
+int gcc_spectral_norm_fwd(const float* w_bar, float* u, float* v, int height, int width, float* t_out, float* sigma_out,
+                          float* scratch2, void* stream);
+/* bf16 GEMM operand packs of w_bar / sigma (the weight the spectral-normed conv uses, :38) */
+int gcc_pack_weight_scaled_bf16(const float* src, const float* sigma_dev, void* direct, void* transposed, int D0, int T,
+                                int D1, int D1p, int D0p, void* stream);
+/* backward of w = w_bar / sigma, sigma = u . (w_bar v): dw_bar += (dw_eff - (s/sigma) u v^T) / sigma with
+ * s = sum(dw_eff * w_bar); du += dsigma * t_saved, dv += dsigma * w_bar^T u, dsigma = -s / sigma^2 (du, dv may be NULL:
+ * the vectors only carry a gradient after set_requires_grad(netD, True), :553-559). scratch1: 1 float. */
+int gcc_spectral_norm_bwd(const float* dw_eff, const float* w_bar, const float* u, const float* v, const float* sigma,
+                          const float* t_saved, int height, int width, float* dw_bar, float* du, float* dv, float* scratch1,
+                          void* stream);
+/* Self_Attn core (models/SAGAN.py:96-104): q, k bf16 [N][L][dp] (d logical channels), v bf16 [N][L][Cp];
+ * probs bf16 [N][L][L] = softmax_j(q_i . k_j), out[n][i][c] = sum_j probs[i][j] v[j][c]. */
+int gcc_attn_fwd_bf16(const void* q, const void* k, const void* v, int N, int L, int d, int dp, int C, int Cp, void* probs,
+                      void* out, void* stream);
+int gcc_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* probs, const void* dout, int N, int L,
+                      int d, int dp, int C, int Cp, void* de_scratch, void* dq, void* dk, void* dv, void* stream);
+/* out = gamma * a + x (Self_Attn's residual, :106); bwd: da = gamma dy, dgamma += sum dy a (dx = dy) */
+int gcc_scale_add_bf16(const void* a, const void* x, const float* gamma_dev, void* y, long long n, void* stream);
+int gcc_scale_add_bwd_bf16(const void* dy, const void* a, const float* gamma_dev, void* da, float* dgamma, long long n,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif
