@@ -76,6 +76,45 @@ __global__ void copy_channels_scalar_kernel(const bf16* __restrict__ src, int Cs
   }
 }
 
+// torch.cat of two <= 8-channel images whose channels fit one 16-byte pixel (pix2pix's cat(real_A, fake_B): 3 + 3):
+// one vector load per input pixel, one vector store.  split = the backward (either output may be NULL).
+__global__ void cat_small_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y,
+                                 int ca, int cb, long long npix) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 ua = a[i], ub = b[i];
+    const unsigned short* pa = reinterpret_cast<const unsigned short*>(&ua);
+    const unsigned short* pb = reinterpret_cast<const unsigned short*>(&ub);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    unsigned short* po = reinterpret_cast<unsigned short*>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) po[k] = k < ca ? pa[k] : (k < ca + cb ? pb[k - ca] : (unsigned short)0);
+    y[i] = o;
+  }
+}
+__global__ void split_small_kernel(const uint4* __restrict__ dy, uint4* __restrict__ da, uint4* __restrict__ db, int ca,
+                                   int cb, long long npix) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = dy[i];
+    const unsigned short* p = reinterpret_cast<const unsigned short*>(&u);
+    if (da != nullptr) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      unsigned short* po = reinterpret_cast<unsigned short*>(&o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) po[k] = k < ca ? p[k] : (unsigned short)0;
+      da[i] = o;
+    }
+    if (db != nullptr) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      unsigned short* po = reinterpret_cast<unsigned short*>(&o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) po[k] = (k < cb && k + ca < 8) ? p[k + ca] : (unsigned short)0;
+      db[i] = o;
+    }
+  }
+}
+
 // ---- activations / dropout / add ------------------------------------------------------------
 // mode 1 leaky-relu, 2 relu, 3 tanh
 __global__ void act_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long nvec, int mode,
@@ -563,6 +602,20 @@ extern "C" int gcc_copy_channels_bf16(const void* src, int Cs, int s_off, void* 
     copy_channels_scalar_kernel<<<blocks_for(npix * C), 256, 0, st>>>((const bf16*)src, Cs, s_off, (bf16*)dst, Cd,
                                                                       d_off, C, npix, accumulate);
   }
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_cat_small_bf16(const void* a, const void* b, void* y, int ca, int cb, long long npix, void* stream) {
+  if (ca < 0 || cb < 0 || ca + cb > 8) { gcc_set_error(__FILE__, __LINE__, "cat_small: ca + cb must be <= 8"); return GCC_ERR_ARG; }
+  cat_small_kernel<<<blocks_for(npix), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)y, ca, cb,
+                                                                      npix);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_split_small_bf16(const void* dy, void* da, void* db, int ca, int cb, long long npix, void* stream) {
+  if (ca < 0 || cb < 0 || ca + cb > 8) { gcc_set_error(__FILE__, __LINE__, "split_small: ca + cb must be <= 8"); return GCC_ERR_ARG; }
+  split_small_kernel<<<blocks_for(npix), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)da, (uint4*)db, ca, cb,
+                                                                        npix);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

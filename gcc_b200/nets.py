@@ -70,7 +70,7 @@ class ConvLayer:
         oh, ow = ops.conv_out_hw(h, w, self.k, self.stride, self.pad, self.kind == "convT", self.outpad)
         if self.colpath or self.headpath or n * oh * ow <= 16384 or not x.is_cuda:
             return self(x), None
-        sums = torch.zeros(2 * rp8(self.cout), dtype=torch.float32, device=x.device)
+        sums = ops.zero_pool.take(2 * rp8(self.cout), x.device)
         return ops.ConvFn.apply(x, self.weight, self.bias, self, ACT_NONE, 0.2, sums), sums
 
 

@@ -49,6 +49,35 @@ def _splitk_ws(n, oh, ow, rows, device):
     return ws.data_ptr(), elems, ws
 
 
+class _ZeroPool:
+    """Zero-initialised fp32 scratch handed out by bump allocation and re-zeroed with ONE fill per training phase
+    (``reset()`` at the start of optimize_parameters / optimizer_netD_arch) instead of one tiny fill kernel per
+    BatchNorm statistics buffer (~90 per iteration).  Only for scratch that dies with the phase's autograd graph."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def take(self, n, device):
+        ent = self.bufs.get(device)
+        if ent is None:
+            ent = self.bufs[device] = [torch.zeros(1 << 20, dtype=torch.float32, device=device), 0]
+        buf, off = ent
+        n8 = (n + 7) // 8 * 8
+        if off + n8 > buf.numel():
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        ent[1] = off + n8
+        return buf[off:off + n]
+
+    def reset(self):
+        for ent in self.bufs.values():
+            if ent[1]:
+                ent[0][:ent[1]].zero_()
+                ent[1] = 0
+
+
+zero_pool = _ZeroPool()
+
+
 def conv_out_hw(h, w, k, stride, pad, transposed, outpad=0):
     if not transposed:
         return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
@@ -434,12 +463,16 @@ class CatFn(torch.autograd.Function):
         a, b = _check(a).contiguous(), b.contiguous()
         n, h, w, _ = a.shape
         ct = rp8(ca + cb)
+        st = _st()
+        ctx.dims = (ca, cb, a.shape[3], b.shape[3])
+        if ct == 8 and a.shape[3] == 8 and b.shape[3] == 8:      # both images and the result are one vector per pixel
+            y = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=a.device)
+            call("gcc_cat_small_bf16", a.data_ptr(), b.data_ptr(), y.data_ptr(), ca, cb, n * h * w, st)
+            return y
         alloc = torch.empty if ct == ca + cb else torch.zeros
         y = alloc(n, h, w, ct, dtype=torch.bfloat16, device=a.device)
-        st = _st()
         call("gcc_copy_channels_bf16", a.data_ptr(), a.shape[3], 0, y.data_ptr(), ct, 0, ca, n * h * w, 0, st)
         call("gcc_copy_channels_bf16", b.data_ptr(), b.shape[3], 0, y.data_ptr(), ct, ca, cb, n * h * w, 0, st)
-        ctx.dims = (ca, cb, a.shape[3], b.shape[3])
         return y
 
     @staticmethod
@@ -449,6 +482,15 @@ class CatFn(torch.autograd.Function):
         n, h, w, ct = dy.shape
         st = _st()
         da = db = None
+        if ct == 8 and cap == 8 and cbp == 8:
+            if ctx.needs_input_grad[0]:
+                da = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=dy.device)
+            if ctx.needs_input_grad[1]:
+                db = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=dy.device)
+            if da is not None or db is not None:
+                call("gcc_split_small_bf16", dy.data_ptr(), None if da is None else da.data_ptr(),
+                     None if db is None else db.data_ptr(), ca, cb, n * h * w, st)
+            return da, db, None, None
         if ctx.needs_input_grad[0]:
             if ca == cap and ca % 8 == 0:
                 da = dy[..., :ca]

@@ -206,20 +206,26 @@ class Pix2PixModel(nn.Module):
 
     # ------------------------------------------------------------------ inputs / forward
     def set_input(self, input):
+        """Pix2Pix.py:453-458.  The NHWC bf16 conversions (and the host->device copies) of a batch are done once and
+        shared through the batch dict: the teacher's ``set_input(self.input)`` (Pix2Pix.py:568,587) reuses them."""
         self.input = input
         AtoB = self.opt.direction == "AtoB"
-        A = input["A" if AtoB else "B"].to(self.device, non_blocking=True)
-        B = input["B" if AtoB else "A"].to(self.device, non_blocking=True)
-        self.image_paths = [input.get("A_paths" if AtoB else "B_paths"), input.get("B_paths" if AtoB else "A_paths")]
+        ka, kb = ("A", "B") if AtoB else ("B", "A")
+        ta, tb = input[ka], input[kb]
+        self.image_paths = [input.get(ka + "_paths"), input.get(kb + "_paths")]
+        key = (ka, ta.data_ptr(), ta._version, tb.data_ptr(), tb._version, str(self.device))
+        cached = input.get("_gcc_b200") if isinstance(input, dict) else None
+        if cached is not None and cached[0] == key:
+            A, B, a_nhwc, b_nhwc, real_AB = cached[1]
+        else:
+            A = ta.to(self.device, non_blocking=True)
+            B = tb.to(self.device, non_blocking=True)
+            a_nhwc, b_nhwc = ops.to_nhwc(A), ops.to_nhwc(B)
+            real_AB = ops.CatFn.apply(a_nhwc, b_nhwc, 3, 3)
+            if isinstance(input, dict):
+                input["_gcc_b200"] = (key, (A, B, a_nhwc, b_nhwc, real_AB))
         self._A_nchw, self._B_nchw = A, B
-        self.real_A_nhwc = ops.to_nhwc(A)
-        self.real_B_nhwc = ops.to_nhwc(B)
-        n, h, w, _ = self.real_A_nhwc.shape
-        real_AB = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=self.device)
-        ops.to_nhwc(A, out=real_AB, c_off=0)
-        ops.to_nhwc(B, out=real_AB, c_off=3)
-        real_AB[..., 6:].zero_()
-        self.real_AB = real_AB
+        self.real_A_nhwc, self.real_B_nhwc, self.real_AB = a_nhwc, b_nhwc, real_AB
 
     @property
     def real_A(self):
@@ -346,6 +352,7 @@ class Pix2PixModel(nn.Module):
         self.netD.taps = []
 
     def optimize_parameters(self):
+        ops.zero_pool.reset()
         if self.opt.online_distillation:
             T = self.teacher_model
             T.set_input(self.input)
@@ -367,6 +374,7 @@ class Pix2PixModel(nn.Module):
         self._release_graphs()
 
     def optimizer_netD_arch(self):
+        ops.zero_pool.reset()
         self.forward()
         self.teacher_model.set_input(self.input)
         self.teacher_model.forward()

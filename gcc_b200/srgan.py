@@ -616,6 +616,7 @@ class SRGAN(torch.nn.Module):
         self.netD.taps = []
 
     def optimize_parameters(self):
+        ops.zero_pool.reset()
         if self.opt.online_distillation:
             T = self.teacher_model
             T.set_input(self.input)
@@ -639,6 +640,7 @@ class SRGAN(torch.nn.Module):
         self._release_graphs()
 
     def optimizer_netD_arch(self):
+        ops.zero_pool.reset()
         self.forward()
         self.teacher_model.set_input(self.input)
         self.teacher_model.forward()

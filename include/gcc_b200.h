@@ -99,6 +99,10 @@ int gcc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, long lo
 int gcc_copy_channels_bf16(const void* src, int Cs, int s_off, void* dst, int Cd, int d_off, int C, long long npix,
                            int accumulate, void* stream);
 /* mode 1 leaky-relu, 2 relu, 3 tanh; bwd takes the forward input (1,2) or output (3) as ref */
+/* torch.cat([a, b], 1) for two 8-channel-padded images with ca + cb <= 8 logical channels (cat(real_A, fake_B),
+ * models/Pix2Pix.py:467,471,516) and its backward split (da / db may be NULL); one 16-byte vector per pixel. */
+int gcc_cat_small_bf16(const void* a, const void* b, void* y, int ca, int cb, long long npix, void* stream);
+int gcc_split_small_bf16(const void* dy, void* da, void* db, int ca, int cb, long long npix, void* stream);
 int gcc_act_fwd_bf16(const void* x, void* y, long long n, int mode, float slope, void* stream);
 int gcc_act_bwd_bf16(const void* ref, const void* dy, void* dx, long long n, int mode, float slope, void* stream);
 /* nn.Dropout(p) (models/Pix2Pix.py:64): counter-based mask from (*seed_dev, salt, index); apply to dy for bwd */

@@ -18,6 +18,10 @@ for r in csv.DictReader(lines):
     rows.append((name, ns, grid))
 skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 rows = rows[skip:]
+# bench.py launches a cumsum (scan) marker right before the timed region: keep what follows the last marker
+marks = [i for i, r in enumerate(rows) if "scan" in r[0].lower() or "cumsum" in r[0].lower()]
+if marks:
+    rows = rows[marks[-1] + 1:]
 tot = sum(ns for _, ns, _ in rows)
 agg = defaultdict(lambda: [0, 0.0])
 for name, ns, _ in rows:
