@@ -331,6 +331,7 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
 // dx = gamma*rstd*mask * (dg - (S1 + xhat*S2)/M)   [norm]   or   dx = mask*dg [identity]
 // with per-thread register coefficients: gg = x*p + q, dx = c1*dg - c2 - c3*x  (thread = channel group x lane).
 // block (0,0) also accumulates dgamma += mask*S2, dbeta += mask*S1, dalpha += gamma*S2 + beta*S1 (summed over n).
+template <bool HAS_D2>
 __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int nimg, int lanes, const bf16* __restrict__ dy, int dy_Cp,
                                       int dy_coff, const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
                                       const float* __restrict__ red, bf16* __restrict__ dx, float* dgamma,
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
     const long long step = (long long)gridDim.x * lanes;
     const bf16* xb = a.x + pix0 * a.Cp + g * 8;
     const bf16* d1b = dy ? dy + pix0 * dy_Cp + dy_coff + g * 8 : nullptr;
-    const bf16* d2b = dy2 ? dy2 + pix0 * dy2_Cp + dy2_coff + g * 8 : nullptr;
+    const bf16* d2b = (HAS_D2 && dy2) ? dy2 + pix0 * dy2_Cp + dy2_coff + g * 8 : nullptr;
     bf16* ob = dx + pix0 * a.Cp + g * 8;
     auto emit = [&](const uint4 ux, const uint4 u1, const uint4 u2, long long p) {
       const Vec8 xv = unpack8(ux), d1 = unpack8(u1), d2 = unpack8(u2);
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
         const float gg = xv.v[k] * cp[k] + cq[k];
         float dg = 0.f;
         if (d1b) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
-        if (d2b) dg += d2.v[k] * act_grad(gg, act2, a.slope);
+        if (HAS_D2 && d2b) dg += d2.v[k] * act_grad(gg, act2, a.slope);
         o.v[k] = c1[k] * dg - c2[k] - c3[k] * xv.v[k];
       }
       store8(ob + p * a.Cp, o);
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
     const uint4 zero = make_uint4(0, 0, 0, 0);
     auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * a.Cp) : zero; };
     auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * dy_Cp) : zero; };
-    auto ld2 = [&](long long q) { return (d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
+    auto ld2 = [&](long long q) { return (HAS_D2 && d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
     // register double buffer over pairs of pixels
     long long p = (long long)blockIdx.x * lanes + lane;
     uint4 cx[2], e1[2], e2[2], nx[2], n1[2], n2[2];
@@ -564,9 +565,13 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
   int alanes;
   const int athreads = stats_threads(a.G, &alanes);
   const int bx = dx ? lane_blocks(a.npix, alanes, groups, 2) : 1;
-  norm_bwd_apply_kernel<<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
-      a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, (bf16*)dx, dgamma,
-      dbeta, dalpha);
+  if (dy2 != nullptr)
+    norm_bwd_apply_kernel<true><<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
+        a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, (bf16*)dx, dgamma,
+        dbeta, dalpha);
+  else
+    norm_bwd_apply_kernel<false><<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
+        a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, nullptr, 0, 0, 0, red, (bf16*)dx, dgamma, dbeta, dalpha);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
