@@ -4,21 +4,22 @@
 // (reference call sites: nn.Conv2d / nn.ConvTranspose2d in models/Pix2Pix.py:31-56,
 // 216-260, 280-300 and the Gram bmm in models/Pix2Pix.py:733-740):
 //
-//  * conv_gemm_kernel  ("pixel-major" GEMM):  Y[pix, r] = sum_{tap, c} X[pix (+) tap, c] * Wp[r][tap][c]
+//  * conv_gemm_persistent_kernel ("pixel-major" GEMM):  Y[pix, r] = sum_{tap, c} X[pix (+) tap, c] * Wp[r][tap][c]
 //      A = activation patches, fetched by TMA straight from the NHWC bf16 tensor as a 4-D box
 //          (64 channels x Wt x Ht x Nt pixels, zero fill outside the image = conv zero padding),
-//      B = packed weights [rows][taps][channels] (K-major), D = 128 pixels x BLOCK_N rows in TMEM.
-//      Used for Conv2d fprop, Conv2d dgrad, ConvTranspose2d fprop/dgrad, 1x1 convs, Gram backward.
-//      Stride-2 gathers use four parity views of the input (one tensor map each); stride-2
-//      scatters (transposed conv) run as four sub-pixel classes with a strided output.
+//      B = packed weights [rows][taps][channels] (K-major), D = 128 pixels x BLOCK_N rows in TMEM (double buffered).
+//      Persistent (one CTA per SM walks the tiles), 320 threads: warp 0 = TMA producer, warp 1 = TMEM alloc +
+//      single-thread MMA issuer, warps 2..9 = epilogue.  Used for Conv2d fprop, Conv2d dgrad, ConvTranspose2d
+//      fprop/dgrad, 1x1 convs, Gram backward.  Stride-2 gathers use four parity views of the input (one tensor
+//      map each); stride-2 scatters (transposed conv) run as four sub-pixel classes of the same launch.
 //
 //  * wgrad_gemm_kernel ("channel-major" GEMM): dW[r][tap][c] = sum_pix P[pix, r] * Q[pix (+) tap, c]
-//      both operands are MN-major tiles (64 pixels x 64 channels boxes), D = 128 r x BLOCK_N c.
+//      both operands are MN-major tiles (64 pixels x 64 channels boxes), D = 128|256 r x BLOCK_N c.
+//      192 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (fp32 stores / reductions).
 //      Used for all weight gradients and (batched, tap = 0, P = Q) for the Gram matrices.
 //
-// Pipeline per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA
-// issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  smem ring of STAGES slots
-// guarded by full/empty mbarriers; accumulator hand-off through a tmem_full mbarrier.
+// smem rings of STAGES slots guarded by full/empty mbarriers; accumulator hand-off through tmem_full (/ tmem_empty)
+// mbarriers; every mbarrier wait is bounded and traps instead of hanging.
 #include "common.cuh"
 
 namespace gcc {
@@ -65,144 +66,6 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   if (act == 1) return v > 0.f ? v : v * slope;
   if (act == 2) return tanhf(v);
   return v;
-}
-
-// ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ GemmGeom p) {
-  constexpr uint32_t kABytes = kBlockM * 128;
-  constexpr uint32_t kBBytes = BLOCK_N * 128;
-  constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int bx = blockIdx.x;
-  const int tw = bx % p.tiles_w;
-  bx /= p.tiles_w;
-  const int th = bx % p.tiles_h;
-  const int tn = bx / p.tiles_h;
-  const int b0 = tw << p.log_wt, a0 = th << p.log_ht, n0 = tn << p.log_nt;
-  const int n_tile = blockIdx.y;
-  const int num_kb = p.num_taps * p.k_chunks;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.a_maps[0]);
-    tma_prefetch_desc(&p.b_map);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / p.k_chunks;
-        const int kc = kb - tap * p.k_chunks;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], kStageBytes);
-        uint8_t* sa = smem + stage * kStageBytes;
-        tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, b0 + p.tap_dw[tap],
-                    a0 + p.tap_dh[tap], n0);
-        tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK,
-                    p.w_per_image ? n0 : (int)p.tap_widx[tap], n_tile * BLOCK_N);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-        const uint32_t sb = sa + kABytes;
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-      umma_commit(tmem_full_bar);
-    }
-  } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int wt_mask = (1 << p.log_wt) - 1, ht_mask = (1 << p.log_ht) - 1;
-    const int b = b0 + (r & wt_mask);
-    const int a = a0 + ((r >> p.log_wt) & ht_mask);
-    const int n = n0 + (r >> (p.log_wt + p.log_ht));
-    const bool valid = (n < p.GN) && (a < p.GH) && (b < p.GW);
-    bf16* orow = p.out + (long long)n * p.out_sn + (long long)a * p.out_sh + (long long)b * p.out_sw;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
-      const int col0 = n_tile * BLOCK_N + c0;
-      if (col0 >= p.out_cols) break;  // warp-uniform
-      uint32_t v[32];
-      if constexpr (kChunk == 32) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-      } else {
-        uint32_t v16[16];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v16);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = v16[i];
-      }
-      tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < kChunk / 8; ++g) {
-          const int col = col0 + g * 8;
-          if (col < p.out_cols) {
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float x = __uint_as_float(v[g * 8 + i]);
-              if (p.bias != nullptr && col + i < p.bias_cols) x += __ldg(p.bias + col + i);
-              f[i] = apply_act(x, p.act, p.slope);
-            }
-            uint4 o;
-            o.x = pack_bf16(f[0], f[1]);
-            o.y = pack_bf16(f[2], f[3]);
-            o.z = pack_bf16(f[4], f[5]);
-            o.w = pack_bf16(f[6], f[7]);
-            *reinterpret_cast<uint4*>(orow + col) = o;
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -387,7 +250,7 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent variant of conv_gemm_kernel (the one the library launches).
+// The implicit-GEMM convolution kernel (persistent).
 //  * grid = min(#tiles, #SMs); each CTA walks tiles  tile = blockIdx.x + i * gridDim.x
 //  * the smem ring keeps running across tile boundaries (the TMA producer never drains)
 //  * TWO accumulator stages in TMEM (2 x BLOCK_N columns): the 8 epilogue warps drain tile i while the MMA
@@ -847,23 +710,6 @@ static int make_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int 
 }
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-
-template <int BLOCK_N, int STAGES>
-static int launch_conv_gemm(const GemmGeom& g, int m_tiles, int n_tiles, cudaStream_t st) {
-  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem) != cudaSuccess) {
-      gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
-      return GCC_ERR_CUDA;
-    }
-    configured = true;
-  }
-  conv_gemm_kernel<BLOCK_N, STAGES><<<dim3(m_tiles, n_tiles), 192, smem, st>>>(g);
-  GCC_CHECK_LAUNCH();
-  return GCC_OK;
-}
 
 template <int BLOCK_N, int STAGES, int MT>
 static int launch_wgrad_gemm(const GemmGeom& g, dim3 grid, cudaStream_t st) {
