@@ -309,6 +309,8 @@ class Discriminator(_SANet):
         assert image_size == 64
         self.arena = arena if arena is not None else ParamArena(device, betas=(0.0, 0.9))
         self.sn_arena = sn_arena if sn_arena is not None else self.arena
+        if gated and gate_arena is None:
+            gate_arena = ParamArena(device)
         self.gate_arena = gate_arena
         self._arenas = [a for a in (self.arena, self.sn_arena if self.sn_arena is not self.arena else None, gate_arena)
                         if a is not None]

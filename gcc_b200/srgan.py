@@ -298,6 +298,8 @@ class Discriminator(_SRNet):
                  device="cuda"):
         super().__init__()
         self.arena = arena if arena is not None else ParamArena(device)
+        if gated and gate_arena is None:
+            gate_arena = ParamArena(device)
         self.gate_arena = gate_arena
         self._arenas = [self.arena] + ([gate_arena] if gate_arena is not None else [])
         self.gated = gated

@@ -118,3 +118,47 @@ def test_cyclegan_prune_cfg_bit_exact_vs_golden(golden_dir):
     for thr in (0.8, 0.95, 1.05, 1.15):
         assert prune.cyclegan_prunenet_cfg(R, thr) == g["cfg@%g" % thr], thr
     assert prune.cyclegan_max_min_conv_norm(R) == pytest.approx(g["maxmin"], rel=1e-6)
+
+
+def test_srgan_sagan_state_dict_layout_and_roundtrip():
+    """SRGAN / SAGAN nets expose exactly the reference's state-dict names and shapes (the oracle's shape tables were
+    loaded strictly into the reference modules by oracle/make_golden.py) and round-trip values, including the
+    spectral-norm vector weight_v that is stored in channels-last column order internally."""
+    from gcc_b200 import sagan, srgan
+    from oracle import sagan_oracle as SA
+    from oracle import srgan_oracle as SR
+
+    def _check(net, shapes):        # same names and shapes; the ORDER of the keys is not part of the contract here
+        sd = net.state_dict()
+        assert sorted(sd.keys()) == sorted(shapes.keys())
+        for k, s in shapes.items():
+            assert tuple(sd[k].shape) == tuple(s), k
+    cfg = [5, 8, 3, 7, 8, 6, 4, 8, 2, 8, 8, 1, 8, 5, 3, 8]
+    _check(srgan.Generator(n_channels=8, device="cpu"), SR.sr_generator_shapes(8))
+    _check(srgan.Generator(n_channels=8, filter_cfgs=cfg, device="cpu"), SR.sr_generator_shapes(8, cfg))
+    _check(srgan.Discriminator(n_channels=8, device="cpu"), SR.sr_disc_shapes(8, False))
+    _check(srgan.MaskDiscriminator(n_channels=8, device="cpu"), SR.sr_disc_shapes(8, True))
+    _check(srgan.TruncatedVGG19(device="cpu"), SR.vgg_shapes())
+    _check(sagan.Generator(ngf=8, device="cpu"), SA.generator_shapes(8))
+    _check(sagan.Generator(ngf=8, filter_cfgs=[20, 12, 24, 8], device="cpu"), SA.generator_shapes(8, 128, [20, 12, 24, 8]))
+    _check(sagan.Discriminator(ndf=8, device="cpu"), SA.disc_shapes(8, False))
+    net = sagan.MaskDiscriminator(ndf=8, device="cpu")
+    _check(net, SA.disc_shapes(8, True))
+    P = SA.make_params(SA.disc_shapes(8, True), "t.netD.")
+    net.load_state_dict({k: v.detach() for k, v in P.items()})
+    sd = net.state_dict()
+    assert all(torch.equal(sd[k], P[k].detach()) for k in P)
+    # internal order of weight_v: (kh, kw, c) instead of the reference's (c, kh, kw)
+    v_int = net.sn[1].v.detach()
+    v_ref = P["l2.0.module.weight_v"].detach()
+    assert torch.equal(v_int.reshape(16, 8).t().reshape(-1), v_ref)
+
+
+def test_srgan_sagan_options():
+    from gcc_b200 import options
+    o = options.parse(["--model", "srgan", "--dataroot", "x"])
+    assert (o.gan_mode, o.lr, o.batch_size, o.lr_policy, o.lr_decay_iters, o.lambda_SR_adversarial) == \
+        ("vanilla", 1e-4, 16, "step", 15, 1e-3)
+    o = options.parse(["--model", "sagan", "--dataroot", "x/celeb"])
+    assert (o.gan_mode, o.lr, o.batch_size, o.crop_size, o.n_epochs, o.z_dim) == ("hinge", 1e-4, 64, 64, 100, 128)
+    assert options.get_model_class(o).__name__ == "SAGANModel"
