@@ -325,7 +325,7 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvGeom2& p, int tile_id)
   return t;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool kTmaStore>
 __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __grid_constant__ ConvGeom2 p) {
   constexpr uint32_t kABytes = kBlockM * 128;
   constexpr uint32_t kBBytes = BLOCK_N * 128;
@@ -337,9 +337,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
-  // BLOCK_N <= 128 (short-K, store-bound layers): the bf16 tile is staged in 128B-swizzled 64-column units
-  // (128 rows x 128 B = 16 KB each, double buffered) and written by TMA; otherwise warp-private staging below.
-  constexpr bool kTmaStore = BLOCK_N <= 128;
+  // kTmaStore (BLOCK_N <= 128 and a short K loop: store-bound layers): the bf16 tile is staged in 128B-swizzled
+  // 64-column units (128 rows x 128 B = 16 KB each, double buffered) and written by TMA; otherwise (long K loops,
+  // which want the shared memory for a deeper operand ring) warp-private staging below.
+  static_assert(!kTmaStore || BLOCK_N <= 128, "the TMA-store epilogue stages at most two 64-column units");
   constexpr int kUnits = BLOCK_N / 64;
   constexpr uint32_t kOutBytes = kTmaStore ? 2 * kUnits * 16384 : 0;
   uint8_t* out_base = smem + STAGES * kStageBytes;
@@ -795,13 +796,13 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool TS>
 static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
-  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + (BLOCK_N <= 128 ? 2 * (BLOCK_N / 64) * 16384 : 0) + 1024 +
-                   256 + 8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
+  const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + (TS ? 2 * (BLOCK_N / 64) * 16384 : 0) + 1024 + 256 +
+                   8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem) != cudaSuccess) {
       gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
       return GCC_ERR_CUDA;
@@ -809,7 +810,7 @@ static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
     configured = true;
   }
   const int grid = g.total_tiles < num_sms() ? g.total_tiles : num_sms();
-  conv_gemm_persistent_kernel<BLOCK_N, STAGES><<<grid, 320, smem, st>>>(g);
+  conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS><<<grid, 320, smem, st>>>(g);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -984,9 +985,10 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   g.stats_ld = stats_ld;
 
   trace_begin(st);
-  if (BN == 64) rc = launch_conv_persistent<64, 6>(g, st);
-  else if (BN == 128) rc = launch_conv_persistent<128, 4>(g, st);
-  else rc = launch_conv_persistent<256, 4>(g, st);
+  if (BN == 64) rc = launch_conv_persistent<64, 6, true>(g, st);
+  else if (BN == 128 && max_kb <= 8) rc = launch_conv_persistent<128, 4, true>(g, st);
+  else if (BN == 128) rc = launch_conv_persistent<128, 6, false>(g, st);
+  else rc = launch_conv_persistent<256, 4, false>(g, st);
   if (rc) return rc;
   if (g.k_splits > 1) {
     long long b = (out_elems + 255) / 256;
