@@ -487,7 +487,9 @@ class NLayerDiscriminator(_Net):
         self.taps = []
         h = x
         for li in range(4):
-            if li == 0:
+            if li == 0 and self.norms[0].alpha is None:
+                h = self.convs[0](h, ACT_LRELU, 0.2)        # plain D: LeakyReLU fused into the conv epilogue
+            elif li == 0:
                 h = self.norms[0](self.convs[0](h), ACT_LRELU)
             else:
                 c, csums = self.convs[li].with_stats(h)
