@@ -34,6 +34,9 @@ def parse_args():
     p.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     p.add_argument("--trace", type=int, default=0, help="debug: after warm-up run one eager step with per-GEMM-launch "
                    "event timing logged to stderr (GCCTRACE lines) and exit without a bench line")
+    p.add_argument("--pace", type=int, default=1, help="N > 1: host waits for each iteration before queueing the next")
+    p.add_argument("--clock_ms", type=int, default=200, help="nvidia-smi sampling interval during the timed region "
+                   "(the profiling recipe's 200 ms; every sample briefly stalls the sampled GPU)")
     p.add_argument("--watchdog_s", type=int, default=600, help="abort the whole process after this many seconds")
     p.add_argument("--ngf", type=int, default=32)
     p.add_argument("--teacher_ngf", type=int, default=64)
@@ -75,13 +78,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, interval_ms=200):
+        self.idx, self.rows, self.proc, self.ms = gpu_index, [], None, int(interval_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.ms)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -258,11 +261,20 @@ def run_b200(args):
     devb = [{k: v.cuda() for k, v in h.items()} for h in host]
 
     graphed = None
+    pace_ev = torch.cuda.Event()
 
     def step(d, read_losses):
         if graphed is not None:
             graphed.run(d)
-            return model.get_current_losses() if read_losses else None
+            if read_losses:
+                return model.get_current_losses()
+            if world > 1 and args.pace:
+                # data parallel: keep the host at most one iteration ahead of the device.  Measured on 4 and 8 GPUs:
+                # an unpaced host (all K iterations' graph segments and collectives queued at once) runs 1-4 ms per
+                # iteration SLOWER than the end-to-end loop, whose loss read-back paces it.
+                pace_ev.record()
+                pace_ev.synchronize()
+            return None
         model.set_input({"A": d["A"], "B": d["B"], "A_paths": "", "B_paths": ""})
         model.optimize_parameters()
         model.set_input({"A": d["vA"], "B": d["vB"], "A_paths": "", "B_paths": ""})
@@ -302,7 +314,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         _lib.lib().gcc_debug_set_flags(0)
         return
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_ms)
     if rank == 0:
         sampler.start()  # sampled from the warm-up on: the GPU is under the same load as in the timed region
     launches_per_step = None
