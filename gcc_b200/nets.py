@@ -48,7 +48,7 @@ class ConvLayer:
         arena.add(self.wname, shape, kind)
         if bias:
             arena.add(self.bname, (cout,), "vec")
-        # k4 s2 p1 layers whose image side has <= 8 channels run through im2col/col2im (ops.ColConvFn)
+        # k4 s2 p1 layers whose image side has <= 8 channels: image-mode GEMMs / col2im (ops.ColConvFn)
         self.colpath = (k == 4 and stride == 2 and pad == 1 and outpad == 0 and
                         ((kind == "conv" and cin <= 8) or (kind == "convT" and cout <= 8)))
         # k4 s1 p1 convs with <= 8 output channels (PatchGAN logits head) run as a 1x1 GEMM + fold (ops.HeadConvFn)

@@ -166,9 +166,12 @@ def _tap_major_weight(layer, pack, c):
 
 
 class ColConvFn(torch.autograd.Function):
-    """k4 s2 p1 Conv2d with <= 8 input channels / ConvTranspose2d with <= 8 output channels: the image side is
-    expanded by im2col / folded by col2im (16 taps x 8 channels = one 128-wide GEMM dimension) and the
-    contraction runs as a 1x1 conv on the tcgen05 kernels (see elementwise.cu, "im2col / col2im")."""
+    """k4 s2 p1 layers whose image side has <= 8 channels.
+    Conv2d (<= 8 input channels: first layer of the U-Net / PatchGANs): forward and weight gradient run in the GEMM
+    kernels' image mode (the 16 taps x 8 channels are gathered by TMA into K = 128, no column buffer); the data
+    gradient is one 1x1 GEMM producing tap-major columns + col2im.
+    ConvTranspose2d (<= 8 output channels: last layer of the U-Net): forward = 1x1 GEMM + col2im; backward = im2col
+    of the output gradient + 1x1 GEMMs (see elementwise.cu, "im2col / col2im")."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, layer, act, slope):
