@@ -162,3 +162,57 @@ def test_srgan_sagan_options():
     o = options.parse(["--model", "sagan", "--dataroot", "x/celeb"])
     assert (o.gan_mode, o.lr, o.batch_size, o.crop_size, o.n_epochs, o.z_dim) == ("hinge", 1e-4, 64, 64, 100, 128)
     assert options.get_model_class(o).__name__ == "SAGANModel"
+
+
+def test_random_pruned_cfgs_build_the_reference_shapes():
+    """Arbitrary (non multiple-of-8) pruned widths, incl. dropped inner U-Net levels: the nets expose exactly the
+    shapes the oracle's (= the reference's) shape tables give."""
+    import random
+    from gcc_b200 import nets, sagan, srgan
+    from oracle import sagan_oracle as SA
+    from oracle import srgan_oracle as SR
+    rnd = random.Random(7)
+    for trial in range(6):
+        ngf = 8
+        f = [rnd.randint(1, 40) for _ in range(15)]
+        if trial % 3 == 2:                       # a zero entry drops the innermost level(s) (Pix2Pix.py:87,97)
+            f[7] = 0
+        c = [f[0], f[1], f[2], f[3], f[4], f[5], f[6]] + [0] * 8
+        c[7] = f[7]
+        skips = [f[6], f[5], f[4], f[3], f[2], f[1], f[0]]
+        for i in range(7):
+            c[8 + i] = f[8 + i] + skips[i]
+        shapes = O.unet_param_shapes(ngf, f, c)
+        sd = nets.UnetGenertor(ngf=ngf, filter_cfgs=f, channel_cfgs=c, device="cpu").state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(s) for k, s in shapes.items())
+        rc = [rnd.randint(1, 33) for _ in range(23)]
+        shapes = O.resnet_param_shapes(ngf, rc)
+        sd = nets.MobileResnetGenerator(ngf=ngf, cfg=rc, device="cpu").state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(s) for k, s in shapes.items())
+        sc = [rnd.randint(1, 19) for _ in range(16)]
+        shapes = SR.sr_generator_shapes(ngf, sc)
+        sd = srgan.Generator(n_channels=ngf, filter_cfgs=sc, device="cpu").state_dict()
+        assert all(tuple(sd[k].shape) == tuple(s) for k, s in shapes.items()) and len(sd) == len(shapes)
+        ac = [rnd.randint(1, 5) * 8 for _ in range(4)]      # attention needs channels divisible by 8 (in_dim // 8)
+        shapes = SA.generator_shapes(ngf, 128, ac)
+        sd = sagan.Generator(ngf=ngf, filter_cfgs=ac, device="cpu").state_dict()
+        assert all(tuple(sd[k].shape) == tuple(s) for k, s in shapes.items()) and len(sd) == len(shapes)
+
+
+def test_zero_pool_bump_allocation_and_reset():
+    from gcc_b200 import ops
+    pool = ops._ZeroPool()
+    dev = torch.device("cpu")
+    a = pool.take(10, dev)
+    b = pool.take(3, dev)
+    assert a.numel() == 10 and b.numel() == 3 and a.data_ptr() != b.data_ptr()
+    assert (b.data_ptr() - a.data_ptr()) == 16 * 4            # 8-element granules
+    a.add_(1.0)
+    b.add_(2.0)
+    pool.reset()
+    assert float(a.sum()) == 0.0 and float(b.sum()) == 0.0      # the used prefix was re-zeroed
+    assert pool.take(10, dev).data_ptr() == a.data_ptr()       # and the bump pointer rewound
+    big = pool.take(1 << 21, dev)                              # larger than the pool: plain zeros, pool untouched
+    assert big.numel() == 1 << 21 and float(big.abs().sum()) == 0.0
