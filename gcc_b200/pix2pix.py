@@ -12,6 +12,7 @@ gradient arenas are all-reduced over NCCL before every optimizer step (data para
 """
 import copy
 import os
+import weakref
 from collections import OrderedDict
 
 import torch
@@ -213,17 +214,19 @@ class Pix2PixModel(nn.Module):
         ka, kb = ("A", "B") if AtoB else ("B", "A")
         ta, tb = input[ka], input[kb]
         self.image_paths = [input.get(ka + "_paths"), input.get(kb + "_paths")]
-        key = (ka, ta.data_ptr(), ta._version, tb.data_ptr(), tb._version, str(self.device))
+        key = (ka, ta._version, tb._version, str(self.device))
         cached = input.get("_gcc_b200") if isinstance(input, dict) else None
-        if cached is not None and cached[0] == key:
-            A, B, a_nhwc, b_nhwc, real_AB = cached[1]
+        # a hit needs the SAME live source tensors (weak references: a recycled address or id cannot alias) at the
+        # same version (in-place refills of static input buffers bump it)
+        if cached is not None and cached[0] == key and cached[1]() is ta and cached[2]() is tb:
+            A, B, a_nhwc, b_nhwc, real_AB = cached[3]
         else:
             A = ta.to(self.device, non_blocking=True)
             B = tb.to(self.device, non_blocking=True)
             a_nhwc, b_nhwc = ops.to_nhwc(A), ops.to_nhwc(B)
             real_AB = ops.CatFn.apply(a_nhwc, b_nhwc, 3, 3)
             if isinstance(input, dict):
-                input["_gcc_b200"] = (key, (A, B, a_nhwc, b_nhwc, real_AB))
+                input["_gcc_b200"] = (key, weakref.ref(ta), weakref.ref(tb), (A, B, a_nhwc, b_nhwc, real_AB))
         self._A_nchw, self._B_nchw = A, B
         self.real_A_nhwc, self.real_B_nhwc, self.real_AB = a_nhwc, b_nhwc, real_AB
 
