@@ -2,16 +2,24 @@
 """Benchmark of the GCC cooperative-compression training step (BASELINE.json metric:
 "GCC train images/sec (pix2pix 256^2, 1/2/4/8 B200); conv tensor-pipe %").
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU oracle port on the host cores
+    python bench.py --gpus N --steps K --warmup W [--config NAME]           # this repo's B200 path
+    python bench.py --impl reference --gpus N --steps K ... [--config NAME] # the CPU oracle port on the host cores
 
 One "step" = one GCC iteration of the reference's train loop (train.py:144-151):
 set_input(train batch) -> optimize_parameters() -> set_input(val batch) -> clipping_mask_alpha()
--> optimizer_netD_arch(), on the configuration BASELINE.json quotes the metric on (configs[1]):
-pix2pix GCC student (U-Net ngf 32, gated PatchGAN ndf 128) distilled online from the ngf-64 teacher,
-256x256 synthetic cityscapes-shaped pairs, batch 32 per GPU, bf16 tensor-core math, dropout on
-(scripts/pix2pix/train.sh).  Data parallel over N GPUs = N ranks x batch 32 (weak scaling), flat
-gradient arenas all-reduced with NCCL before each optimizer step.
+-> optimizer_netD_arch().  Workloads (--config):
+
+  c2 (default)  BASELINE configs[1]: pix2pix GCC student (U-Net ngf 32, gated PatchGAN ndf 128) distilled online from
+                the ngf-64 teacher, 256x256, batch 32 per GPU, bf16, dropout on (scripts/pix2pix/train.sh)
+  c2_pruned     the same with the literal pruned student of SURVEY.md 7/8d (odd widths 37, 65, 143 ...)
+  c2_resnet     the same with the MobileResNet-9 backbone (student ngf 32, teacher ngf 64)
+  cyclegan      configs[2]: CycleGAN 256x256, student ngf 24 with the reference's shipped channel lists
+                (utils/prune_util.py:120-121), teacher ngf 64, ndf 64, batch 8 per GPU
+  srgan         configs[3]: SRGAN 4x, 96 -> 384 (HR crops of 384), student ngf 24 / teacher 64, batch 16 per GPU
+  sagan         configs[4]: SAGAN 64x64 (the only size the reference's forward supports), ngf 48 / teacher 64, batch 64
+
+Data parallel over N GPUs = N ranks x the per-GPU batch (weak scaling), flat gradient arenas all-reduced with NCCL
+before each optimizer step (captured inside the iteration's CUDA graph).
 """
 import argparse
 import json
@@ -24,6 +32,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PRUNED_F = [32, 37, 65, 143, 144, 136, 134, 256, 120, 127, 128, 138, 62, 33, 13]
+PRUNED_C = [32, 37, 65, 143, 144, 136, 134, 256, 254, 263, 272, 281, 127, 70, 45]
+CYC_A = [24, 48, 86, 72, 86, 47, 86, 44, 86, 43, 86, 43, 86, 29, 86, 30, 86, 37, 86, 36, 86, 48, 24]
+CYC_B = [24, 48, 96, 91, 96, 73, 96, 62, 96, 61, 96, 74, 96, 54, 96, 51, 96, 58, 96, 81, 96, 48, 24]
+
+CONFIGS = {
+    "c2": dict(model="pix2pix", opt=dict(ngf=32, teacher_ngf=64, ndf=128, teacher_ndf=128, backbone="unet"),
+               cfgs=(None, None), batch=32, size=256),
+    "c2_pruned": dict(model="pix2pix", opt=dict(ngf=32, teacher_ngf=64, ndf=128, teacher_ndf=128, backbone="unet"),
+                      cfgs=(PRUNED_F, PRUNED_C), batch=32, size=256),
+    "c2_resnet": dict(model="pix2pix", opt=dict(ngf=32, teacher_ngf=64, ndf=128, teacher_ndf=128, backbone="resnet"),
+                      cfgs=(None, None), batch=32, size=256),
+    "cyclegan": dict(model="cyclegan", opt=dict(ngf=24, teacher_ngf=64, ndf=64, teacher_ndf=64), cfgs=(CYC_A, CYC_B),
+                     batch=8, size=256),
+    "srgan": dict(model="srgan", opt=dict(ngf=24, teacher_ngf=64, ndf=128, teacher_ndf=64, image_size=384),
+                  cfgs=(None, None), batch=16, size=384),
+    "sagan": dict(model="sagan", opt=dict(ngf=48, teacher_ngf=64, ndf=64, teacher_ndf=64), cfgs=(None, None), batch=64,
+                  size=64),
+}
+
 
 def parse_args():
     p = argparse.ArgumentParser()
@@ -31,24 +59,24 @@ def parse_args():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    p.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    p.add_argument("--batch", type=int, default=0, help="images per GPU per step (0 = the config's)")
     p.add_argument("--trace", type=int, default=0, help="debug: after warm-up run one eager step with per-GEMM-launch "
                    "event timing logged to stderr (GCCTRACE lines) and exit without a bench line")
-    p.add_argument("--pace", type=int, default=1, help="N > 1: host waits for each iteration before queueing the next")
-    p.add_argument("--clock_ms", type=int, default=200, help="nvidia-smi sampling interval during the timed region "
-                   "(the profiling recipe's 200 ms; every sample briefly stalls the sampled GPU)")
-    p.add_argument("--watchdog_s", type=int, default=600, help="abort the whole process after this many seconds")
-    p.add_argument("--ngf", type=int, default=32)
-    p.add_argument("--teacher_ngf", type=int, default=64)
-    p.add_argument("--ndf", type=int, default=128)
-    p.add_argument("--backbone", default="unet")
+    p.add_argument("--clock_ms", type=int, default=200, help="nvidia-smi sampling interval during the timed region")
+    p.add_argument("--watchdog_s", type=int, default=900, help="abort the whole process after this many seconds")
     p.add_argument("--no_dropout", action="store_true")
-    p.add_argument("--cpu_iters", type=int, default=20, help="timed CPU-baseline iterations (batch 1), ~0.5 s each on 16 cores")
+    p.add_argument("--sync_bn", action="store_true", help="N > 1: global-batch parity (synchronised BatchNorm + loss sums)")
+    p.add_argument("--cpu_iters", type=int, default=0, help="timed CPU-baseline iterations at batch 1 (0 = sized to ~20 s)")
     p.add_argument("--skip_cpu_baseline", action="store_true")
     p.add_argument("--skip_e2e", action="store_true", help="profiling runs only")
     p.add_argument("--skip_roofline", action="store_true", help="profiling runs only")
     p.add_argument("--graph", type=int, default=1, help="1 (default): capture the whole iteration in a CUDA graph and replay it; 0: eager launches")
-    return p.parse_args()
+    a = p.parse_args()
+    a.cfg = CONFIGS[a.config]
+    if a.batch <= 0:
+        a.batch = a.cfg["batch"]
+    return a
 
 
 def peaks():
@@ -60,16 +88,23 @@ def peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-# fwd GMACs per sample (probe with a conv hook): used for the step-level FLOP accounting
-def step_gmacs(ngf, teacher_ngf, ndf, backbone):
-    unet = {64: 6.05, 32: 1.55}
-    resnet = {64: 11.07, 32: 3.12}
-    tab = resnet if backbone == "resnet" else unet
-    g_t = tab.get(teacher_ngf, tab[64] * (teacher_ngf / 64.0) ** 2)
-    g_s = tab.get(ngf, tab[64] * (ngf / 64.0) ** 2)
-    d = 12.57 * (ndf / 128.0) ** 2
-    gram = 8.0 if backbone != "resnet" else 9.4
-    return 4 * g_t + 4 * g_s + 24 * d + gram + 0.6
+def step_gmacs(args):
+    """Algorithmic GMAC per image per iteration (fwd = 1x, full bwd = 2x, dgrad-only = 1x of a net's
+    forward MACs; true multiply-accumulates from gcc_b200.macs), pix2pix: 4 g_T + 4 g_S + 24 d + Gram + transform."""
+    from gcc_b200 import macs, nets
+    c, o = args.cfg, args.cfg["opt"]
+    if c["model"] != "pix2pix":
+        return None
+    if o["backbone"] == "resnet":
+        mk = lambda ngf, f: nets.MobileResnetGenerator(ngf=ngf, cfg=f, device="cpu")
+    else:
+        mk = lambda ngf, f: nets.UnetGenertor(ngf=ngf, filter_cfgs=f, channel_cfgs=c["cfgs"][1] if f is not None else None,
+                                              device="cpu")
+    g_t = macs.count_macs(mk(o["teacher_ngf"], None)) / 1e9
+    g_s = macs.count_macs(mk(o["ngf"], c["cfgs"][0])) / 1e9
+    d = macs.count_macs(nets.NLayerDiscriminator(input_nc=6, ndf=o["ndf"], device="cpu")) / 1e9
+    gram = 8.0 if o["backbone"] != "resnet" else 9.4
+    return {"g_T": g_t, "g_S": g_s, "d": d, "total": 4 * g_t + 4 * g_s + 24 * d + gram + 0.6}
 
 
 class ClockSampler:
@@ -112,42 +147,90 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_name(args):
+    c, o = args.cfg, args.cfg["opt"]
+    if c["model"] == "pix2pix":
+        stu = "%s ngf %d" % (o["backbone"], o["ngf"])
+        if c["cfgs"][0] is not None:
+            stu += " pruned to filter_cfgs %s" % (c["cfgs"][0],)
+        return ("%s: pix2pix GCC student (%s, gated PatchGAN ndf %d) distilled online from ngf-%d teacher, 256x256, "
+                "batch %d/GPU, dropout %s" % (args.config, stu, o["ndf"], o["teacher_ngf"], args.batch,
+                                              "off" if args.no_dropout else "on"))
+    if c["model"] == "cyclegan":
+        return ("cyclegan: CycleGAN GCC student (MobileResNet ngf %d, cfgs of utils/prune_util.py:120-121, gated ndf %d) "
+                "distilled online from ngf-%d teacher, 256x256, batch %d/GPU" % (o["ngf"], o["ndf"], o["teacher_ngf"], args.batch))
+    if c["model"] == "srgan":
+        return ("srgan: SRGAN 4x GCC student (SRResNet ngf %d, gated D ndf %d) distilled online from ngf-%d teacher, "
+                "%d -> %d, truncated-VGG19 perceptual loss (random weights), batch %d/GPU" % (
+                    o["ngf"], o["ndf"], o["teacher_ngf"], c["size"] // 4, c["size"], args.batch))
+    return ("sagan: SAGAN GCC student (ngf %d, gated spectral-norm D ndf %d, self-attention) distilled online from ngf-%d "
+            "teacher, 64x64, batch %d/GPU" % (o["ngf"], o["ndf"], o["teacher_ngf"], args.batch))
+
+
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(args, iters, warmup=1):
-    """images/s of the CPU oracle port (oracle/gcc_oracle.py, pinned to the reference by tests/golden) on
-    the host cores: a bounded sample = `iters` GCC iterations at batch 1 of the same networks."""
+def cpu_oracle_rate(args, iters=0, warmup=1, budget_s=20.0):
+    """images/s of the CPU oracle port (oracle/*.py, pinned to the reference by tests/golden) on the host cores: a
+    bounded sample = `iters` GCC iterations at batch 1 of the same networks (0: as many as fit ~budget_s), with the two
+    phases (optimize_parameters / optimizer_netD_arch) timed separately."""
     import torch
     from oracle import gcc_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    opt = O.Opt(ngf=args.ngf, ndf=args.ndf, teacher_ngf=args.teacher_ngf, teacher_ndf=128, backbone=args.backbone,
-                no_dropout=args.no_dropout, direction="BtoA")
-    S, T = O.build_pair(opt)
-    times = []
-    for it in range(warmup + iters):
-        A, B = O.det_image("bench.A.%d" % it, 1, 3, 256, 256), O.det_image("bench.B.%d" % it, 1, 3, 256, 256)
-        vA, vB = O.det_image("bench.vA.%d" % it, 1, 3, 256, 256), O.det_image("bench.vB.%d" % it, 1, 3, 256, 256)
+    c, o = args.cfg, args.cfg["opt"]
+    model = c["model"]
+    if model == "pix2pix":
+        opt = O.Opt(no_dropout=args.no_dropout, direction="BtoA", **o)
+        S, _ = O.build_pair(opt, c["cfgs"][0], c["cfgs"][1])
+        mk = lambda t: (O.det_image(t + ".A", 1, 3, 256, 256), O.det_image(t + ".B", 1, 3, 256, 256))
+    elif model == "cyclegan":
+        S, _ = O.build_cycle_pair(O.CycleOpt(**o), c["cfgs"][0], c["cfgs"][1])
+        mk = lambda t: (O.det_image(t + ".A", 1, 3, 256, 256), O.det_image(t + ".B", 1, 3, 256, 256))
+    elif model == "srgan":
+        from oracle import srgan_oracle as SR
+        oo = {k: v for k, v in o.items() if k != "image_size"}
+        S, _ = SR.build_sr_pair(SR.SROpt(**oo))
+        hr = c["size"]
+        mk = lambda t: (SR.convert_to_imagenet(O.det_image(t + ".lr", 1, 3, hr // 4, hr // 4)), O.det_image(t + ".hr", 1, 3, hr, hr))
+    else:
+        from oracle import sagan_oracle as SA
+        S, _ = SA.build_sa_pair(SA.SAOpt(**o))
+        mk = lambda t: (O.det_normal(t + ".z", (1, 128)), O.det_image(t + ".real", 1, 3, 64, 64))
+    t_opt, t_arch = [], []
+    it, t_start = 0, time.perf_counter()
+    while True:
+        a, b = mk("bench.%d" % it)
+        va, vb = mk("bench.v%d" % it)
         t0 = time.perf_counter()
-        S.set_input(A, B)
+        S.set_input(a, b)
         S.optimize_parameters()
-        S.set_input(vA, vB)
+        t1 = time.perf_counter()
+        S.set_input(va, vb)
         S.clipping_mask_alpha()
         S.optimizer_netD_arch()
-        float(S.loss_D_arch)
-        dt = time.perf_counter() - t0
+        t2 = time.perf_counter()
         if it >= warmup:
-            times.append(dt)
-    mean = sum(times) / len(times)
+            t_opt.append(t1 - t0)
+            t_arch.append(t2 - t1)
+        it += 1
+        done = len(t_opt)
+        if (iters and done >= iters) or (not iters and done >= 3 and time.perf_counter() - t_start > budget_s):
+            break
+    med = lambda v: sorted(v)[len(v) // 2]
+    mean = (sum(t_opt) + sum(t_arch)) / len(t_opt)
     return {"value": 1.0 / mean, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "%d GCC iterations at batch 1 (same nets: %s ngf %d / teacher %d / ndf %d, fp32, torch CPU "
-                      "%d threads), %.2f s/iter" % (iters, args.backbone, args.ngf, args.teacher_ngf, args.ndf, cores, mean),
-            "s_per_iter": mean}
+            "sample": "%d GCC iterations at batch 1 after %d warm-up (oracle port of the reference step, same nets as the "
+                      "GPU arm, fp32, torch CPU %d threads), %.3f s/iter" % (len(t_opt), warmup, cores, mean),
+            "s_per_iter": mean, "optimize_parameters_s_median": med(t_opt), "optimizer_netD_arch_s_median": med(t_arch)}
 
 
-def workload_name(args):
-    return ("pix2pix GCC student (%s ngf %d, gated PatchGAN ndf %d) distilled online from ngf-%d teacher, 256x256, "
-            "batch %d/GPU, dropout %s" % (args.backbone, args.ngf, args.ndf, args.teacher_ngf, args.batch,
-                                          "off" if args.no_dropout else "on"))
+def cpu_c1_rate(iters=3):
+    """BASELINE configs[0] / BASELINE.md section 4 (C1): pix2pix MobileResNet-9 ngf 64 + PatchGAN ndf 128, batch 1, on the
+    CPU oracle port -- reported beside the headline as the reference's own CPU-runnable case."""
+    a = argparse.Namespace(cfg=dict(model="pix2pix", opt=dict(ngf=64, teacher_ngf=64, ndf=128, teacher_ndf=128,
+                                                              backbone="resnet"), cfgs=(None, None)), no_dropout=False)
+    r = cpu_oracle_rate(a, iters=iters)
+    return {k: r[k] for k in ("value", "unit", "cores", "s_per_iter", "optimize_parameters_s_median",
+                              "optimizer_netD_arch_s_median")}
 
 
 def run_reference(args):
@@ -155,7 +238,8 @@ def run_reference(args):
     if rank != 0:
         return
     base = cpu_oracle_rate(args, iters=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
-    line = {"metric": "GCC train images/sec (pix2pix 256^2)", "value": base["value"], "unit": "images/s",
+    line = {"metric": "GCC train images/sec (pix2pix 256^2)" if args.cfg["model"] == "pix2pix" else
+            "GCC train images/sec (%s)" % args.config, "value": base["value"], "unit": "images/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * base["s_per_iter"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -163,55 +247,87 @@ def run_reference(args):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.config == "c2":
+        line["c1_resnet_ngf64_b1"] = cpu_c1_rate(iters=2)
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------ B200 arm
-def dominant_kernel_roofline(batch, pk):
-    """CUDA-event timing of the dominant kernel alone: PatchGAN 512->1024 k4 s1 fprop (conv_gemm_persistent_kernel<256,4>),
-    L2 flushed between launches.  Algorithmic FLOPs = 2 * (batch*31*31) * 1024 * (512*16)."""
+def ncu_facts(key):
+    """DRAM traffic / tensor-pipe utilisation of a kernel from the committed `ncu --set full` capture, as extracted by
+    scripts/ncu_extract.py into profiles/roofline_kernels.json (names the capture file it came from)."""
+    path = os.path.join(ROOT, "profiles", "roofline_kernels.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get(key)
+    return None
+
+
+def dominant_kernel_roofline(args, pk):
+    """CUDA-event timing of the dominant kernel of the workload, alone, L2 flushed between launches.
+    pix2pix: PatchGAN 512->1024 k4 s1 fprop (conv_gemm_persistent_kernel<256,4>), algorithmic FLOPs =
+    2 * (batch*31*31) * 1024 * (512*16), against the measured burst bf16 peak.
+    CycleGAN / SRGAN / SAGAN (HBM-bound steps): the norm-apply kernel on the workload's largest normalised activation,
+    algorithmic bytes = read x + write y = 4 B/element, against the measured HBM copy bandwidth."""
     import torch
     from gcc_b200 import _lib
-    n, h, w, cin, cout, k = batch, 32, 32, 512, 1024, 4
-    x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
-    wt = (torch.randn(cout, k * k, cin, device="cuda") * 0.02).to(torch.bfloat16)
-    y = torch.empty(n, 31, 31, cout, device="cuda", dtype=torch.bfloat16)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    model, batch = args.cfg["model"], args.batch
 
-    def launch():
-        _lib.call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cin, wt.data_ptr(), cout, k * k, cin, None, y.data_ptr(),
-                  31, 31, cout, 0, 0, k, k, 1, 1, 0, 0.0, 0, None, 0, None, 0, st)
+    def time_it(launch, reps=10):
+        for _ in range(3):
+            launch()
+        times = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            launch()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        return sum(times) / len(times)
 
-    for _ in range(3):
-        launch()
-    times = []
-    for _ in range(10):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        launch()
-        e1.record()
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
-    flops = 2.0 * n * 31 * 31 * cout * cin * k * k
-    ach = flops / (ms * 1e-3) / 1e12
-    # DRAM traffic of this exact launch from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_full_gemm_v2_persistent.csv: dram__bytes_read.sum 55.9 MB + dram__bytes_write.sum 35.1 MB at
-    # batch 32; algorithmic unique bytes = 33.5 MB input + 16.8 MB weights + 63.0 MB output = 113 MB)
-    traffic = 91.1e6 if n == 32 else None
-    return {"bound": "tensor", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-            "frac": ach / pk["bf16_burst"], "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
-            "ncu_tensor_pipe_active_pct": 89.6,
-            "kernel": "conv_gemm_persistent_kernel<256,4>: PatchGAN 512->1024 k4 s1 fprop, M=%d N=1024 K=8192" % (n * 961),
-            "avg_launch_ms": ms, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
+    if model == "pix2pix":
+        n, h, w, cin, cout, k = batch, 32, 32, 512, 1024, 4
+        x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
+        wt = (torch.randn(cout, k * k, cin, device="cuda") * 0.02).to(torch.bfloat16)
+        y = torch.empty(n, 31, 31, cout, device="cuda", dtype=torch.bfloat16)
+        ms = time_it(lambda: _lib.call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cin, wt.data_ptr(), cout, k * k, cin,
+                                       None, y.data_ptr(), 31, 31, cout, 0, 0, k, k, 1, 1, 0, 0.0, 0, None, 0, None, 0, st))
+        flops = 2.0 * n * 31 * 31 * cout * cin * k * k
+        ach = flops / (ms * 1e-3) / 1e12
+        facts = ncu_facts("conv_gemm_512_1024_k4s1_b%d" % n) or {}
+        return {"bound": "tensor", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_burst"], "traffic": facts.get("dram_bytes"),
+                "traffic_unit": "bytes/launch (ncu dram read+write)", "ncu_tensor_pipe_active_pct": facts.get("tensor_pipe_pct"),
+                "ncu_capture": facts.get("capture"),
+                "kernel": "conv_gemm_persistent_kernel<256,4>: PatchGAN 512->1024 k4 s1 fprop, M=%d N=1024 K=8192" % (n * 961),
+                "algorithmic_flop_per_launch": flops, "avg_launch_ms": ms,
+                "peak_source": pk["source"] + ", burst (kernel timed alone)"}
+    # HBM-bound workloads: instance/batch-norm apply on the largest normalised activation
+    if model == "cyclegan":
+        n, hw, c, per_sample, what = batch, 256 * 256, 64, 1, "InstanceNorm apply + ReLU, teacher stem 64 ch @ 256x256"
+    elif model == "srgan":
+        n, hw, c, per_sample, what = batch, 96 * 96, 64, 0, "BatchNorm apply, teacher SRResNet block 64 ch @ 96x96"
+    else:
+        n, hw, c, per_sample, what = batch, 32 * 32, 64, 0, "BatchNorm apply + ReLU, teacher l4 64 ch @ 32x32"
+    x = torch.randn(n, hw, c, device="cuda").to(torch.bfloat16)
+    y = torch.empty_like(x)
+    sums = torch.zeros((n if per_sample else 1) * 2 * c, device="cuda")
+    _lib.call("gcc_norm_stats_bf16", x.data_ptr(), n, hw, c, per_sample, sums.data_ptr(), st)
+    ms = time_it(lambda: _lib.call("gcc_norm_apply_bf16", x.data_ptr(), y.data_ptr(), n, hw, c, c, per_sample, sums.data_ptr(),
+                                   None, None, None, 0.5, 1e-5, None, None, 0.1, 2, 0.2, 0, None, 0, 0, 0, 0, st))
+    nbytes = 4.0 * n * hw * c
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+            "kernel": "norm_apply_kernel: " + what, "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": ms,
+            "peak_source": pk["source"] + ", copy bandwidth"}
 
 
 def _watchdog(seconds):
     """A hung collective or kernel must not hold the GPU box: give up loudly after `seconds`."""
-    import threading
-
     def bark():
         sys.stderr.write("bench.py: watchdog expired after %d s, aborting\n" % seconds)
         sys.stderr.flush()
@@ -230,56 +346,38 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG", "WARN")     # never overrides the caller's setting (e.g. NCCL_DEBUG=INFO)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from gcc_b200 import _lib, options
-    from gcc_b200.pix2pix import Pix2PixModel, build_teacher
-    argv = ["--dataroot", "./database/cityscapes/", "--model", "pix2pix", "--ngf", str(args.ngf), "--ndf", str(args.ndf),
-            "--teacher_ngf", str(args.teacher_ngf), "--darts_discriminator", "--online_distillation",
-            "--lambda_content", "50", "--lambda_gram", "1e4", "--gpu_ids", str(local), "--backbone", args.backbone,
-            "--batch_size", str(args.batch)]
-    if args.no_dropout:
+    from gcc_b200 import _lib, factory
+    from gcc_b200.graph import GraphedIteration
+    from gcc_b200.prefetch import Prefetcher
+    c = args.cfg
+    name = c["model"]
+    argv = []
+    if args.no_dropout and name == "pix2pix":
         argv.append("--no_dropout")
-    opt = options.parse(argv)
-    torch.manual_seed(1234 + rank)
-    model = Pix2PixModel(opt)
-    build_teacher(model, opt)
-    model.model_train()
-    if world > 1:  # replicate the initial weights of rank 0
-        for m in (model, model.teacher_model):
-            for a in (m.arena_G, m.arena_D, m.arena_A):
-                if a is not None:
-                    dist.broadcast(a.P, 0)
-                    a.mark_dirty()
+    if args.sync_bn:
+        argv.append("--sync_bn")
+    opt = factory.make_opt(name, local, argv, batch_size=args.batch, **c["opt"])
+    torch.manual_seed(1234 + rank)          # different seeds per rank: the constructors broadcast rank 0's parameters
+    model, teacher = factory.build_pair(opt, c["cfgs"])
 
     B = args.batch
     g = torch.Generator().manual_seed(99 + rank)
     nbatch = 2
-    host = [{k: torch.rand(B, 3, 256, 256, generator=g).mul_(2).sub_(1).pin_memory() for k in ("A", "B", "vA", "vB")}
+    host = [(factory.synthetic_batch(name, B, c["size"], g, pin=True), factory.synthetic_batch(name, B, c["size"], g, pin=True))
             for _ in range(nbatch)]
-    devb = [{k: v.cuda() for k, v in h.items()} for h in host]
+    devb = [tuple({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()} for d in pair) for pair in host]
+    h2d_fp32 = sum(v.numel() * 4 for pair in host[:1] for d in pair for v in d.values() if torch.is_tensor(v))
 
     graphed = None
-    pace_ev = torch.cuda.Event()
 
-    def step(d, read_losses):
+    def step(pair, read_losses):
         if graphed is not None:
-            graphed.run(d)
-            if read_losses:
-                return model.get_current_losses()
-            if world > 1 and args.pace:
-                # data parallel: keep the host at most one iteration ahead of the device.  Measured on 4 and 8 GPUs:
-                # an unpaced host (all K iterations' graph segments and collectives queued at once) runs 1-4 ms per
-                # iteration SLOWER than the end-to-end loop, whose loss read-back paces it.
-                pace_ev.record()
-                pace_ev.synchronize()
-            return None
-        model.set_input({"A": d["A"], "B": d["B"], "A_paths": "", "B_paths": ""})
-        model.optimize_parameters()
-        model.set_input({"A": d["vA"], "B": d["vB"], "A_paths": "", "B_paths": ""})
-        model.clipping_mask_alpha()
-        model.optimizer_netD_arch()
+            graphed.run(pair[0], pair[1])
+        else:
+            factory.run_iteration(model, pair[0], pair[1])
         if read_losses:
             return model.get_current_losses()  # float() of every loss: device -> host reads
 
@@ -288,14 +386,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, data, read_losses):
+    def timed(nsteps, source, read_losses):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.lib().gcc_launch_count()
         torch.arange(5, device="cuda").cumsum(0)  # marker kernel: scripts/summarize_launches.py cuts the ncu list here
         e0.record()
         for i in range(nsteps):
-            step(data[i % nbatch], read_losses)
+            step(source(i), read_losses)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -319,23 +417,34 @@ def run_b200(args):
         sampler.start()  # sampled from the warm-up on: the GPU is under the same load as in the timed region
     launches_per_step = None
     if args.graph:
-        from gcc_b200.graph import GraphedIteration
         step(devb[0], False)
         l0 = _lib.lib().gcc_launch_count()
         step(devb[1], False)
         launches_per_step = _lib.lib().gcc_launch_count() - l0  # the captured graph replays exactly these launches
-        graphed = GraphedIteration(model, B).capture(devb[0], warmup=1)
+        graphed = GraphedIteration(model).capture(devb[0][0], devb[0][1], warmup=1)
     for i in range(args.warmup):
         step(devb[i % nbatch], False)
-    ms, launches = timed(args.steps, devb, False)
+    ms, launches = timed(args.steps, lambda i: devb[i % nbatch], False)
     if launches_per_step is not None:
         launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
-    if args.skip_e2e:
-        ms_e2e = float("nan")
-    else:
-        step(host[0], True)  # warm the host-input path once
-        ms_e2e, _ = timed(args.steps, host, True)
+    e2e = None
+    if not args.skip_e2e:
+        # end to end through the public API with HOST buffers: every step's inputs go pinned host memory -> device
+        # (gcc_b200.prefetch.Prefetcher: bf16 staging, copy stream) inside the timed region, every step's losses are
+        # read back to the host.
+        def stream_of(n):
+            for i in range(n):
+                yield host[i % nbatch]
+        pf = Prefetcher(stream_of(args.steps + 1), torch.device("cuda", local))
+        step(next(pf), True)     # warm the host-input path once
+        b0 = pf.h2d_bytes
+        ms_e2e, _ = timed(args.steps, lambda i: next(pf), True)
+        h2d = (pf.h2d_bytes - b0) / max(1, args.steps)
+        pf.close()
+        e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+               "h2d_note": "bf16 staging of the fp32 host batch (fp32 would be %d bytes)" % h2d_fp32,
+               "d2h_bytes_per_step": 4 * len(model.loss_names), "ms_per_step": ms_e2e / args.steps}
 
     if rank != 0:
         if world > 1:
@@ -344,28 +453,27 @@ def run_b200(args):
     pk = peaks()
     imgs = world * B * args.steps
     value = imgs / (ms * 1e-3)
-    gmacs = step_gmacs(args.ngf, args.teacher_ngf, args.ndf, args.backbone)
-    step_tflops = value / world * gmacs * 2e9 / 1e12
+    cfgd = {"workload": workload_name(args), "name": args.config, "global_batch": world * B, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (saved activations of all net passes at batch %d) >> 126 MB L2; two alternating "
+                  "input batches" % B, "cuda_graph": bool(args.graph), "sync_bn": bool(args.sync_bn)}
+    gm = step_gmacs(args)
+    if gm is not None:
+        step_tflops = value / world * gm["total"] * 2e9 / 1e12
+        cfgd.update({"algorithmic_gmac_per_image": gm["total"], "fwd_gmac": {k: gm[k] for k in ("g_T", "g_S", "d")},
+                     "gmac_formula": "4 g_T + 4 g_S + 24 d + Gram + transform (SURVEY.md 8d; true MACs, gcc_b200.macs)",
+                     "step_tensor_tflops_per_gpu": step_tflops,
+                     "step_frac_of_sustained_bf16_peak": step_tflops / pk["bf16_sustained"],
+                     "step_frac_of_burst_bf16_peak": step_tflops / pk["bf16_burst"]})
     line = {
-        "metric": "GCC train images/sec (pix2pix 256^2)", "value": value, "unit": "images/s", "n_gpus": world,
+        "metric": "GCC train images/sec (pix2pix 256^2)" if name == "pix2pix" else "GCC train images/sec (%s)" % args.config,
+        "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": "dp%d" % world,
-                   "l2": "per-step working set (activations of 15 net passes at batch %d, several GB) >> 126 MB L2; "
-                         "two alternating input batches" % B,
-                   "cuda_graph": bool(args.graph),
-                   "algorithmic_gmac_per_image": gmacs,
-                   "step_tensor_tflops_per_gpu": step_tflops,
-                   "step_frac_of_sustained_bf16_peak": step_tflops / pk["bf16_sustained"]},
-        "clocks": clocks,
-        "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s",
-                "h2d_bytes_per_step": 4 * B * 3 * 256 * 256 * 4, "d2h_bytes_per_step": 4 * len(model.loss_names),
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfgd, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(launches),
     }
     if world == 1:
         if not args.skip_roofline:
-            line["roofline"] = dominant_kernel_roofline(B, pk)
+            line["roofline"] = dominant_kernel_roofline(args, pk)
         if not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_rate(args, iters=args.cpu_iters)
     else:

@@ -64,5 +64,19 @@ def build(verbose=False, force=False):
     return LIB
 
 
+def build_check(verbose=False):
+    """CUDA-core cross-check kernels (scripts/csrc/conv_direct.cu): development probes only, NOT part of the product
+    library or its public header.  Same argument lists as gcc_conv_gemm_bf16 / gcc_wgrad_gemm_bf16."""
+    root = os.path.dirname(HERE)
+    src = [os.path.join(root, "scripts", "csrc", f) for f in ("conv_direct.cu", "check_stub.cu")]
+    out = os.path.join(root, "scripts", "libgcc_b200_check.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in src):
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", CSRC, "-I", os.path.join(root, "include"), "-shared", "-o", out] + src
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(verbose=True, force="--force" in sys.argv))

@@ -712,17 +712,26 @@ static int make_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int 
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
+// per-device caches (one process may drive several devices): function attributes and the SM count
+static constexpr int kMaxDevices = 64;
+static int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 template <int BLOCK_N, int STAGES, int MT>
 static int launch_wgrad_gemm(const GemmGeom& g, dim3 grid, cudaStream_t st) {
   const int smem = STAGES * (2 * MT * 8192 + (BLOCK_N / 64) * 8192) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = cur_device();
+  if (!configured[dev]) {
     if (cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem) != cudaSuccess) {
       gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
       return GCC_ERR_CUDA;
     }
-    configured = true;
+    configured[dev] = true;
   }
   wgrad_gemm_kernel<BLOCK_N, STAGES, MT><<<grid, 192, smem, st>>>(g);
   GCC_CHECK_LAUNCH();
@@ -785,29 +794,29 @@ static void trace_end(cudaStream_t st, const char* kind, int N, int H, int W, in
   fprintf(stderr, "GCCTRACE %s N=%d H=%d W=%d C=%d R=%d OH=%d OW=%d k=%d s=%d mode=%d BN=%d tiles=%d ksplit=%d kb=%d stats=%d us=%.1f tflops=%.0f\n",
           kind, N, H, W, C, R, OH, OW, k, s, mode, BN, tiles, ksplit, kb, stats, ms * 1e3, flop / (ms * 1e9));
 }
-static int g_num_sms = 0;
+static int g_num_sms[kMaxDevices] = {};
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = kNumSMs;
+  const int dev = cur_device();
+  if (g_num_sms[dev] == 0) {
+    cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms[dev] <= 0) g_num_sms[dev] = kNumSMs;
   }
-  return g_num_sms;
+  return g_num_sms[dev];
 }
 
 template <int BLOCK_N, int STAGES, bool TS>
 static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
   const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + (TS ? 2 * (BLOCK_N / 64) * 16384 : 0) + 1024 + 256 +
                    8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = cur_device();
+  if (!configured[dev]) {
     if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem) != cudaSuccess) {
       gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
       return GCC_ERR_CUDA;
     }
-    configured = true;
+    configured[dev] = true;
   }
   const int grid = g.total_tiles < num_sms() ? g.total_tiles : num_sms();
   conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS><<<grid, 320, smem, st>>>(g);

@@ -573,6 +573,68 @@ static inline int blocks_for(long long n, int per = 256) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ---------------------------------------------------------------------------------------- image pool
+// ImagePool.query (utils/image_pool.py:22-54) with the pool, its fill count and the random stream resident on the
+// device, so that a captured CUDA graph replays the query with fresh decisions.  state[0] = images stored so far,
+// state[1] = random counter.  One thread decides sequentially for the b images of the batch (the reference loops
+// over them in order: a later image may swap out an earlier one of the same batch):
+//   dec[2i]   = where out[i] comes from: -1 own image, s >= 0 pool slot s (content before this call),
+//               -(2 + j) image j of this batch (it was stored into the chosen slot earlier in the loop)
+//   dec[2i+1] = pool slot that receives image i at the end of the call, or -1
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+__global__ void image_pool_decide_kernel(long long* state, int pool_size, int b, int* dec) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long count = state[0];
+  unsigned long long ctr = (unsigned long long)state[1];
+  for (int i = 0; i < b; ++i) {
+    int src = -1, dst = -1;
+    if (count < pool_size) {
+      dst = (int)count++;
+    } else {
+      const unsigned long long r = splitmix64(ctr++);
+      if ((r >> 11) * (1.0 / 9007199254740992.0) > 0.5) {
+        const int slot = (int)(splitmix64(ctr++) % (unsigned long long)pool_size);
+        src = slot;
+        for (int j = i - 1; j >= 0; --j)       // the slot may hold an image of this very batch
+          if (dec[2 * j + 1] == slot) { src = -(2 + j); dec[2 * j + 1] = -1; break; }
+        dst = slot;
+      }
+    }
+    dec[2 * i] = src;
+    dec[2 * i + 1] = dst;
+  }
+  state[0] = count;
+  state[1] = (long long)ctr;
+}
+__global__ void image_pool_gather_kernel(const uint4* __restrict__ images, const uint4* __restrict__ pool,
+                                         const int* __restrict__ dec, uint4* __restrict__ out, long long vec_per_image) {
+  const int i = blockIdx.y;
+  const int src = dec[2 * i];
+  const uint4* s = src == -1 ? images + (long long)i * vec_per_image
+                             : (src >= 0 ? pool + (long long)src * vec_per_image
+                                         : images + (long long)(-(src + 2)) * vec_per_image);
+  uint4* o = out + (long long)i * vec_per_image;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < vec_per_image;
+       v += (long long)gridDim.x * blockDim.x)
+    o[v] = s[v];
+}
+__global__ void image_pool_scatter_kernel(const uint4* __restrict__ images, uint4* __restrict__ pool,
+                                          const int* __restrict__ dec, long long vec_per_image) {
+  const int i = blockIdx.y;
+  const int dst = dec[2 * i + 1];
+  if (dst < 0) return;
+  const uint4* s = images + (long long)i * vec_per_image;
+  uint4* o = pool + (long long)dst * vec_per_image;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < vec_per_image;
+       v += (long long)gridDim.x * blockDim.x)
+    o[v] = s[v];
+}
+
 }  // namespace gcc
 
 using namespace gcc;
@@ -722,10 +784,13 @@ extern "C" int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w,
     long long bx = (npix + lanes * 16 - 1) / (lanes * 16);
     if (bx > 148 * 4) bx = 148 * 4;
     const size_t smem = sizeof(float) * lanes * G * 80;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (!configured[dev]) {
       cudaFuncSetAttribute(dw3x3_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      configured = true;
+      configured[dev] = true;
     }
     dw3x3_bwd_weight_kernel<<<(unsigned)bx, threads, smem, st>>>((const bf16*)x, (const bf16*)dy, dw, dbias, N, H, W,
                                                                  G, C, lanes);
@@ -776,6 +841,26 @@ extern "C" int gcc_unfold_k4s1_c8(const void* dy, void* dcol, int N, int H, int 
 extern "C" int gcc_unpad_wgrad_rows(const float* tmp, float* g, int C, int K, void* stream) {
   if (C > 8) { gcc_set_error(__FILE__, __LINE__, "unpad_wgrad_rows: C must be <= 8"); return GCC_ERR_ARG; }
   unpad_wgrad_rows_kernel<<<blocks_for((long long)C * 16 * K), 256, 0, (cudaStream_t)stream>>>(tmp, g, C, K);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+extern "C" int gcc_image_pool_query_bf16(const void* images, void* pool, long long* state_dev, int* dec_ws, void* out,
+                                         int b, long long elems_per_image, int pool_size, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (elems_per_image % 8 || b <= 0 || pool_size <= 0) {
+    gcc_set_error(__FILE__, __LINE__, "image_pool_query: bad arguments");
+    return GCC_ERR_ARG;
+  }
+  const long long vec = elems_per_image / 8;
+  image_pool_decide_kernel<<<1, 32, 0, st>>>(state_dev, pool_size, b, dec_ws);
+  GCC_CHECK_LAUNCH();
+  long long bx = (vec + 255) / 256;
+  if (bx > 148 * 4) bx = 148 * 4;
+  image_pool_gather_kernel<<<dim3((unsigned)bx, b), 256, 0, st>>>((const uint4*)images, (const uint4*)pool, dec_ws,
+                                                                  (uint4*)out, vec);
+  GCC_CHECK_LAUNCH();
+  image_pool_scatter_kernel<<<dim3((unsigned)bx, b), 256, 0, st>>>((const uint4*)images, (uint4*)pool, dec_ws, vec);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(256, 4) norm_stats_kernel(const bf16* __restri
 
 struct NormArgs {
   const bf16* x;
-  long long npix;  // pixels per statistics group (N*H*W for batch norm, H*W for instance norm)
+  long long npix;  // pixels per statistics group (N*H*W for batch norm, H*W for instance norm) on THIS device
+  long long stat_npix;  // pixels behind `sums` / `red` (= npix, or the global count under sync batch norm)
   int Cp, C, G;
   int per_sample;
   const float* sums;   // nullptr: identity (no normalisation)
@@ -135,7 +136,7 @@ __device__ __forceinline__ void channel_affine(const NormArgs& a, int n, int c, 
   rstd = 1.f;
   if (a.sums != nullptr) {
     const float* sb = a.sums + (long long)(a.per_sample ? n : 0) * 2 * a.Cp;
-    const float inv = 1.f / (float)a.npix;
+    const float inv = 1.f / (float)a.stat_npix;
     mean = sb[c] * inv;
     const float var = fmaxf(sb[a.Cp + c] * inv - mean * mean, 0.f);
     rstd = rsqrtf(var + a.eps);
@@ -200,10 +201,10 @@ norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict_
   // running statistics (train-mode BatchNorm2d side effect; momentum 0.1, unbiased variance)
   if (running_mean != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && a.sums != nullptr) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-      const float inv = 1.f / (float)a.npix;
+      const float inv = 1.f / (float)a.stat_npix;
       const float mean = a.sums[c] * inv;
       const float var = fmaxf(a.sums[a.Cp + c] * inv - mean * mean, 0.f);
-      const float unb = a.npix > 1 ? var * ((float)a.npix / (float)(a.npix - 1)) : var;
+      const float unb = a.stat_npix > 1 ? var * ((float)a.stat_npix / (float)(a.stat_npix - 1)) : var;
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
     }
@@ -334,12 +335,12 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
 template <bool HAS_D2>
 __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int nimg, int lanes, const bf16* __restrict__ dy, int dy_Cp,
                                       int dy_coff, const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
-                                      const float* __restrict__ red, bf16* __restrict__ dx, float* dgamma,
-                                      float* dbeta, float* dalpha) {
+                                      const float* __restrict__ red, const float* __restrict__ red_param,
+                                      bf16* __restrict__ dx, float* dgamma, float* dbeta, float* dalpha) {
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
   const int n = blockIdx.y;
-  const float invM = 1.f / (float)a.npix;
+  const float invM = 1.f / (float)a.stat_npix;
   if (dx != nullptr && lane < lanes) {
     const float* rb = red + (long long)n * 2 * a.Cp;
     float cp[8], cq[8], c1[8], c2[8], c3[8];
@@ -405,9 +406,9 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
     const int groups = a.per_sample ? nimg : 1;
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       float S1 = 0.f, S2 = 0.f;
-      for (int m = 0; m < groups; ++m) {
-        S1 += red[(long long)m * 2 * a.Cp + c];
-        S2 += red[(long long)m * 2 * a.Cp + a.Cp + c];
+      for (int m = 0; m < groups; ++m) {  // parameter gradients come from THIS device's sums (red_param)
+        S1 += red_param[(long long)m * 2 * a.Cp + c];
+        S2 += red_param[(long long)m * 2 * a.Cp + a.Cp + c];
       }
       const float gam = a.gamma ? a.gamma[c] : 1.f;
       const float bet = a.beta ? a.beta[c] : 0.f;
@@ -434,13 +435,14 @@ using namespace gcc;
 
 static int fill_args(NormArgs& a, const void* x, int N, long long HW, int Cp, int C, int per_sample,
                      const float* sums, const float* gamma, const float* beta, const float* alpha, float thr,
-                     float eps, int act, float slope, int gate_after = 0) {
+                     float eps, int act, float slope, int gate_after = 0, long long stat_count = 0) {
   if (Cp % 8 || C > Cp || Cp / 8 > 512) {
     gcc_set_error(__FILE__, __LINE__, "norm: channel count must be a multiple of 8 and <= 4096");
     return GCC_ERR_ARG;
   }
   a.x = (const bf16*)x;
   a.npix = per_sample ? HW : (long long)N * HW;
+  a.stat_npix = (stat_count > 0 && !per_sample) ? stat_count : a.npix;
   a.Cp = Cp; a.C = C; a.G = Cp / 8;
   a.per_sample = per_sample;
   a.sums = sums; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
@@ -495,10 +497,11 @@ extern "C" int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, 
                                    const float* sums, const float* gamma, const float* beta, const float* alpha,
                                    float thr, float eps, float* running_mean, float* running_var, float momentum,
                                    int act, float slope, int gate_after, void* y2, int y2_Cp, int y2_coff, int act2,
-                                   void* stream) {
+                                   long long stat_count, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   NormArgs a;
-  int rc = fill_args(a, x, N, HW, Cp, C, per_sample, sums, gamma, beta, alpha, thr, eps, act, slope, gate_after);
+  int rc = fill_args(a, x, N, HW, Cp, C, per_sample, sums, gamma, beta, alpha, thr, eps, act, slope, gate_after,
+                     stat_count);
   if (rc) return rc;
   if (y2 != nullptr && ((y2_Cp % 8) || (y2_coff % 8))) {
     gcc_set_error(__FILE__, __LINE__, "norm_apply: second output window must be 8-channel aligned");
@@ -539,17 +542,24 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
                                  const float* gamma, const float* beta, const float* alpha, float thr, float eps,
                                  int act, float slope, int gate_after, const void* dy, int dy_Cp, int dy_coff,
                                  const void* dy2, int dy2_Cp, int dy2_coff, int act2, float* red, void* dx,
-                                 float* dgamma, float* dbeta, float* dalpha, void* stream) {
+                                 float* dgamma, float* dbeta, float* dalpha, long long stat_count, int phase,
+                                 const float* red_param, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   NormArgs a;
-  int rc = fill_args(a, x, N, HW, Cp, C, per_sample, sums, gamma, beta, alpha, thr, eps, act, slope, gate_after);
+  int rc = fill_args(a, x, N, HW, Cp, C, per_sample, sums, gamma, beta, alpha, thr, eps, act, slope, gate_after,
+                     stat_count);
   if (rc) return rc;
   if ((dy && ((dy_Cp % 8) || (dy_coff % 8))) || (dy2 && ((dy2_Cp % 8) || (dy2_coff % 8)))) {
     gcc_set_error(__FILE__, __LINE__, "norm_bwd: gradient windows must be 8-channel aligned");
     return GCC_ERR_ARG;
   }
   const int groups = per_sample ? N : 1;
-  const bool need_red = (sums != nullptr) || dgamma || dbeta || dalpha;
+  if (phase < 0 || phase > 2) {
+    gcc_set_error(__FILE__, __LINE__, "norm_bwd: phase must be 0 (both), 1 (reduce) or 2 (apply)");
+    return GCC_ERR_ARG;
+  }
+  if (red_param == nullptr) red_param = red;
+  const bool need_red = ((sums != nullptr) || dgamma || dbeta || dalpha || phase == 1) && phase != 2;
   if (need_red) {
     if (cudaMemsetAsync(red, 0, sizeof(float) * 2 * Cp * groups, st) != cudaSuccess) return GCC_ERR_CUDA;
     int lanes;
@@ -562,16 +572,18 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
         a, lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
     GCC_CHECK_LAUNCH();
   }
+  if (phase == 1) return GCC_OK;
   int alanes;
   const int athreads = stats_threads(a.G, &alanes);
   const int bx = dx ? lane_blocks(a.npix, alanes, groups, 2) : 1;
   if (dy2 != nullptr)
     norm_bwd_apply_kernel<true><<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
-        a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, (bf16*)dx, dgamma,
-        dbeta, dalpha);
+        a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, red_param,
+        (bf16*)dx, dgamma, dbeta, dalpha);
   else
     norm_bwd_apply_kernel<false><<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
-        a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, nullptr, 0, 0, 0, red, (bf16*)dx, dgamma, dbeta, dalpha);
+        a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, nullptr, 0, 0, 0, red, red_param, (bf16*)dx, dgamma, dbeta,
+        dalpha);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

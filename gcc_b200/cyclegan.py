@@ -17,6 +17,7 @@ import torch.nn as nn
 
 from . import ops
 from .arena import ParamArena
+from .base import GccModelMixin
 from .nets import ConvLayer, MaskNLayerDiscriminator, MobileResnetGenerator, NLayerDiscriminator
 from .ops import GAN_MODES
 from .pix2pix import _ArenaOptimizer, get_scheduler
@@ -47,7 +48,34 @@ class ImagePool:
         return torch.cat(out, 0)
 
 
-class MobileCycleGANModel(nn.Module):
+class DeviceImagePool:
+    """ImagePool with the buffer, its fill count and the random stream on the device (`gcc_image_pool_query_bf16`):
+    same policy as utils/image_pool.py:22-54, but capturable in a CUDA graph -- every replay draws fresh decisions.
+    The random stream is a device counter (not Python's `random`), so the swap choices differ from a host pool's."""
+
+    def __init__(self, pool_size, seed=0):
+        self.pool_size = pool_size
+        self.buf = self.state = self.dec = None
+        self.seed = seed
+
+    def query(self, images):
+        images = images.detach().contiguous()
+        if self.pool_size == 0:
+            return images
+        b = images.shape[0]
+        per = images[0].numel()
+        if self.buf is None:
+            self.buf = torch.zeros((self.pool_size,) + tuple(images.shape[1:]), dtype=images.dtype, device=images.device)
+            self.state = torch.tensor([0, self.seed], dtype=torch.int64, device=images.device)
+        if self.dec is None or self.dec.numel() < 2 * b:
+            self.dec = torch.zeros(2 * b, dtype=torch.int32, device=images.device)
+        out = torch.empty_like(images)
+        ops.call("gcc_image_pool_query_bf16", images.data_ptr(), self.buf.data_ptr(), self.state.data_ptr(),
+                 self.dec.data_ptr(), out.data_ptr(), b, per, self.pool_size, ops._st())
+        return out
+
+
+class MobileCycleGANModel(GccModelMixin, nn.Module):
 
     def __init__(self, opt, cfg_AtoB=None, cfg_BtoA=None):
         super().__init__()
@@ -63,7 +91,7 @@ class MobileCycleGANModel(nn.Module):
         self.discriminator_extract_layers = ["model.4", "model.12"] if opt.darts_discriminator else ["model.3", "model.9"]
         self.distill = bool(opt.online_distillation or getattr(opt, "normal_distillation", False))
         self.teacher_model = None
-        self._ema = {"A": None, "B": None}
+        self._base_init()
 
         self.arena_G = ParamArena(dev)
         self.transform_A_convs, self.transform_B_convs = [], []
@@ -113,6 +141,46 @@ class MobileCycleGANModel(nn.Module):
             arch_opt.lr_policy, arch_opt.lr_decay_iters = "step", opt.n_epochs - 1
             self.arch_scheduler = get_scheduler(self.optimizer_arch, arch_opt)
             self.schedulers.append(self.arch_scheduler)
+        self.broadcast_parameters()
+
+    def _gcc_arenas(self):
+        return {k: a for k, a in (("G", self.arena_G), ("D", self.arena_D), ("A", self.arena_A)) if a is not None}
+
+    def _gcc_optimizers(self):
+        d = {"G": self.optimizer_G, "D": self.optimizer_D}
+        if self.arena_A is not None:
+            d["arch"] = self.optimizer_arch
+        return d
+
+    def _gcc_nets(self):
+        return {"netG_A": self.netG_A, "netG_B": self.netG_B, "netD_A": self.netD_A, "netD_B": self.netD_B}
+
+    def _gcc_extra_state(self):
+        st = {}
+        for k, pool in (("A", self.fake_A_pool), ("B", self.fake_B_pool)):
+            if isinstance(pool, DeviceImagePool):
+                st[k] = ("device", None if pool.buf is None else pool.buf.cpu(), None if pool.state is None else pool.state.cpu())
+            else:
+                st[k] = ("host", [t.detach().cpu() for t in pool.images], None)
+        return st
+
+    def _gcc_load_extra_state(self, st):
+        for k, name in (("A", "fake_A_pool"), ("B", "fake_B_pool")):
+            kind, data, state = st[k]
+            if kind == "device":
+                self.use_device_pools()
+                pool = getattr(self, name)
+                if data is not None:
+                    pool.buf, pool.state = data.to(self.device), state.to(self.device)
+            else:
+                getattr(self, name).images = [t.to(self.device) for t in data]
+
+    def use_device_pools(self):
+        """Swap the host-random image pools for device-resident ones (needed before CUDA-graph capture)."""
+        if not isinstance(self.fake_A_pool, DeviceImagePool):
+            rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+            self.fake_A_pool = DeviceImagePool(self.fake_A_pool.pool_size, seed=1 + 7919 * rank)
+            self.fake_B_pool = DeviceImagePool(self.fake_B_pool.pool_size, seed=2 + 7919 * rank)
 
     def init_net(self):
         """util.init_weights (utils/util.py:261-286); transform convs keep the nn.Conv2d default; alpha = 1."""
@@ -150,6 +218,14 @@ class MobileCycleGANModel(nn.Module):
         self.image_paths = [input.get("A_paths" if AtoB else "B_paths"), input.get("B_paths" if AtoB else "A_paths")]
         self.real_A, self.real_B = A, B
         self.real_A_nhwc, self.real_B_nhwc = ops.to_nhwc(A), ops.to_nhwc(B)
+
+    def _adopt_input(self, other):
+        """Teacher side of ``T.set_input(self.input)`` (CycleGAN.py:569,592): share the converted batch."""
+        if other.opt.direction != self.opt.direction or other.device != self.device:
+            return self.set_input(other.input)
+        self.input, self.image_paths = other.input, other.image_paths
+        self.real_A, self.real_B = other.real_A, other.real_B
+        self.real_A_nhwc, self.real_B_nhwc = other.real_A_nhwc, other.real_B_nhwc
 
     def _nchw(self, name):
         return ops.to_nchw(getattr(self, name + "_nhwc").detach(), 3)
@@ -216,13 +292,8 @@ class MobileCycleGANModel(nn.Module):
             setattr(self, "loss_D_%s_arch_fake_real" % k, l_fake_real)
             setattr(self, "loss_D_%s_arch_real" % k, l_real)
             diff = (l_fake_real - l_fake).abs()
-            if isTeacher:  # EMA state in one persistent device scalar per discriminator (CUDA-graph friendly)
-                if self._ema[k] is None:
-                    self._ema[k] = diff.detach().clone()
-                else:
-                    b = self.opt.ema_beta
-                    self._ema[k].copy_(b * diff.detach() + (1.0 - b) * self._ema[k])
-                out[k] = self._ema[k]
+            if isTeacher:  # EMA state in one persistent device scalar per discriminator (base.py)
+                out[k] = self._ema_update(k, diff)
             else:
                 out[k] = diff
         self.current_netD_A_arch_diff_loss, self.current_netD_B_arch_diff_loss = out["A"], out["B"]
@@ -306,7 +377,7 @@ class MobileCycleGANModel(nn.Module):
         ops.zero_pool.reset()
         if self.opt.online_distillation:
             T = self.teacher_model
-            T.set_input(self.input)
+            T._adopt_input(self)
             T.optimize_parameters()
             for k in "AB":
                 feats = [(f.detach(), c) for f, c in (getattr(T, "g_taps_" + k) + getattr(T, "d_taps_" + k))]
@@ -328,7 +399,7 @@ class MobileCycleGANModel(nn.Module):
     def optimizer_netD_arch(self):
         ops.zero_pool.reset()
         self.forward()
-        self.teacher_model.set_input(self.input)
+        self.teacher_model._adopt_input(self)
         self.teacher_model.forward()
         self.set_requires_grad([self.netD_A, self.netD_B], True)
         self.set_netD_weight_grad(False)
@@ -412,16 +483,20 @@ class MobileCycleGANModel(nn.Module):
         os.makedirs(save_dir, exist_ok=True)
         ckpt = {"G_A": self.netG_A.state_dict(), "G_B": self.netG_B.state_dict(), "D_A": self.netD_A.state_dict(),
                 "D_B": self.netD_B.state_dict(), "epoch": epoch, "cfg": (self.cfg_AtoB, self.cfg_BtoA), "fid": fid}
-        torch.save(ckpt, os.path.join(save_dir, "model_best_%s.pth" % direction if isbest else "model_%d.pth" % epoch))
+        torch.save(self._ckpt_add_resume(ckpt),
+                   os.path.join(save_dir, "model_best_%s.pth" % direction if isbest else "model_%d.pth" % epoch))
 
-    def load_models(self, load_path, load_discriminator=True):
-        ckpt = torch.load(load_path, map_location=self.device)
+    def load_models(self, load_path, load_discriminator=True, resume=None):
+        """`resume`: None = continue training exactly (optimizer moments, counters, EMA, teacher) when the file carries
+        the `gcc_b200` entry and the discriminator is loaded too; False = weights only, as the reference."""
+        ckpt = torch.load(load_path, map_location=self.device, weights_only=False)
         drop = lambda sd: {k: v for k, v in sd.items() if not (k.endswith("total_ops") or k.endswith("total_params"))}
         self.netG_A.load_state_dict(drop(ckpt["G_A"]))
         self.netG_B.load_state_dict(drop(ckpt["G_B"]))
         if load_discriminator:
             self.netD_A.load_state_dict(drop(ckpt["D_A"]))
             self.netD_B.load_state_dict(drop(ckpt["D_B"]))
+        self._ckpt_load_resume(ckpt, load_discriminator, resume)
         print("loading the model from %s" % load_path)
 
     # ------------------------------------------------------------------ pruning (index selection)

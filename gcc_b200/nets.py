@@ -229,13 +229,21 @@ class UnetGenertor(_Net):
         self._arenas = [self.arena]
         self.ngf, self.use_dropout = ngf, use_dropout
         self.lv, self.present = unet_channels(ngf, filter_cfgs, channel_cfgs, input_nc, output_nc)
-        pre = unet_level_prefixes()
+        # Levels whose cfg entry is zero are left out and the next deeper PRESENT level becomes the submodule
+        # (models/Pix2Pix.py:87-102); module names follow the nesting actually built.  The deepest present level gets
+        # an Identity submodule when it is not the innermost block (Pix2Pix.py:62-69).
+        self.levels = [i for i in range(8) if self.present[i]]
+        self.next_level = {a: b for a, b in zip(self.levels, self.levels[1:])}
+        pre_list = unet_level_prefixes(len(self.levels))
+        pre = {lvl: pre_list[k] for k, lvl in enumerate(self.levels)}
+        for a, b in self.next_level.items():
+            if self.lv[b][0] != self.lv[a][1] or self.lv[a][2] != self.lv[a][1] + self.lv[b][3]:
+                raise ValueError("U-Net cfg: level %d (out %d, up-in %d) does not chain to level %d (in %d, up-out %d)" % (
+                    a, self.lv[a][1], self.lv[a][2], b, self.lv[b][0], self.lv[b][3]))
         A = self.arena
         self.down, self.dnorm, self.up, self.unorm = {}, {}, {}, {}
         layers = []
-        for i in range(8):
-            if not self.present[i]:
-                continue
+        for i in self.levels:
             di, do, ui, uo = self.lv[i]
             p = pre[i]
             if i == 0:
@@ -253,13 +261,11 @@ class UnetGenertor(_Net):
                 self.unorm[i] = NormLayer(A, p + ".6", uo, "bn", device)
         # registration order = reference module order (down modules, submodule, up modules)
         def order(i):
-            if not self.present[i]:
-                return
             layers.append(self.down[i])
             if i in self.dnorm:
                 layers.append(self.dnorm[i])
-            if i + 1 < 8:
-                order(i + 1)
+            if i in self.next_level:
+                order(self.next_level[i])
             layers.append(self.up[i])
             if i in self.unorm:
                 layers.append(self.unorm[i])
@@ -286,10 +292,10 @@ class UnetGenertor(_Net):
         else:
             d, dsums = self.down[i].with_stats(a)
             y, y2 = self.dnorm[i](d, ACT_LRELU, ACT_RELU, dsums)
-            if i + 1 < 8 and self.present[i + 1]:
-                rc, crc = self._block(i + 1, y, y2, do)
+            if i in self.next_level:
+                rc, crc = self._block(self.next_level[i], y, y2, do)
                 feat = y
-            else:
+            else:                      # Identity submodule: the in-place uprelu also mutates the hooked tensor
                 rc, crc, feat = y2, do, y2
             if i == 1:
                 self.taps[0], self.taps[3] = (feat, do), (rc, crc)
@@ -310,7 +316,7 @@ class UnetGenertor(_Net):
         di, do, ui, uo = self.lv[0]
         d0 = self.down[0](x)
         a, a_relu = self.dnorm[0](d0, ACT_LRELU, ACT_RELU)
-        r, cr = self._block(1, a, a_relu, do)
+        r, cr = self._block(self.next_level[0], a, a_relu, do)
         return self.up[0](r, ACT_TANH)
 
 

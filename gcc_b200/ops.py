@@ -17,6 +17,32 @@ BN_MOM = 0.1
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
 
+# Global-batch parity under data parallel, off by default: when set (models built with --sync_bn
+# inside an initialised process group), BatchNorm statistics (forward: sum x, sum x^2; backward: sum dg, sum dg*xhat)
+# and every loss mean are all-reduced BEFORE any non-linearity that follows (sqrt of the MSE / Gram MSE, |.| of the
+# arch-step loss differences), so that N ranks x batch b compute the step of one device at batch N*b (running
+# statistics, the teacher EMA scalar and the reported losses then stay replicated).
+GLOBAL_BATCH_SYNC = False
+
+
+def _world():
+    return torch.distributed.get_world_size() if GLOBAL_BATCH_SYNC else 1
+
+
+def _allreduce_sum(t):
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+
+
+def _global_mean(t):
+    """Per-rank mean (device scalar, in place) -> mean over the global batch.  The backward kernels keep the per-rank
+    scaling: every rank holds the gradient of the GLOBAL loss times the world size, the convention under which
+    averaging the parameter gradients over ranks (the data-parallel all-reduce) yields the global-batch gradient."""
+    if GLOBAL_BATCH_SYNC:
+        _allreduce_sum(t)
+        t.mul_(1.0 / _world())
+    return t
+
+
 
 def _st():
     return torch.cuda.current_stream().cuda_stream
@@ -348,6 +374,7 @@ class NormActFn(torch.autograd.Function):
                  layer.running_mean.data_ptr(), layer.running_var.data_ptr(), gp, bp, ap, layer.thr, BN_EPS, act,
                  layer.slope, None if y2 is None else y2.data_ptr(), cp, 0, act2 or 0, st)
             ctx.eval_bn = True
+            ctx.stat_count = 0
         else:
             ctx.eval_bn = False
             if mode != "id":
@@ -358,6 +385,11 @@ class NormActFn(torch.autograd.Function):
                     call("gcc_norm_stats_bf16", x.data_ptr(), n, h * w, cp, per_sample, sums.data_ptr(), st)
                 if layer.stats_hook is not None:
                     layer.stats_hook(sums)
+                if GLOBAL_BATCH_SYNC and mode == "bn":
+                    if sums_in is not None:
+                        sums = sums.clone()      # the producer's buffer belongs to the shared zero pool
+                    _allreduce_sum(sums)
+            stat_count = n * h * w * _world() if mode == "bn" else 0
             rm = rv = None
             if mode == "bn" and layer.running_mean is not None:
                 rm, rv = layer.running_mean.data_ptr(), layer.running_var.data_ptr()
@@ -365,7 +397,8 @@ class NormActFn(torch.autograd.Function):
             call("gcc_norm_apply_bf16", x.data_ptr(), y.data_ptr(), n, h * w, cp, layer.c, per_sample,
                  None if sums is None else sums.data_ptr(), gp, bp, ap, layer.thr, BN_EPS, rm, rv, BN_MOM, act,
                  layer.slope, 1 if (getattr(layer, "gate_after", mode == "id") and mode == "id" and alpha is not None) else 0,
-                 None if y2 is None else y2.data_ptr(), cp, 0, act2 or 0, st)
+                 None if y2 is None else y2.data_ptr(), cp, 0, act2 or 0, stat_count, st)
+            ctx.stat_count = stat_count
         ctx.layer, ctx.act, ctx.act2 = layer, act, act2
         ctx.save_for_backward(x, sums, gamma, beta, alpha)
         ctx.set_materialize_grads(False)
@@ -396,12 +429,24 @@ class NormActFn(torch.autograd.Function):
         dalpha = arena_of(alpha) if (alpha is not None and ctx.needs_input_grad[3]) else None
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         red = torch.empty((n if per_sample else 1) * 2 * cp, dtype=torch.float32, device=x.device)
-        call("gcc_norm_bwd_bf16", x.data_ptr(), n, h * w, cp, layer.c, per_sample,
-             None if sums is None else sums.data_ptr(), None if gamma is None else gamma.data_ptr(),
-             None if beta is None else beta.data_ptr(), None if alpha is None else alpha.data_ptr(), layer.thr, BN_EPS,
-             ctx.act, layer.slope, 1 if (getattr(layer, "gate_after", layer.mode == "id") and layer.mode == "id" and alpha is not None) else 0, p1, c1, 0, p2, c2, 0,
-             ctx.act2 or 0, red.data_ptr(),
-             None if dx is None else dx.data_ptr(), dgamma, dbeta, dalpha, st)
+        gate_after = 1 if (getattr(layer, "gate_after", layer.mode == "id") and layer.mode == "id" and alpha is not None) else 0
+
+        def bwd(phase, red_param):
+            call("gcc_norm_bwd_bf16", x.data_ptr(), n, h * w, cp, layer.c, per_sample,
+                 None if sums is None else sums.data_ptr(), None if gamma is None else gamma.data_ptr(),
+                 None if beta is None else beta.data_ptr(), None if alpha is None else alpha.data_ptr(), layer.thr, BN_EPS,
+                 ctx.act, layer.slope, gate_after, p1, c1, 0, p2, c2, 0, ctx.act2 or 0, red.data_ptr(),
+                 None if dx is None else dx.data_ptr(), dgamma, dbeta, dalpha, ctx.stat_count, phase,
+                 None if red_param is None else red_param.data_ptr(), st)
+
+        if GLOBAL_BATCH_SYNC and layer.mode == "bn":
+            # sync batch norm: dx needs the GLOBAL sums, the parameter gradients this rank's share of them
+            bwd(1, None)
+            red_local = red.clone()
+            _allreduce_sum(red)
+            bwd(2, red_local)
+        else:
+            bwd(0, None)
         return dx, None, None, None, None, None, None, None
 
 
@@ -573,6 +618,7 @@ class GanLossFn(torch.autograd.Function):
         out = torch.zeros((), dtype=torch.float32, device=pred.device)
         npix = pred.numel() // pred.shape[-1]
         call("gcc_gan_loss_fwd_bf16", pred.data_ptr(), npix, pred.shape[-1], c, mode, kind, out.data_ptr(), _st())
+        _global_mean(out)
         ctx.args = (npix, c, mode, kind)
         ctx.save_for_backward(pred)
         return out
@@ -599,6 +645,7 @@ class DiffLossFn(torch.autograd.Function):
         acc = torch.zeros((), dtype=torch.float32, device=a.device)
         st = _st()
         call("gcc_diff_reduce_bf16", a.data_ptr(), b.data_ptr(), npix, a.shape[-1], c, 1 if mode else 0, acc.data_ptr(), st)
+        _global_mean(acc)               # mean over the global batch BEFORE the square root
         if mode == 1:
             out = torch.empty_like(acc)
             call("gcc_scalar_sqrt", acc.data_ptr(), out.data_ptr(), st)
@@ -640,6 +687,7 @@ class GramRmseFn(torch.autograd.Function):
         acc = torch.zeros((), dtype=torch.float32, device=f.device)
         st = _st()
         call("gcc_sqdiff_reduce_f32", gs.data_ptr(), gt.data_ptr(), gs.numel(), acc.data_ptr(), st)
+        _global_mean(acc)
         if mse:
             out = acc
         else:

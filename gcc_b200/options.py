@@ -28,13 +28,16 @@ _SWITCHES = ["no_dropout", "serial_batches", "no_flip", "split_dataset", "scale_
              "darts_discriminator", "arch_lr_step", "adaptive_ema", "regular", "arch_base_loss", "only_arch_base",
              "normalize_arch", "clear_arch", "online_distillation", "normal_distillation", "center_crop",
              "generator_only"]
+# gcc_b200 extensions (not reference flags): --sync_bn = global-batch parity under data parallel (synchronised
+# BatchNorm statistics and loss partial sums all-reduced before sqrt / abs)
+_EXT_SWITCHES = ["sync_bn"]
 
 
 def make_parser():
     p = argparse.ArgumentParser("GAN-Compression (gcc_b200)")
     for name, typ, default in _FLAGS:
         p.add_argument("--" + name, type=typ, default=default)
-    for name in _SWITCHES:
+    for name in _SWITCHES + _EXT_SWITCHES:
         p.add_argument("--" + name, action="store_true")
     return p
 

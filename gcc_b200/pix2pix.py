@@ -12,7 +12,6 @@ gradient arenas are all-reduced over NCCL before every optimizer step (data para
 """
 import copy
 import os
-import weakref
 from collections import OrderedDict
 
 import torch
@@ -20,6 +19,7 @@ import torch.nn as nn
 
 from . import ops
 from .arena import ParamArena, rp8
+from .base import GccModelMixin, capturing, dist_on
 from .nets import (ConvLayer, MaskNLayerDiscriminator, MobileResnetGenerator, NLayerDiscriminator, UnetGenertor,
                    unet_level_prefixes)
 from .ops import GAN_MODES
@@ -39,14 +39,19 @@ class _ArenaOptimizer:
         self.arena.zero_grad()
 
     def step(self):
-        self.arena.set_lr(self.param_groups[0]["lr"])
+        if not capturing():
+            self.arena.set_lr(self.param_groups[0]["lr"])
         _allreduce_grads(self.arena)
         self.arena.step()
 
 
-def _dist_on():
-    return torch.distributed.is_available() and torch.distributed.is_initialized() and \
-        torch.distributed.get_world_size() > 1
+_dist_on = dist_on
+
+
+def capture_collectives():
+    """Whether a data-parallel iteration is captured as ONE CUDA graph with the NCCL all-reduces as graph nodes
+    (default) or as graph segments with eager collectives in between (GCC_B200_CAPTURE_NCCL=0)."""
+    return os.environ.get("GCC_B200_CAPTURE_NCCL", "1") != "0" and torch.distributed.get_backend() == "nccl"
 
 
 # Set by gcc_b200.graph.GraphedIteration while it captures a data-parallel iteration: the gradient exchange is a
@@ -79,9 +84,37 @@ class _LambdaLR:
         self.optimizer.param_groups[0]["lr"] = self.base * self.fn(self.epoch)
 
 
+class _PlateauLR:
+    """torch.optim.lr_scheduler.ReduceLROnPlateau(mode='min', factor=0.2, threshold=0.01 (relative), patience=5),
+    the reference's 'plateau' policy (utils/util.py:299-300).  ``step(metric)`` needs the monitored value; the
+    reference's update_learning_rate calls ``scheduler.step()`` without one, which raises TypeError upstream too."""
+
+    def __init__(self, optimizer, factor=0.2, threshold=0.01, patience=5, eps=1e-8):
+        self.optimizer, self.factor, self.threshold, self.patience, self.eps = optimizer, factor, threshold, patience, eps
+        self.best, self.bad, self.epoch = float("inf"), 0, 0
+
+    def step(self, *metrics):
+        if not metrics:
+            raise TypeError("step() missing 1 required positional argument: 'metrics'")
+        cur = float(metrics[0])
+        self.epoch += 1
+        if cur < self.best * (1.0 - self.threshold):
+            self.best, self.bad = cur, 0
+        else:
+            self.bad += 1
+        if self.bad > self.patience:
+            g = self.optimizer.param_groups[0]
+            new = g["lr"] * self.factor
+            if g["lr"] - new > self.eps:
+                g["lr"] = new
+            self.bad = 0
+
+
 def get_scheduler(optimizer, opt):
-    """utils/util.py:288-303 (linear / step / cosine; plateau needs a metric and is not driven by the step)."""
+    """utils/util.py:288-303 (linear / step / plateau / cosine)."""
     import math
+    if opt.lr_policy == "plateau":
+        return _PlateauLR(optimizer)
     if opt.lr_policy == "linear":
         return _LambdaLR(optimizer, lambda e: 1.0 - max(0, e + opt.epoch_count - opt.n_epochs) /
                          float(opt.n_epochs_decay + 1))
@@ -92,7 +125,7 @@ def get_scheduler(optimizer, opt):
     raise NotImplementedError("learning rate policy [%s] is not implemented" % opt.lr_policy)
 
 
-class Pix2PixModel(nn.Module):
+class Pix2PixModel(GccModelMixin, nn.Module):
 
     def __init__(self, opt, filter_cfgs=None, channel_cfgs=None):
         super().__init__()
@@ -105,9 +138,9 @@ class Pix2PixModel(nn.Module):
         self.loss_names = ["G_GAN", "G_L1", "D_real", "D_fake"]
         self.visual_names = ["real_A", "fake_B", "real_B"]
         self.current_D_arch_diff_loss = 0.0
-        self._ema_state = None
         self.teacher_model = None
         dev = self.device
+        self._base_init()
         self.distill = bool(opt.online_distillation or getattr(opt, "normal_distillation", False))
 
         # ---- generator + optimizer_G arena (transform convs first, as in Pix2Pix.py:403-415)
@@ -174,6 +207,19 @@ class Pix2PixModel(nn.Module):
             self.schedulers.append(self.arch_scheduler)
         self.total_generator_features = {}
         self.total_discriminator_features = {}
+        self.broadcast_parameters()
+
+    def _gcc_arenas(self):
+        return {k: a for k, a in (("G", self.arena_G), ("D", self.arena_D), ("A", self.arena_A)) if a is not None}
+
+    def _gcc_optimizers(self):
+        d = {"G": self.optimizer_G, "D": self.optimizer_D}
+        if self.arena_A is not None:
+            d["arch"] = self.optimizer_arch
+        return d
+
+    def _gcc_nets(self):
+        return {"netG": self.netG, "netD": self.netD}
 
     # ------------------------------------------------------------------ init (util.init_weights)
     def init_net(self):
@@ -207,36 +253,36 @@ class Pix2PixModel(nn.Module):
 
     # ------------------------------------------------------------------ inputs / forward
     def set_input(self, input):
-        """Pix2Pix.py:453-458.  The NHWC bf16 conversions (and the host->device copies) of a batch are done once and
-        shared through the batch dict: the teacher's ``set_input(self.input)`` (Pix2Pix.py:568,587) reuses them."""
+        """Pix2Pix.py:453-458.  The host->device copies and NHWC bf16 conversions of a batch are done once per phase:
+        the teacher's ``set_input(self.input)`` inside optimize_parameters / optimizer_netD_arch (Pix2Pix.py:568,587)
+        takes the student's converted tensors (``_adopt_input``) instead of converting the same batch again.  Nothing
+        is written into the caller's dict and nothing is cached across calls."""
         self.input = input
         AtoB = self.opt.direction == "AtoB"
         ka, kb = ("A", "B") if AtoB else ("B", "A")
-        ta, tb = input[ka], input[kb]
         self.image_paths = [input.get(ka + "_paths"), input.get(kb + "_paths")]
-        key = (ka, ta._version, tb._version, str(self.device))
-        cached = input.get("_gcc_b200") if isinstance(input, dict) else None
-        # a hit needs the SAME live source tensors (weak references: a recycled address or id cannot alias) at the
-        # same version (in-place refills of static input buffers bump it)
-        if cached is not None and cached[0] == key and cached[1]() is ta and cached[2]() is tb:
-            A, B, a_nhwc, b_nhwc, real_AB = cached[3]
-        else:
-            A = ta.to(self.device, non_blocking=True)
-            B = tb.to(self.device, non_blocking=True)
-            a_nhwc, b_nhwc = ops.to_nhwc(A), ops.to_nhwc(B)
-            real_AB = ops.CatFn.apply(a_nhwc, b_nhwc, 3, 3)
-            if isinstance(input, dict):
-                input["_gcc_b200"] = (key, weakref.ref(ta), weakref.ref(tb), (A, B, a_nhwc, b_nhwc, real_AB))
+        A = input[ka].to(self.device, non_blocking=True)
+        B = input[kb].to(self.device, non_blocking=True)
+        a_nhwc, b_nhwc = ops.to_nhwc(A), ops.to_nhwc(B)
+        real_AB = ops.CatFn.apply(a_nhwc, b_nhwc, 3, 3)
         self._A_nchw, self._B_nchw = A, B
         self.real_A_nhwc, self.real_B_nhwc, self.real_AB = a_nhwc, b_nhwc, real_AB
 
+    def _adopt_input(self, other):
+        """Teacher side of ``T.set_input(self.input)``: same batch, same direction -> share the device tensors."""
+        if other.opt.direction != self.opt.direction or other.device != self.device:
+            return self.set_input(other.input)
+        self.input, self.image_paths = other.input, other.image_paths
+        self._A_nchw, self._B_nchw = other._A_nchw, other._B_nchw
+        self.real_A_nhwc, self.real_B_nhwc, self.real_AB = other.real_A_nhwc, other.real_B_nhwc, other.real_AB
+
     @property
     def real_A(self):
-        return self._A_nchw
+        return self._A_nchw.float()      # (a prefetched batch arrives as bf16)
 
     @property
     def real_B(self):
-        return self._B_nchw
+        return self._B_nchw.float()
 
     @property
     def fake_B(self):
@@ -277,14 +323,9 @@ class Pix2PixModel(nn.Module):
         self.loss_D_arch_real = self._gan(pred_real, 0)
         diff = (self.loss_D_arch_fake_real - self.loss_D_arch_fake).abs()
         if isTeacher:
-            # EMA state (Pix2Pix.py:503-508) kept in ONE persistent device scalar so that a captured CUDA graph
-            # carries it across replays; the teacher D is frozen here, so the state is graph-free as upstream.
-            if self._ema_state is None:
-                self._ema_state = diff.detach().clone()
-            else:
-                b = self.opt.ema_beta
-                self._ema_state.copy_(b * diff.detach() + (1.0 - b) * self._ema_state)
-            self.current_D_arch_diff_loss = self._ema_state
+            # EMA state (Pix2Pix.py:503-508): persistent device scalar, beta read from device memory (base.py); the
+            # teacher D is frozen here, so the state is graph-free as upstream.
+            self.current_D_arch_diff_loss = self._ema_update("D", diff)
         else:
             self.current_D_arch_diff_loss = diff
         return self.current_D_arch_diff_loss, torch.sign(self.loss_D_arch_fake_real - self.loss_D_arch_fake)
@@ -358,7 +399,7 @@ class Pix2PixModel(nn.Module):
         ops.zero_pool.reset()
         if self.opt.online_distillation:
             T = self.teacher_model
-            T.set_input(self.input)
+            T._adopt_input(self)
             T.optimize_parameters()
             feats = [f.detach() for f, _ in (T.g_taps + T.d_taps)]
             chans = [c for _, c in (T.g_taps + T.d_taps)]
@@ -379,7 +420,7 @@ class Pix2PixModel(nn.Module):
     def optimizer_netD_arch(self):
         ops.zero_pool.reset()
         self.forward()
-        self.teacher_model.set_input(self.input)
+        self.teacher_model._adopt_input(self)
         self.teacher_model.forward()
         self.set_requires_grad(self.netD, True)
         self.set_netD_weight_grad(False)
@@ -472,13 +513,16 @@ class Pix2PixModel(nn.Module):
         ckpt = {"G": self.netG.state_dict(), "D": self.netD.state_dict(), "epoch": epoch,
                 "cfg": (self.filter_cfgs, self.channel_cfgs), "fid": fid}
         path = os.path.join(save_dir, "model_best_%s.pth" % direction if isbest else "model_%d.pth" % epoch)
-        torch.save(ckpt, path)
+        torch.save(self._ckpt_add_resume(ckpt), path)
 
-    def load_models(self, load_path, load_discriminator=True):
-        ckpt = torch.load(load_path, map_location=self.device)
+    def load_models(self, load_path, load_discriminator=True, resume=None):
+        """`resume`: None = continue training exactly (optimizer moments, counters, EMA, teacher) when the file carries
+        the `gcc_b200` entry and the discriminator is loaded too; False = weights only, as the reference."""
+        ckpt = torch.load(load_path, map_location=self.device, weights_only=False)
         self.netG.load_state_dict(ckpt["G"])
         if load_discriminator:
             self.netD.load_state_dict(ckpt["D"])
+        self._ckpt_load_resume(ckpt, load_discriminator, resume)
         print("loading the model from %s" % load_path)
         return ckpt["fid"], float("inf")
 
@@ -486,7 +530,7 @@ class Pix2PixModel(nn.Module):
     def prune(self, threshold, lottery_path=None):
         from . import prune as P
         if self.opt.backbone == "resnet":
-            cfgs = (P.resnet_prune_cfg(self.netG.state_dict(), threshold), None)
+            cfgs = (P.resnet_prune_cfg(self.netG.state_dict(), threshold, P.convt_names(self.netG)), None)
         elif self.opt.scale_prune:
             cfgs = P.unet_scale_prune_cfg(self.netG.state_dict(), self.opt.ngf, threshold)
         elif self.opt.norm_prune:
@@ -501,7 +545,7 @@ class Pix2PixModel(nn.Module):
 
     def max_min_conv_norm(self):
         from . import prune as P
-        return P.max_min_conv_norm(self.netG.state_dict(), self.opt.backbone)
+        return P.max_min_conv_norm(self.netG.state_dict(), self.opt.backbone, P.convt_names(self.netG))
 
 
 def build_teacher(model, opt):

@@ -87,7 +87,16 @@ _RES_UNPRUNABLE = ["model.26"] + ["model.%d.conv_block.%d.conv.0" % (i, j) for i
 _RES_RESIDUAL = ["model.7"] + ["model.%d.conv_block.6.conv.2" % i for i in range(10, 19)]
 
 
-def resnet_prune_cfg(sd, threshold):
+_RES_CONVT = ("model.19", "model.22")     # the two ConvTranspose2d of a full 9-block MobileResNet generator
+
+
+def convt_names(net):
+    """Names of a net's transposed convs by layer KIND (the reference tests isinstance(m, nn.ConvTranspose2d),
+    Pix2Pix.py:791,936): in a generator whose blocks were dropped by an earlier pruning the module indices shift."""
+    return tuple(l.tname for l in getattr(net, "_layers", []) if getattr(l, "kind", None) == "convT")
+
+
+def resnet_prune_cfg(sd, threshold, convt=_RES_CONVT):
     sd = _cpu(sd)
     alive = None
     for n in _RES_RESIDUAL:
@@ -103,7 +112,7 @@ def resnet_prune_cfg(sd, threshold):
         if name in _RES_RESIDUAL:
             cfg.append(int(alive.sum()))
         else:
-            cfg.append(int((_l1(v, name in ("model.19", "model.22")) > threshold).sum()))
+            cfg.append(int((_l1(v, name in convt) > threshold).sum()))
     return cfg
 
 
@@ -122,7 +131,7 @@ def unet_max_min_bn_scale(sd):
     return min(pr_max, un_max), lo
 
 
-def max_min_conv_norm(sd, backbone):
+def max_min_conv_norm(sd, backbone, convt=_RES_CONVT):
     sd = _cpu(sd)
     pre = unet_level_prefixes()
     prunable = {pre[5] + ".1", pre[6] + ".1", pre[7] + ".1", pre[7] + ".3", pre[6] + ".5", pre[5] + ".5"}
@@ -134,7 +143,7 @@ def max_min_conv_norm(sd, backbone):
         if name in _RES_UNPRUNABLE:
             continue
         if backbone == "resnet":
-            tr = name in ("model.19", "model.22")
+            tr = name in convt
         else:
             tr = dict(_unet_conv_order()).get(name, False)
         nrm = _l1(v, tr)

@@ -21,7 +21,8 @@ from . import ops
 from .arena import ParamArena, rp8
 from .nets import ConvLayer, NormLayer, _Tree
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, GAN_MODES, _check, _st, call, conv_out_hw
-from .pix2pix import _allreduce_grads
+from .base import GccModelMixin, capturing
+from .pix2pix import _allreduce_grads, get_scheduler
 from .srgan import _merge, _SRNet
 
 LRELU = 0.1
@@ -384,16 +385,20 @@ class _MultiArenaOptimizer:
         for a, _ in self.arenas:
             a.zero_grad()
 
+    def arenas_of(self):
+        return [a for a, _ in self.arenas]
+
     def step(self):
         for a, times in self.arenas:
-            a.set_lr(self.param_groups[0]["lr"])
+            if not capturing():
+                a.set_lr(self.param_groups[0]["lr"])
             _allreduce_grads(a)
             for _ in range(times):
                 a.step()
 
 
 # ------------------------------------------------------------------------------------------------------- model
-class SAGANModel(torch.nn.Module):
+class SAGANModel(GccModelMixin, torch.nn.Module):
     """models/SAGAN.py:279-764 on the B200 kernels."""
 
     def __init__(self, opt, filter_cfgs=None, channel_cfgs=None):
@@ -407,8 +412,8 @@ class SAGANModel(torch.nn.Module):
         self.loss_names = ["G_GAN", "D_real", "D_fake"]
         self.visual_names = ["fake_img", "real_img"]
         self.current_D_arch_diff_loss = 0.0
-        self._ema_state = None
         self.teacher_model = None
+        self._base_init()
         self.generator_extract_layers = ["l2", "attn2"]
         self.discriminator_extract_layers = ["l2", "attn2"]
         self.distill = bool(opt.online_distillation or getattr(opt, "normal_distillation", False))
@@ -444,11 +449,32 @@ class SAGANModel(torch.nn.Module):
             self.netD.finalize()
         self.optimizer_D = _MultiArenaOptimizer([(self.arena_D, 1), (self.arena_Ds, dup_d)], opt.lr * 4, betas)
         self.optimizers = []
+        self.schedulers = []
+        if opt.darts_discriminator and getattr(opt, "arch_lr_step", False):
+            # StepLR(step_size=40, gamma=0.1) over optimizer_arch only (SAGAN.py:348-353, stepped at :548-549)
+            arch_opt = copy.deepcopy(opt)
+            arch_opt.lr_policy, arch_opt.lr_decay_iters = "step", 40
+            self.arch_scheduler = get_scheduler(self.optimizer_arch, arch_opt)
+            self.schedulers.append(self.arch_scheduler)
         self.init_net()
         self.gan_mode = GAN_MODES.get(opt.gan_mode)
         if self.gan_mode is None:
             raise NotImplementedError("gan mode %s not implemented" % opt.gan_mode)
         self.total_generator_features, self.total_discriminator_features = {}, {}
+        self.broadcast_parameters()
+
+    def _gcc_arenas(self):
+        return {k: a for k, a in (("G", self.arena_G), ("Gs", self.arena_Gs), ("D", self.arena_D), ("Ds", self.arena_Ds),
+                                  ("A", self.arena_A)) if a is not None}
+
+    def _gcc_optimizers(self):
+        d = {"G": self.optimizer_G, "D": self.optimizer_D}
+        if self.arena_A is not None:
+            d["arch"] = self.optimizer_arch
+        return d
+
+    def _gcc_nets(self):
+        return {"netG": self.netG, "netD": self.netD}
 
     def _all_arenas(self):
         return [a for a in (self.arena_G, self.arena_Gs, self.arena_D, self.arena_Ds, self.arena_A) if a is not None]
@@ -492,6 +518,14 @@ class SAGANModel(torch.nn.Module):
         self.z_nhwc = ops.to_nhwc(self.z.reshape(self.z.shape[0], self.z.shape[1], 1, 1))
         self.real_img_nhwc = ops.to_nhwc(self._real_nchw)
 
+    def _adopt_input(self, other):
+        """Teacher side of ``T.set_input(self.input)`` (SAGAN.py:500,519): share the converted batch."""
+        if other.device != self.device:
+            return self.set_input(other.input)
+        self.input, self.image_paths = other.input, other.image_paths
+        self.z, self._real_nchw = other.z, other._real_nchw
+        self.z_nhwc, self.real_img_nhwc = other.z_nhwc, other.real_img_nhwc
+
     @property
     def real_img(self):
         return self._real_nchw
@@ -534,12 +568,7 @@ class SAGANModel(torch.nn.Module):
         self.loss_D_arch_real = self._gan(pred_real, 0)
         diff = (self.loss_D_arch_fake_real - self.loss_D_arch_fake).abs()
         if isTeacher:
-            if self._ema_state is None:
-                self._ema_state = diff.detach().clone()
-            else:
-                b = self.opt.ema_beta
-                self._ema_state.copy_(b * diff.detach() + (1.0 - b) * self._ema_state)
-            self.current_D_arch_diff_loss = self._ema_state
+            self.current_D_arch_diff_loss = self._ema_update("D", diff)
         else:
             self.current_D_arch_diff_loss = diff
         return self.current_D_arch_diff_loss, torch.sign(self.loss_D_arch_fake_real - self.loss_D_arch_fake)
@@ -610,7 +639,7 @@ class SAGANModel(torch.nn.Module):
         ops.zero_pool.reset()
         if self.opt.online_distillation:
             T = self.teacher_model
-            T.set_input(self.input)
+            T._adopt_input(self)
             T.optimize_parameters()
             feats = [f.detach() for f, _ in (T.g_taps + T.d_taps)]
             chans = [c for _, c in (T.g_taps + T.d_taps)]
@@ -631,7 +660,7 @@ class SAGANModel(torch.nn.Module):
     def optimizer_netD_arch(self):
         ops.zero_pool.reset()
         self.forward()
-        self.teacher_model.set_input(self.input)
+        self.teacher_model._adopt_input(self)
         self.teacher_model.forward()
         self.set_requires_grad(self.netD, True)
         self.set_netD_weight_grad(False)
@@ -650,6 +679,8 @@ class SAGANModel(torch.nn.Module):
         self.opt.ema_beta = 1.0 - epoch / (self.opt.n_epochs + self.opt.n_epochs_decay)
 
     def update_learning_rate(self, epoch):
+        for sch in self.schedulers:
+            sch.step()
         self.adaptive_ema_beta(epoch)
         print("learning rate = %.7f" % self.optimizer_G.param_groups[0]["lr"])
 
@@ -724,13 +755,16 @@ class SAGANModel(torch.nn.Module):
         ckpt = {"G": self._pop_ops(self.netG.state_dict()), "D": self._pop_ops(self.netD.state_dict()), "epoch": epoch,
                 "cfg": (self.filter_cfgs, self.channel_cfgs), "fid": fid}
         path = os.path.join(save_dir, "model_best_%s.pth" % direction if isbest else "model_%d.pth" % epoch)
-        torch.save(ckpt, path)
+        torch.save(self._ckpt_add_resume(ckpt), path)
 
-    def load_models(self, load_path, load_discriminator=True):
-        ckpt = torch.load(load_path, map_location=self.device)
+    def load_models(self, load_path, load_discriminator=True, resume=None):
+        """`resume`: None = continue training exactly (optimizer moments, counters, EMA, teacher) when the file carries
+        the `gcc_b200` entry and the discriminator is loaded too; False = weights only, as the reference."""
+        ckpt = torch.load(load_path, map_location=self.device, weights_only=False)
         self.netG.load_state_dict(self._pop_ops(ckpt["G"]))
         if load_discriminator:
             self.netD.load_state_dict(self._pop_ops(ckpt["D"]))
+        self._ckpt_load_resume(ckpt, load_discriminator, resume)
         print("loading the model from %s" % load_path)
         return ckpt["fid"], float("inf")
 

@@ -20,6 +20,7 @@ from . import ops
 from .arena import ParamArena, rp8
 from .nets import ConvLayer, NormLayer, _Net, _Tree
 from .ops import ACT_LRELU, ACT_NONE, ACT_TANH, GAN_MODES, _check, _st, call
+from .base import GccModelMixin
 from .pix2pix import _ArenaOptimizer, get_scheduler
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
@@ -385,7 +386,7 @@ class TruncatedVGG19(_SRNet):
 
 
 # ------------------------------------------------------------------------------------------------------- model
-class SRGAN(torch.nn.Module):
+class SRGAN(GccModelMixin, torch.nn.Module):
     """models/SRGAN.py:296-842 on the B200 kernels."""
 
     def __init__(self, opt, filter_cfgs=None, channel_cfgs=None):
@@ -398,8 +399,8 @@ class SRGAN(torch.nn.Module):
         self.filter_cfgs, self.channel_cfgs = filter_cfgs, channel_cfgs
         self.current_epoch = 0
         self.current_D_arch_diff_loss = 0.0
-        self._ema_state = None
         self.teacher_model = None
+        self._base_init()
         self.visual_names = ["real_lr", "fake_hr", "real_hr"]
         generator_only = bool(getattr(opt, "generator_only", False))
         self.loss_names = ["content"] if generator_only else ["G_GAN", "D_real", "D_fake", "content", "perceptual"]
@@ -454,6 +455,20 @@ class SRGAN(torch.nn.Module):
         self.schedulers = [get_scheduler(o, opt) for o in self.optimizers]
         self._consts = _imagenet_consts(dev)
         self.total_generator_features, self.total_discriminator_features = {}, {}
+        self.broadcast_parameters()
+
+    def _gcc_arenas(self):
+        return {k: a for k, a in (("G", self.arena_G), ("P", self.arena_P), ("D", self.arena_D), ("A", self.arena_A))
+                if a is not None}
+
+    def _gcc_optimizers(self):
+        d = {"G": self.optimizer_G, "D": self.optimizer_D}
+        if self.arena_A is not None:
+            d["arch"] = self.optimizer_arch
+        return d
+
+    def _gcc_nets(self):
+        return {"netG": self.netG, "netD": self.netD}
 
     # ------------------------------------------------------------------ init (util.init_weights + nn.PReLU default)
     def _arenas(self):
@@ -505,6 +520,17 @@ class SRGAN(torch.nn.Module):
         self.image_paths = [input.get("lr_names"), input.get("hr_names")]
         self.real_lr_nhwc = ops.to_nhwc(self._lr_nchw)
         self.real_hr_nhwc = ops.to_nhwc(self._hr_nchw)
+        self._hr_raw_nhwc = self.real_hr_nhwc
+
+    def _adopt_input(self, other):
+        """Teacher side of ``T.set_input(self.input)`` (SRGAN.py:487,508): share the converted batch (the hr image
+        BEFORE the student's in-place re-binding to its imagenet-normalised version)."""
+        if other.device != self.device:
+            return self.set_input(other.input)
+        self.input, self.image_paths = other.input, other.image_paths
+        self._lr_nchw, self._hr_nchw = other._lr_nchw, other._hr_nchw
+        self.real_lr_nhwc = other.real_lr_nhwc
+        self.real_hr_nhwc = self._hr_raw_nhwc = other._hr_raw_nhwc
 
     @property
     def real_lr(self):
@@ -554,12 +580,7 @@ class SRGAN(torch.nn.Module):
         self.loss_D_arch_real = self._gan(pred_real, 0)
         diff = (self.loss_D_arch_fake_real - self.loss_D_arch_fake).abs()
         if isTeacher:
-            if self._ema_state is None:
-                self._ema_state = diff.detach().clone()
-            else:
-                b = self.opt.ema_beta
-                self._ema_state.copy_(b * diff.detach() + (1.0 - b) * self._ema_state)
-            self.current_D_arch_diff_loss = self._ema_state
+            self.current_D_arch_diff_loss = self._ema_update("D", diff)
         else:
             self.current_D_arch_diff_loss = diff
         return self.current_D_arch_diff_loss, torch.sign(self.loss_D_arch_fake_real - self.loss_D_arch_fake)
@@ -621,7 +642,7 @@ class SRGAN(torch.nn.Module):
         ops.zero_pool.reset()
         if self.opt.online_distillation:
             T = self.teacher_model
-            T.set_input(self.input)
+            T._adopt_input(self)
             T.optimize_parameters()
             feats = [f.detach() for f, _ in (T.g_taps + T.d_taps)]
             chans = [c for _, c in (T.g_taps + T.d_taps)]
@@ -644,7 +665,7 @@ class SRGAN(torch.nn.Module):
     def optimizer_netD_arch(self):
         ops.zero_pool.reset()
         self.forward()
-        self.teacher_model.set_input(self.input)
+        self.teacher_model._adopt_input(self)
         self.teacher_model.forward()
         self.set_requires_grad(self.netD, True)
         self.set_netD_weight_grad(False)
@@ -766,13 +787,16 @@ class SRGAN(torch.nn.Module):
         ckpt = {"G": self._pop_ops(self.netG.state_dict()), "D": self._pop_ops(self.netD.state_dict()), "epoch": epoch,
                 "cfg": (self.filter_cfgs, self.channel_cfgs), "psnr": fid}
         path = os.path.join(save_dir, "model_best_%s.pth" % direction if isbest else "model_%d.pth" % epoch)
-        torch.save(ckpt, path)
+        torch.save(self._ckpt_add_resume(ckpt), path)
 
-    def load_models(self, load_path, load_discriminator=True):
-        ckpt = torch.load(load_path, map_location=self.device)
+    def load_models(self, load_path, load_discriminator=True, resume=None):
+        """`resume`: None = continue training exactly (optimizer moments, counters, EMA, teacher) when the file carries
+        the `gcc_b200` entry and the discriminator is loaded too; False = weights only, as the reference."""
+        ckpt = torch.load(load_path, map_location=self.device, weights_only=False)
         self.netG.load_state_dict(self._pop_ops(ckpt["G"]))
         if load_discriminator:
             self.netD.load_state_dict(self._pop_ops(ckpt["D"]))
+        self._ckpt_load_resume(ckpt, load_discriminator, resume)
         print("loading the model from %s" % load_path)
         return ckpt["psnr"], float("inf")
 

@@ -50,14 +50,6 @@ int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w
 int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void* q, int H, int W, int Cq,
                         float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched, int accumulate,
                         float scale, void* stream);
-/* CUDA-core cross-checks with identical signatures (tests only). */
-int gcc_conv_direct_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
-                         const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
-                         int KW, int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
-                         long long ws_elems, float* stats, int stats_ld, void* stream);
-int gcc_wgrad_direct_bf16(const void* p, int N, int OH, int OW, int Cp, const void* q, int H, int W, int Cq,
-                          float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched, int accumulate,
-                          float scale, void* stream);
 void gcc_debug_force_block_n(int bn);
 void gcc_debug_set_flags(int f); /* timing experiments: bit0 skip conv epilogue stores, bit1 skip TMEM loads */
 
@@ -75,19 +67,25 @@ int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, int per_samp
 int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, int Cp, int C, int per_sample, const float* sums,
                         const float* gamma, const float* beta, const float* alpha, float thr, float eps,
                         float* running_mean, float* running_var, float momentum, int act, float slope,
-                        int gate_after, void* y2, int y2_Cp, int y2_coff, int act2, void* stream);
+                        int gate_after, void* y2, int y2_Cp, int y2_coff, int act2, long long stat_count,
+                        void* stream);
 int gcc_norm_apply_eval_bf16(const void* x, void* y, int N, long long HW, int Cp, int C, const float* running_mean,
                              const float* running_var, const float* gamma, const float* beta, const float* alpha,
                              float thr, float eps, int act, float slope, void* y2, int y2_Cp, int y2_coff, int act2,
                              void* stream);
 /* backward of the block: dx (bf16, may be NULL), dgamma/dbeta/dalpha (fp32 [C], may be NULL; dalpha is
  * the straight-through gate gradient sum dg*z; parameter gradients ACCUMULATE into their buffers).
- * dy / dy2 are gradient windows of y / y2. */
+ * dy / dy2 are gradient windows of y / y2.
+ * Synchronised batch norm (data parallel): `stat_count` > 0 is the number of pixels behind `sums` / `red`
+ * when the caller has all-reduced them over the ranks (0 = this device's N*HW); `phase` 1 runs only the reduction
+ * (red = this device's sum dg, sum dg*xhat), the caller all-reduces a copy, and `phase` 2 runs only the apply pass with
+ * the global `red` for dx and `red_param` (this device's sums, NULL = red) for dgamma / dbeta / dalpha; phase 0 = both
+ * (the same argument `stat_count` exists on gcc_norm_apply_bf16). */
 int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int C, int per_sample, const float* sums,
                       const float* gamma, const float* beta, const float* alpha, float thr, float eps, int act,
                       float slope, int gate_after, const void* dy, int dy_Cp, int dy_coff, const void* dy2, int dy2_Cp,
                       int dy2_coff, int act2, float* red, void* dx, float* dgamma, float* dbeta, float* dalpha,
-                      void* stream);
+                      long long stat_count, int phase, const float* red_param, void* stream);
 
 /* ---- elementwise / layout (elementwise.cu) ---- */
 /* set_input boundary (models/Pix2Pix.py:453-458): NCHW fp32 <-> NHWC bf16 channel windows */
@@ -139,6 +137,14 @@ int gcc_unpad_wgrad_c8(const float* tmp, float* g, int R, int C, void* stream);
 int gcc_fold_k4s1_c8(const void* ycol, int Ccol, int C, const float* bias, void* y, int N, int H, int W, void* stream);
 int gcc_unfold_k4s1_c8(const void* dy, void* dcol, int N, int H, int W, void* stream);
 int gcc_unpad_wgrad_rows(const float* tmp, float* g, int C, int K, void* stream);
+
+/* ImagePool.query (utils/image_pool.py:22-54) with device-resident state, so a captured CUDA graph draws fresh
+ * decisions on every replay.  images: bf16 [b][elems_per_image] (the generated batch), pool: bf16
+ * [pool_size][elems_per_image], state_dev: int64 [2] = {images stored so far, random counter} (zero-initialised by the
+ * caller, advanced here), dec_ws: int32 [2 b] scratch, out: bf16 [b][elems_per_image] = the images the discriminator
+ * sees.  Same policy as the reference: fill the pool first, then with probability 1/2 swap with a random slot. */
+int gcc_image_pool_query_bf16(const void* images, void* pool, long long* state_dev, int* dec_ws, void* out, int b,
+                              long long elems_per_image, int pool_size, void* stream);
 
 /* ---- loss reductions (loss.cu) ---- */
 /* GANLoss (models/GANLoss.py:38-59). mode: 0 hinge, 1 lsgan, 2 vanilla, 3 wgangp.

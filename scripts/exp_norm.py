@@ -27,9 +27,9 @@ timeit(lambda: y.copy_(x), "torch copy bf16 (r+w)", 2 * nbytes)
 timeit(lambda: x.float().sum(), "torch sum (read)", nbytes)
 timeit(lambda: _lib.call("gcc_norm_stats_bf16", x.data_ptr(), N, H * W, C, 0, sums.data_ptr(), st), "norm_stats (read)", nbytes)
 timeit(lambda: _lib.call("gcc_norm_apply_bf16", x.data_ptr(), y.data_ptr(), N, H * W, C, C, 0, sums.data_ptr(), gamma.data_ptr(),
-                         beta.data_ptr(), None, 0.5, 1e-5, rm.data_ptr(), rv.data_ptr(), 0.1, 1, 0.2, 0, None, 0, 0, 0, st),
+                         beta.data_ptr(), None, 0.5, 1e-5, rm.data_ptr(), rv.data_ptr(), 0.1, 1, 0.2, 0, None, 0, 0, 0, 0, st),
        "norm_apply bn+lrelu (r+w)", 2 * nbytes)
 timeit(lambda: _lib.call("gcc_norm_bwd_bf16", x.data_ptr(), N, H * W, C, C, 0, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                          None, 0.5, 1e-5, 1, 0.2, 0, dy.data_ptr(), C, 0, None, 0, 0, 0, red.data_ptr(), dx.data_ptr(), None, None,
-                         None, st), "norm_bwd reduce+apply (2r+2r+w)", 5 * nbytes)
+                         None, 0, 0, None, st), "norm_bwd reduce+apply (2r+2r+w)", 5 * nbytes)
 timeit(lambda: _lib.call("gcc_act_fwd_bf16", x.data_ptr(), y.data_ptr(), x.numel(), 1, 0.2, st), "act_fwd lrelu (r+w)", 2 * nbytes)

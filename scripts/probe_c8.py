@@ -3,6 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gcc_b200 import _lib
+import _check
 L = _lib.lib(); st = torch.cuda.current_stream().cuda_stream
 torch.manual_seed(0)
 def conv(fn, x, w, b, R, flags):
@@ -10,7 +11,7 @@ def conv(fn, x, w, b, R, flags):
     rp = (R + 7) // 8 * 8
     y = torch.zeros(n, h // 2, wd // 2, rp, device="cuda", dtype=torch.bfloat16)
     L.gcc_debug_set_flags(flags)
-    _lib.call(fn, x.data_ptr(), n, h, wd, 8, w.data_ptr(), R, 16, 8, b.data_ptr(), y.data_ptr(), h // 2, wd // 2, rp, 0, 0,
+    _check.call(fn, x.data_ptr(), n, h, wd, 8, w.data_ptr(), R, 16, 8, b.data_ptr(), y.data_ptr(), h // 2, wd // 2, rp, 0, 0,
               4, 4, 2, 1, 1, 0.2, 0, None, 0, None, 0, st)
     torch.cuda.synchronize(); L.gcc_debug_set_flags(0)
     return y.float()
@@ -18,7 +19,7 @@ def wgrad(fn, dy, x, R, flags):
     n, h, wd, _ = x.shape
     dw = torch.zeros(R, 16, 8, device="cuda")
     L.gcc_debug_set_flags(flags)
-    _lib.call(fn, dy.data_ptr(), n, h // 2, wd // 2, dy.shape[3], x.data_ptr(), h, wd, 8, dw.data_ptr(), R, 8, 4, 4, 2, 1,
+    _check.call(fn, dy.data_ptr(), n, h // 2, wd // 2, dy.shape[3], x.data_ptr(), h, wd, 8, dw.data_ptr(), R, 8, 4, 4, 2, 1,
               0, 0, 1.0, st)
     torch.cuda.synchronize(); L.gcc_debug_set_flags(0)
     return dw

@@ -12,6 +12,9 @@ import torch.nn.functional as F
 
 from gcc_b200 import _lib
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _check  # noqa: E402
+
 dev = "cuda"
 
 
@@ -42,7 +45,7 @@ def run_conv(fn, x, w, bias, OH, OW, R, transposed, KH, KW, stride, pad, act=0, 
     Rr, T, Cw = w.shape
     cy = cy or rp8(R)
     y = torch.full((N, OH, OW, cy), 7.0, dtype=torch.bfloat16, device=dev)
-    _lib.call(fn, x.data_ptr(), N, H, W, Cx, w.data_ptr(), R, T, Cw, _lib.ptr(bias), y.data_ptr(), OH, OW, cy, coff,
+    _check.call(fn, x.data_ptr(), N, H, W, Cx, w.data_ptr(), R, T, Cw, _lib.ptr(bias), y.data_ptr(), OH, OW, cy, coff,
               transposed, KH, KW, stride, pad, act, slope, 0, None, 0, None, 0, _lib.current_stream())
     torch.cuda.synchronize()
     return y
@@ -120,7 +123,7 @@ def wgrad_case(name, N, H, W, Cin, Cout, k, stride, pad, batched=0, seed=0):
     outs = {}
     for fn in ("gcc_wgrad_direct_bf16", "gcc_wgrad_gemm_bf16"):
         dw = torch.full(shape, 3.0, dtype=torch.float32, device=dev)
-        _lib.call(fn, dyb.data_ptr(), N, OH, OW, dyb.shape[-1], xb.data_ptr(), H, W, xb.shape[-1], dw.data_ptr(),
+        _check.call(fn, dyb.data_ptr(), N, OH, OW, dyb.shape[-1], xb.data_ptr(), H, W, xb.shape[-1], dw.data_ptr(),
                   Cout, Cin, k, k, stride, pad, batched, 0, 1.0, _lib.current_stream())
         torch.cuda.synchronize()
         outs[fn] = dw

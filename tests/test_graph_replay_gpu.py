@@ -1,0 +1,199 @@
+"""The path bench.py times is the CUDA-graph replay (gcc_b200.graph.GraphedIteration); these tests pin it to the eager
+call sequence of train.py:144-151:
+
+  * pix2pix: W warm-up + 3 replays == W + 3 eager iterations on a twin model, with `update_learning_rate(epoch)` (a
+    10x LR drop) and a changed teacher `opt.ema_beta` BETWEEN iterations -- both must reach the replayed graph
+    (device-resident scalars, gcc_b200/base.py); BatchNorm `num_batches_tracked` must keep counting.
+  * resume: save -> load into a freshly built pair -> the next iteration is the same (optimizer moments, step
+    counters, transform convs, EMA, teacher included).
+  * CycleGAN / SRGAN / SAGAN: capture + replay equals eager too (CycleGAN with the device-resident image pool).
+
+The same kernels run in both modes, so the only differences are fp32 atomics ordering (BatchNorm statistics, split-K,
+weight gradients); stated bounds: losses 1e-2 relative (+2e-3 abs), last-iteration weight update dW rel-L2 5e-2.
+"""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from gcc_b200 import _lib
+    _lib.call("gcc_check_device")
+    return True
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+TINY = {"pix2pix": dict(ngf=8, teacher_ngf=16, ndf=16, teacher_ndf=16),
+        "cyclegan": dict(ngf=8, teacher_ngf=16, ndf=16, teacher_ndf=16),
+        "srgan": dict(ngf=8, teacher_ngf=16, ndf=8, teacher_ndf=8),
+        "sagan": dict(ngf=16, teacher_ngf=32, ndf=16, teacher_ndf=32)}
+SIZE = {"pix2pix": 256, "cyclegan": 64, "srgan": 48, "sagan": None}
+
+
+def _pair(name, **extra):
+    from gcc_b200 import factory
+    kw = dict(TINY[name])
+    kw.update(extra)
+    argv = ["--no_dropout"] if name in ("pix2pix",) else []
+    opt = factory.make_opt(name, 0, argv, **kw)
+    return factory.build_pair(opt)
+
+
+def _twin(name, **extra):
+    """Two (student, teacher) pairs with identical state."""
+    a, at = _pair(name, **extra)
+    b, bt = _pair(name, **extra)
+    b.load_resume_state(a.resume_state())
+    return (a, at), (b, bt)
+
+
+def _batches(name, n, b=2):
+    from gcc_b200 import factory
+    g = torch.Generator().manual_seed(7)
+    return [(factory.synthetic_batch(name, b, SIZE[name], g), factory.synthetic_batch(name, b, SIZE[name], g))
+            for _ in range(n)]
+
+
+def _weights(model):
+    return torch.cat([a.P.detach().float().flatten() for m in (model, model.teacher_model)
+                      for a in m._gcc_arenas().values()]).cpu()
+
+
+def _close_losses(x, y, tag):
+    assert set(x) == set(y)
+    for k in x:
+        assert abs(x[k] - y[k]) <= 1e-2 * abs(y[k]) + 2e-3, (tag, k, x[k], y[k])
+
+
+def test_pix2pix_replay_equals_eager_with_lr_and_ema_changes(cuda):
+    from gcc_b200 import factory
+    from gcc_b200.graph import GraphedIteration
+    # linear policy with n_epochs 1 / n_epochs_decay 1: lr x1, x0.5, x0 ... use 'step' for a clean 10x drop per epoch
+    extra = dict(lr_policy="step", lr_decay_iters=1)
+    (E, ET), (G, GT) = _twin("pix2pix", **extra)
+    data = _batches("pix2pix", 4)
+    W = 2
+    # eager twin: warm-up on batch 0 (exactly what capture() runs), then 3 iterations
+    for _ in range(W):
+        factory.run_iteration(E, *data[0])
+    gi = GraphedIteration(G).capture(data[0][0], data[0][1], warmup=W)
+    torch.cuda.synchronize()
+    assert _rel(_weights(G), _weights(E)) < 1e-3
+    lr0 = E.optimizer_G.param_groups[0]["lr"]
+    for it in range(3):
+        if it == 1:          # end of an "epoch": 10x LR drop for G / D, and a new EMA factor on the teacher
+            for m in (E, G):
+                m.update_learning_rate(1)
+                m.teacher_model.opt.ema_beta = 0.25
+            assert abs(E.optimizer_G.param_groups[0]["lr"] - 0.1 * lr0) < 1e-12
+        w_e, w_g = _weights(E), _weights(G)
+        factory.run_iteration(E, *data[1 + it])
+        gi.run(*data[1 + it])
+        torch.cuda.synchronize()
+        le, lg = E.get_current_losses(), G.get_current_losses()
+        _close_losses(lg, le, "iteration %d" % it)
+        d_e, d_g = _weights(E) - w_e, _weights(G) - w_g
+        # a stale learning rate in the graph would make this 10x (rel ~ 9); a stale ema_beta shows in the loss above
+        assert _rel(d_g, d_e) < 5e-2, (it, _rel(d_g, d_e), float(d_e.norm()), float(d_g.norm()))
+    ema_e = float(ET._ema_states["D"])
+    ema_g = float(GT._ema_states["D"])
+    assert abs(ema_e - ema_g) <= 1e-2 * abs(ema_e) + 1e-4
+    assert abs(float(G.arena_G.hyper[0]) - 0.1 * lr0) < 1e-9      # the device copy follows the scheduler
+    # BatchNorm counters keep counting under replay
+    se, sg = E.netD.state_dict(), G.netD.state_dict()
+    for k in se:
+        if k.endswith("num_batches_tracked"):
+            assert int(se[k]) == int(sg[k]) and int(sg[k]) > 0, k
+    ste, stg = ET.netG.state_dict(), GT.netG.state_dict()
+    for k in ste:
+        if k.endswith("num_batches_tracked"):
+            assert int(ste[k]) == int(stg[k]), k
+        elif "running" in k:
+            assert _rel(stg[k], ste[k]) < 1e-2, k
+
+
+def test_pix2pix_resume_next_iteration_identical(cuda, tmp_path):
+    """Checkpoint -> fresh pair -> same next iteration (reference format + the `gcc_b200` resume entry)."""
+    from gcc_b200 import factory
+    A, AT = _pair("pix2pix")
+    data = _batches("pix2pix", 3)
+    for i in range(2):
+        factory.run_iteration(A, *data[i])
+    A.update_learning_rate(1)
+    A.save_models(2, str(tmp_path))
+    ck = torch.load(str(tmp_path / "model_2.pth"), map_location="cpu", weights_only=False)
+    assert {"G", "D", "epoch", "cfg", "fid"} <= set(ck) and "gcc_b200" in ck     # reference keys + ours
+    B, BT = _pair("pix2pix")
+    B.load_models(str(tmp_path / "model_2.pth"))
+    assert _rel(_weights(B), _weights(A)) == 0.0
+    assert B.optimizer_G.param_groups[0]["lr"] == A.optimizer_G.param_groups[0]["lr"]
+    assert int(B.arena_G.hyper.view(torch.int32)[4]) == int(A.arena_G.hyper.view(torch.int32)[4]) == 2
+    w0 = _weights(A)
+    factory.run_iteration(A, *data[2])
+    factory.run_iteration(B, *data[2])
+    torch.cuda.synchronize()
+    _close_losses(B.get_current_losses(), A.get_current_losses(), "resumed")
+    assert _rel(_weights(B) - w0, _weights(A) - w0) < 5e-2
+
+
+@pytest.mark.parametrize("name", ["cyclegan", "srgan", "sagan"])
+def test_other_models_replay_equals_eager(cuda, name):
+    from gcc_b200 import factory
+    from gcc_b200.graph import GraphedIteration
+    (E, ET), (G, GT) = _twin(name)
+    for m in (E, ET, G, GT):
+        if hasattr(m, "use_device_pools"):
+            m.use_device_pools()
+    data = _batches(name, 3)
+    W = 1
+    for _ in range(W):
+        factory.run_iteration(E, *data[0])
+    gi = GraphedIteration(G).capture(data[0][0], data[0][1], warmup=W)
+    for it in range(2):
+        w_e, w_g = _weights(E), _weights(G)
+        factory.run_iteration(E, *data[1 + it])
+        gi.run(*data[1 + it])
+        torch.cuda.synchronize()
+        le, lg = E.get_current_losses(), G.get_current_losses()
+        for k, v in lg.items():
+            assert v == v and abs(v) < 1e30, (k, v)
+        _close_losses(lg, le, "%s iteration %d" % (name, it))
+        d_e, d_g = _weights(E) - w_e, _weights(G) - w_g
+        assert _rel(d_g, d_e) < 8e-2, (name, it, _rel(d_g, d_e))
+
+
+def test_device_image_pool_policy(cuda):
+    """Fill first, then out[i] is either the image itself or a stored one, and every stored image is one that was
+    generated earlier (utils/image_pool.py:22-54)."""
+    from gcc_b200.cyclegan import DeviceImagePool
+    pool = DeviceImagePool(6, seed=3)
+    seen = set()
+    swaps = 0
+    for step in range(40):
+        imgs = torch.full((4, 2, 2, 8), 0.0, device="cuda", dtype=torch.bfloat16)
+        ids = [step * 4 + i + 1 for i in range(4)]
+        for i, v in enumerate(ids):
+            imgs[i] = float(v % 251)
+        out = pool.query(imgs)
+        torch.cuda.synchronize()
+        got = [int(out[i, 0, 0, 0]) for i in range(4)]
+        seen.update(v % 251 for v in ids)
+        for i, gv in enumerate(got):
+            if step * 4 + i < 6:
+                assert gv == ids[i] % 251            # pool not full yet: returns the image itself
+            assert gv in seen
+            swaps += gv != ids[i] % 251
+        stored = set(int(v) for v in pool.buf[:, 0, 0, 0].float().cpu().tolist())
+        assert stored <= seen | {0}
+    assert int(pool.state[0]) == 6
+    assert 40 < swaps < 120      # ~ half of the 154 post-fill queries swap

@@ -82,6 +82,13 @@ CASES = {
                      [8, 13, 30, 61, 64, 59, 40, 64, 77, 109, 128, 109, 57, 27, 13]), 1),
     "resnet_tiny": ("resnet", {"ngf": 8, "teacher_ngf": 16, "ndf": 16, "teacher_ndf": 16},
                     ([8, 16, 29, 21, 29, 17, 29, 30, 29, 11, 29, 25, 29, 32, 29, 9, 29, 27, 29, 19, 29, 13, 7], None), 1),
+    # BASELINE configs[1] at its real widths (the shapes bench.py times: conv_gemm_persistent_kernel<256,4>,
+    # wgrad_gemm_kernel<256,3,2>, split-K at K = 8192 are reached here through the whole step), batch 2:
+    "unet_c2": ("unet", {"ngf": 32, "teacher_ngf": 64, "ndf": 128, "teacher_ndf": 128}, (None, None), 2),
+    # ... and the literal pruned student of SURVEY.md section 7 / 8d (seed-0 scale_prune(1.0) of the ngf-32 U-Net)
+    "unet_c2_pruned": ("unet", {"ngf": 32, "teacher_ngf": 64, "ndf": 128, "teacher_ndf": 128},
+                       ([32, 37, 65, 143, 144, 136, 134, 256, 120, 127, 128, 138, 62, 33, 13],
+                        [32, 37, 65, 143, 144, 136, 134, 256, 254, 263, 272, 281, 127, 70, 45]), 2),
 }
 
 
