@@ -28,11 +28,38 @@ extern unsigned long long g_gcc_launches;  // kernels launched by this library (
 
 void gcc_set_error(const char* file, int line, const char* msg);
 
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute (programmatic
+// dependent launch): the grid may be scheduled while its predecessor in the stream drains; the kernel's first
+// instruction, griddepcontrol.wait, blocks until the predecessor has completed and its memory is visible.  With
+// ~800 launches per GCC iteration the launch latency and the ramp of each kernel overlap the tail of the previous
+// one instead of adding up.  GCC_B200_PDL=0 (read once) launches everything with plain stream order.
+int gcc_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gcc_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const int on = gcc_pdl_enabled();
+  cfg.attrs = on ? attr : nullptr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 typedef __nv_bfloat16 bf16;
 
 namespace gcc {
 
 static constexpr int kNumSMs = 148;
+
+// programmatic dependent launch (see gcc_launch): wait for the predecessor grid, then let the successor be scheduled
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -238,6 +265,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 }  // namespace gcc
+
+// ------------------------------------------------------ host: internal entry points shared between translation units
+int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
+                         const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH, int KW,
+                         int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
+                         long long ws_elems, float* stats, int stats_ld, int f32_out, void* stream);
+extern "C" int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void* q, int H, int W, int Cq,
+                                   float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched,
+                                   int accumulate, float scale, void* stream);
 
 // ------------------------------------------------------ host: tensor maps
 // cuTensorMapEncodeTiled is fetched through the runtime (no -lcuda link dependency).

@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: barrier init, tensor-map prefetch and the TMEM allocation above overlapped the
+  // previous kernel's tail; no global memory has been touched yet
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // The whole producer warp stays converged: lane 0 waits for the slot and arms the barrier, then lanes
@@ -285,6 +289,7 @@ struct ConvGeom2 {
   float* partial;
   long long part_sn, part_sh, part_sw;
   int debug;  // bit0: skip global stores, bit1: skip TMEM loads (timing experiments only)
+  int f32_out;  // 1: the result stays fp32 in `partial` (red.add into the zeroed workspace), no bf16 output
   float* stats;  // optional fp32 [2][stats_ld]: per-output-channel sum / sum of squares of the bf16 outputs
   int stats_ld;
   // 1: "image" mode for 8-channel inputs (first conv of the U-Net / PatchGAN).  One k-block = 8 taps x 8 channels:
@@ -378,6 +383,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: barrier init, tensor-map prefetch and the TMEM allocation above overlapped the
+  // previous kernel's tail; no global memory has been touched yet
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      if (kTmaStore && p.k_splits == 1) {
+      if (kTmaStore && p.k_splits == 1 && !p.f32_out) {
         uint8_t* obuf = out_base + (uint32_t)(tile_iter & 1) * (kUnits * 16384);
         // the store issued two tiles ago read this buffer: wait for it, then tell everybody
         if (et == 0) tma_store_wait_read<1>();
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
-      if (p.k_splits == 1) {
+      if (p.k_splits == 1 && !p.f32_out) {
         // Each thread owns one pixel row; its 32-column chunk (64 B) is staged in warp-private shared memory and
         // written out with 4 lanes per row, so every store instruction covers whole 32-byte sectors (8 rows x
         // 64 contiguous bytes) instead of 32 half-written sectors 1 row apart.
@@ -650,6 +659,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
 __global__ void splitk_finalize_kernel(const float* __restrict__ partial, bf16* __restrict__ out, long long npix, int Rp,
                                        int Cy, int y_coff, int bias_cols, const float* __restrict__ bias, int act,
                                        float slope) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long total = npix * Rp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -733,7 +744,7 @@ static int launch_wgrad_gemm(const GemmGeom& g, dim3 grid, cudaStream_t st) {
     }
     configured[dev] = true;
   }
-  wgrad_gemm_kernel<BLOCK_N, STAGES, MT><<<grid, 192, smem, st>>>(g);
+  gcc_launch(wgrad_gemm_kernel<BLOCK_N, STAGES, MT>, grid, 192, smem, st, g);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -819,18 +830,24 @@ static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
     configured[dev] = true;
   }
   const int grid = g.total_tiles < num_sms() ? g.total_tiles : num_sms();
-  conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS><<<grid, 320, smem, st>>>(g);
+  gcc_launch(conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS>, grid, 320, smem, st, g);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 
 // splitk_ws: optional fp32 workspace of >= N*OH*OW*round8(R) elements; when given, layers with very few pixel
 // tiles and a long contraction split K across CTAs.  NULL disables split-K.
-extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
-                                  const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
-                                  int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
-                                  float* splitk_ws, long long ws_elems, float* stats, int stats_ld, void* stream) {
+// f32_out = 1: no bf16 output; `splitk_ws` (>= N*OH*OW*round8(R) floats, zeroed here) receives the fp32 result with
+// row pitch round8(R) (used by the attention scores, whose softmax wants un-rounded logits).
+int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
+                         const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH, int KW,
+                         int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
+                         long long ws_elems, float* stats, int stats_ld, int f32_out, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (f32_out && (splitk_ws == nullptr || stats != nullptr || bias != nullptr || act != 0)) {
+    gcc_set_error(__FILE__, __LINE__, "conv gemm: fp32 output needs a workspace and excludes bias / activation / statistics");
+    return GCC_ERR_ARG;
+  }
   if (stats != nullptr && (splitk_ws != nullptr || stats_ld < ((R + 7) / 8 * 8))) {
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: fused statistics exclude split-K and need stats_ld >= round8(R)");
     return GCC_ERR_ARG;
@@ -975,11 +992,25 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   g.k_splits = 1;
   const long long out_elems = (long long)N * OH * OW * Rp;
   const int base_tiles = m_total * g.n_tiles;
+  if (f32_out && ws_elems < out_elems) {
+    gcc_set_error(__FILE__, __LINE__, "conv gemm: fp32 output workspace too small");
+    return GCC_ERR_ARG;
+  }
+  g.f32_out = f32_out;
+  if (f32_out) {
+    g.partial = splitk_ws;
+    g.part_sn = (long long)OH * OW * Rp;
+    g.part_sh = (long long)OW * Rp * os;
+    g.part_sw = (long long)Rp * os;
+    if (cudaMemsetAsync(splitk_ws, 0, sizeof(float) * out_elems, st) != cudaSuccess) return GCC_ERR_CUDA;
+  }
   if (splitk_ws != nullptr && ws_elems >= out_elems && base_tiles * 2 <= num_sms() && max_kb >= 8) {
     int ks = num_sms() / base_tiles;
     if (ks > max_kb / 2) ks = max_kb / 2;
     if (ks > 64) ks = 64;
-    if (ks > 1) {
+    if (ks > 1 && f32_out) {
+      g.k_splits = ks;
+    } else if (ks > 1) {
       g.k_splits = ks;
       g.partial = splitk_ws;
       g.part_sn = (long long)OH * OW * Rp;
@@ -999,16 +1030,24 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
   else if (BN == 128) rc = launch_conv_persistent<128, 6, false>(g, st);
   else rc = launch_conv_persistent<256, 4, false>(g, st);
   if (rc) return rc;
-  if (g.k_splits > 1) {
+  if (g.k_splits > 1 && !f32_out) {
     long long b = (out_elems + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
-    splitk_finalize_kernel<<<(unsigned)b, 256, 0, st>>>(splitk_ws, reinterpret_cast<bf16*>(y), (long long)N * OH * OW, Rp,
+    gcc_launch(splitk_finalize_kernel, (unsigned)b, 256, 0, st, splitk_ws, reinterpret_cast<bf16*>(y), (long long)N * OH * OW, Rp,
                                                        Cy, y_coff, R, bias, act, slope);
     GCC_CHECK_LAUNCH();
   }
   trace_end(st, "conv", N, H, W, Cx, R, OH, OW, KH, stride, transposed, BN, base_tiles, g.k_splits, max_kb,
             stats != nullptr, 2.0 * N * OH * OW * (double)R * Ck * KH * KW / (transposed && stride == 2 ? 4 : 1));
   return GCC_OK;
+}
+
+extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
+                                  const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
+                                  int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
+                                  float* splitk_ws, long long ws_elems, float* stats, int stats_ld, void* stream) {
+  return gcc_conv_gemm_launch(x, N, H, W, Cx, w, R, T, Cw, bias, y, OH, OW, Cy, y_coff, transposed, KH, KW, stride, pad,
+                              act, slope, w_per_image, splitk_ws, ws_elems, stats, stats_ld, 0, stream);
 }
 
 // dW[b][r][t][c] (+)= scale * sum_{pix} P[n, oh, ow, r] * Q[n, s*oh + kh - p, s*ow + kw - p, c]

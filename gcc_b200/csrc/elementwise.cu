@@ -17,6 +17,8 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
 // dst[n,h,w,c_off + c] = bf16(src[n,c,h,w]); channels [c_off + C, zero_to) are zeroed.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int C, long long HW,
                                     int Cp, int c_off, int zero_to) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long total = (long long)N * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -29,6 +31,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16* __restr
 // dst[n,c,h,w] (+)= float(src[n,h,w,c_off + c])
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int N, int C, long long HW,
                                     int Cp, int c_off, int accumulate) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long total = (long long)N * C * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -46,6 +50,8 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, float* __restr
 // dst[p, d_off + c] (=|+=) src[p, s_off + c], c < C.  Vector path when everything is 8-aligned.
 __global__ void copy_channels_vec_kernel(const bf16* __restrict__ src, int Cs, int s_off, bf16* __restrict__ dst,
                                          int Cd, int d_off, int G, long long npix, int accumulate) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long nvec = npix * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -65,6 +71,8 @@ __global__ void copy_channels_vec_kernel(const bf16* __restrict__ src, int Cs, i
 }
 __global__ void copy_channels_scalar_kernel(const bf16* __restrict__ src, int Cs, int s_off, bf16* __restrict__ dst,
                                             int Cd, int d_off, int C, long long npix, int accumulate) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long total = npix * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -80,6 +88,8 @@ __global__ void copy_channels_scalar_kernel(const bf16* __restrict__ src, int Cs
 // one vector load per input pixel, one vector store.  split = the backward (either output may be NULL).
 __global__ void cat_small_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y,
                                  int ca, int cb, long long npix) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 ua = a[i], ub = b[i];
@@ -94,6 +104,8 @@ __global__ void cat_small_kernel(const uint4* __restrict__ a, const uint4* __res
 }
 __global__ void split_small_kernel(const uint4* __restrict__ dy, uint4* __restrict__ da, uint4* __restrict__ db, int ca,
                                    int cb, long long npix) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 u = dy[i];
@@ -119,6 +131,8 @@ __global__ void split_small_kernel(const uint4* __restrict__ dy, uint4* __restri
 // mode 1 leaky-relu, 2 relu, 3 tanh
 __global__ void act_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long nvec, int mode,
                                float slope) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 u = reinterpret_cast<const uint4*>(x)[i];
@@ -138,6 +152,8 @@ __global__ void act_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
 // dx = dy * f'(.) where ref is the forward INPUT for (leaky-)relu and the forward OUTPUT for tanh
 __global__ void act_bwd_kernel(const bf16* __restrict__ ref, const bf16* __restrict__ dy, bf16* __restrict__ dx,
                                long long nvec, int mode, float slope) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 r = reinterpret_cast<const uint4*>(ref)[i];
@@ -162,6 +178,8 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ ref, const bf16* __restr
 // captured CUDA graph draws a fresh mask on every replay.
 __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n, float p,
                                const unsigned long long* __restrict__ seed_ptr, unsigned int salt) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const unsigned long long seed = *seed_ptr;
   const uint32_t s0 = hash_u32((uint32_t)seed ^ salt), s1 = hash_u32((uint32_t)(seed >> 32) + 0x9e3779b9U);
   const float scale = 1.f / (1.f - p);
@@ -175,6 +193,8 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
 }
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y,
                            long long nvec) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 u = reinterpret_cast<const uint4*>(a)[i];
@@ -193,6 +213,8 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
 //   direct     bf16 [D0][T][D1p]      transposed bf16 [D1][T][D0p]    (pads stay zero)
 __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ direct,
                                    bf16* __restrict__ transposed, int D0, int T, int D1, int D1p, int D0p) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long total = (long long)D0 * T * D1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -211,6 +233,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
 // (block, channel).  Requires Cp % 8 == 0 and c_off % 8 == 0 (activations always satisfy this).
 __global__ void colsum_vec_kernel(const bf16* __restrict__ dy, long long npix, int Cp, int c_off, int C, int G,
                                   int lanes, float* __restrict__ out) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   extern __shared__ float red[];  // [lanes][G][8]
   const int tid = threadIdx.x;
   const int g = tid % G, lane = tid / G;
@@ -244,6 +268,8 @@ __device__ __forceinline__ int reflect(int i, int n) {
 }
 __global__ void reflect_pad_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int G,
                                    int pad) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int OH = H + 2 * pad, OW = W + 2 * pad;
   const long long nvec = (long long)N * OH * OW * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
@@ -260,6 +286,8 @@ __global__ void reflect_pad_kernel(const bf16* __restrict__ x, bf16* __restrict_
 // dx[n,ih,iw] = sum of dy over all padded positions that mirror onto (ih, iw)
 __global__ void reflect_pad_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int G,
                                        int pad) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int OH = H + 2 * pad, OW = W + 2 * pad;
   const long long nvec = (long long)N * H * W * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
@@ -295,6 +323,8 @@ __global__ void reflect_pad_bwd_kernel(const bf16* __restrict__ dy, bf16* __rest
 __global__ void dw3x3_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                  const float* __restrict__ bias, bf16* __restrict__ y, int N, int H, int W, int G,
                                  int C) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long nvec = (long long)N * H * W * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -326,12 +356,140 @@ __global__ void dw3x3_fwd_kernel(const bf16* __restrict__ x, const float* __rest
                                                 pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
   }
 }
+// Row-sliding depthwise 3x3: thread = (channel group of 8, pixel lane); an item is a segment of one output row.  The
+// 72 tap weights of the thread's 8 channels live in registers and a 3 x 3 window of 16-byte vectors slides along the
+// row, so every output costs 3 new loads (instead of 9 loads + 72 weight loads in the per-pixel kernels above).
+//   MODE 0: forward with the fused ReflectionPad2d(1):  y = b + sum_k w[k] x[refl(h+kh-1), refl(w+kw-1)]
+//   MODE 1: data gradient of the same: the zero-padded correlation of dy with the flipped taps, where the rows /
+//           columns next to the border also collect the mirrored taps (dx[1] += w[kh=0] dy[0], dx[H-2] += w[kh=2]
+//           dy[H-1], same for columns) -- the fold of reflect_pad_bwd applied to the tap weights instead of the data.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+dw3x3_rows_kernel(const bf16* __restrict__ src, const float* __restrict__ w, const float* __restrict__ bias,
+                  bf16* __restrict__ dst, int H, int W, int G, int C, int lanes, int seg, long long items) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  if (lane >= lanes) return;
+  float we[3][3][8];  // [row offset][column offset][channel]
+  float bs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) bs[k] = (MODE == 0 && bias != nullptr && g * 8 + k < C) ? bias[g * 8 + k] : 0.f;
+  if (MODE == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) we[a][b][k] = (g * 8 + k < C) ? w[(g * 8 + k) * 9 + a * 3 + b] : 0.f;
+  }
+  const int segs = (W + seg - 1) / seg;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const uint4* sv = reinterpret_cast<const uint4*>(src);
+  uint4* dv = reinterpret_cast<uint4*>(dst);
+  for (long long it = (long long)blockIdx.x * lanes + lane; it < items; it += (long long)gridDim.x * lanes) {
+    const int sgi = (int)(it % segs);
+    const long long t = it / segs;
+    const int r = (int)(t % H);
+    const long long n = t / H;
+    const int w0 = sgi * seg, w1 = min(W, w0 + seg);
+    long long rowoff[3];
+    bool rv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      int rr = r + a - 1;
+      if (MODE == 0) {
+        rr = reflect(rr, H);
+        rv[a] = true;
+      } else {
+        rv[a] = rr >= 0 && rr < H;
+      }
+      rowoff[a] = ((n * H + (rv[a] ? rr : 0)) * (long long)W) * G + g;
+    }
+    if (MODE == 1) {
+      // we[a][b] = w[kh = 2 - a][kw = 2 - b] (+ the mirrored tap on the rows next to the border)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            float v = 0.f;
+            if (c < C) {
+              v = __ldg(w + c * 9 + (2 - a) * 3 + (2 - b));
+              if (a == 0 && r == 1) v += __ldg(w + c * 9 + 0 * 3 + (2 - b));
+              if (a == 2 && r == H - 2) v += __ldg(w + c * 9 + 2 * 3 + (2 - b));
+            }
+            we[a][b][k] = v;
+          }
+    }
+    auto ld = [&](int a, int col) -> uint4 {
+      if (MODE == 0) return sv[rowoff[a] + (long long)reflect(col, W) * G];
+      return (rv[a] && col >= 0 && col < W) ? sv[rowoff[a] + (long long)col * G] : zero;
+    };
+    uint4 win[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      win[a][0] = ld(a, w0 - 1);
+      win[a][1] = ld(a, w0);
+    }
+    for (int ow = w0; ow < w1; ++ow) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) win[a][2] = ld(a, ow + 1);
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = bs[k];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const uint4 u = win[a][b];
+          const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                               bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += xv[k] * we[a][b][k];
+        }
+      if (MODE == 1 && (ow == 1 || ow == W - 2)) {
+        // mirrored column taps: dx[.., 1] += w[.., kw = 0] dy[.., 0];  dx[.., W - 2] += w[.., kw = 2] dy[.., W - 1]
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (ow == 1) {
+            const uint4 u = win[a][0];
+            const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                                 bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += xv[k] * we[a][2][k];
+          }
+          if (ow == W - 2) {
+            const uint4 u = win[a][2];
+            const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                                 bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += xv[k] * we[a][0][k];
+          }
+        }
+      }
+      dv[((n * H + r) * (long long)W + ow) * G + g] =
+          make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                     pack_bf16(acc[6], acc[7]));
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        win[a][0] = win[a][1];
+        win[a][1] = win[a][2];
+      }
+    }
+  }
+}
+
 // data gradient: scatter form of the reflected gather = gather over the (<= 3x3 x mirror) sources.
 // Implemented as: dxp = zero-padded correlation on the reflect-PADDED grid, then folded by
 // reflect_pad_bwd.  Here: dyp-style direct accumulation over taps with explicit mirror bookkeeping
 // is avoided by computing on the padded grid: dxp[n, ph, pw, c] = sum_k w[c][k] * dy[n, ph-kh, pw-kw, c].
 __global__ void dw3x3_bwd_data_padded_kernel(const bf16* __restrict__ dy, const float* __restrict__ w,
                                              bf16* __restrict__ dxp, int N, int H, int W, int G, int C) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int PH = H + 2, PW = W + 2;
   const long long nvec = (long long)N * PH * PW * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
@@ -369,6 +527,8 @@ __global__ void dw3x3_bwd_data_padded_kernel(const bf16* __restrict__ dy, const 
 __global__ void dw3x3_bwd_weight_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                         float* __restrict__ dw, float* __restrict__ dbias, int N, int H, int W, int G,
                                         int C, int lanes) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   extern __shared__ float sred[];  // [lanes][G][80]
   const int tid = threadIdx.x;
   const int g = tid % G, lane = tid / G;
@@ -427,6 +587,8 @@ __global__ void dw3x3_bwd_weight_kernel(const bf16* __restrict__ x, const bf16* 
 // are laid out as ONE 128-wide K (or N) so the same tcgen05 kernels run them as 1x1 convs.
 // col[n,oh,ow,(kh*4+kw)*8 + c] = img[n, 2*oh+kh-1, 2*ow+kw-1, c]   (zero outside the image)
 __global__ void im2col_k4s2_c8_kernel(const uint4* __restrict__ img, uint4* __restrict__ col, int N, int H, int W) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2;
   const long long total = (long long)N * OH * OW * 16;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -447,6 +609,8 @@ __global__ void im2col_k4s2_c8_kernel(const uint4* __restrict__ img, uint4* __re
 __global__ void col2im_k4s2_c8_kernel(const bf16* __restrict__ col, int Ccol, int order, int C,
                                       const float* __restrict__ bias, int act, uint4* __restrict__ img, int N, int H,
                                       int W) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2;
   const long long total = (long long)N * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -497,6 +661,8 @@ __global__ void col2im_k4s2_c8_kernel(const bf16* __restrict__ col, int Ccol, in
 }
 // g[r][tap][c] += tmp[r][tap*8 + c]   (c < C <= 8): weight gradient of a col-path layer back to [R][16][C]
 __global__ void unpad_wgrad_c8_kernel(const float* __restrict__ tmp, float* __restrict__ g, int R, int C) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int total = R * 16 * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % C;
@@ -510,6 +676,8 @@ __global__ void unpad_wgrad_c8_kernel(const float* __restrict__ tmp, float* __re
 // per tap); the 16 partial dot products are then folded:  y[n,oy,ox,co] = b[co] + sum_taps ycol[n,oy+kh-1,ox+kw-1,.]
 __global__ void fold_k4s1_kernel(const bf16* __restrict__ ycol, int Ccol, int C, const float* __restrict__ bias,
                                  uint4* __restrict__ y, int N, int H, int W) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int OH = H - 1, OW = W - 1;  // k4 s1 p1
   const long long total = (long long)N * OH * OW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -540,6 +708,8 @@ __global__ void fold_k4s1_kernel(const bf16* __restrict__ ycol, int Ccol, int C,
 }
 // backward expansion: dcol[n,iy,ix,tap*8+c] = dy[n, iy-kh+1, ix-kw+1, c]  (zero outside), dy [N,H-1,W-1,8]
 __global__ void unfold_k4s1_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dcol, int N, int H, int W) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int OH = H - 1, OW = W - 1;
   const long long total = (long long)N * H * W * 16;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -557,6 +727,8 @@ __global__ void unfold_k4s1_kernel(const uint4* __restrict__ dy, uint4* __restri
 }
 // g[c][tap][k] += tmp[tap*8 + c][k]   (c < C): weight gradient of the head back to [C][16][K]
 __global__ void unpad_wgrad_rows_kernel(const float* __restrict__ tmp, float* __restrict__ g, int C, int K) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long total = (long long)C * 16 * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -588,6 +760,8 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   return x ^ (x >> 31);
 }
 __global__ void image_pool_decide_kernel(long long* state, int pool_size, int b, int* dec) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   long long count = state[0];
   unsigned long long ctr = (unsigned long long)state[1];
@@ -613,6 +787,8 @@ __global__ void image_pool_decide_kernel(long long* state, int pool_size, int b,
 }
 __global__ void image_pool_gather_kernel(const uint4* __restrict__ images, const uint4* __restrict__ pool,
                                          const int* __restrict__ dec, uint4* __restrict__ out, long long vec_per_image) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int i = blockIdx.y;
   const int src = dec[2 * i];
   const uint4* s = src == -1 ? images + (long long)i * vec_per_image
@@ -625,6 +801,8 @@ __global__ void image_pool_gather_kernel(const uint4* __restrict__ images, const
 }
 __global__ void image_pool_scatter_kernel(const uint4* __restrict__ images, uint4* __restrict__ pool,
                                           const int* __restrict__ dec, long long vec_per_image) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int i = blockIdx.y;
   const int dst = dec[2 * i + 1];
   if (dst < 0) return;
@@ -641,14 +819,14 @@ using namespace gcc;
 
 extern "C" int gcc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, long long HW, int Cp, int c_off,
                                          int zero_to, void* stream) {
-  nchw_to_nhwc_kernel<<<blocks_for((long long)N * HW), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, N, C, HW, Cp,
+  gcc_launch(nchw_to_nhwc_kernel, blocks_for((long long)N * HW), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, N, C, HW, Cp,
                                                                                        c_off, zero_to);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, long long HW, int Cp, int c_off,
                                          int accumulate, void* stream) {
-  nhwc_to_nchw_kernel<<<blocks_for((long long)N * C * HW), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, N, C,
+  gcc_launch(nhwc_to_nchw_kernel, blocks_for((long long)N * C * HW), 256, 0, (cudaStream_t)stream, (const bf16*)src, dst, N, C,
                                                                                            HW, Cp, c_off, accumulate);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -658,10 +836,10 @@ extern "C" int gcc_copy_channels_bf16(const void* src, int Cs, int s_off, void* 
   cudaStream_t st = (cudaStream_t)stream;
   if (!(Cs % 8) && !(s_off % 8) && !(Cd % 8) && !(d_off % 8) && !(C % 8)) {
     const int G = C / 8;
-    copy_channels_vec_kernel<<<blocks_for(npix * G), 256, 0, st>>>((const bf16*)src, Cs, s_off, (bf16*)dst, Cd, d_off,
+    gcc_launch(copy_channels_vec_kernel, blocks_for(npix * G), 256, 0, st, (const bf16*)src, Cs, s_off, (bf16*)dst, Cd, d_off,
                                                                    G, npix, accumulate);
   } else {
-    copy_channels_scalar_kernel<<<blocks_for(npix * C), 256, 0, st>>>((const bf16*)src, Cs, s_off, (bf16*)dst, Cd,
+    gcc_launch(copy_channels_scalar_kernel, blocks_for(npix * C), 256, 0, st, (const bf16*)src, Cs, s_off, (bf16*)dst, Cd,
                                                                       d_off, C, npix, accumulate);
   }
   GCC_CHECK_LAUNCH();
@@ -669,35 +847,35 @@ extern "C" int gcc_copy_channels_bf16(const void* src, int Cs, int s_off, void* 
 }
 extern "C" int gcc_cat_small_bf16(const void* a, const void* b, void* y, int ca, int cb, long long npix, void* stream) {
   if (ca < 0 || cb < 0 || ca + cb > 8) { gcc_set_error(__FILE__, __LINE__, "cat_small: ca + cb must be <= 8"); return GCC_ERR_ARG; }
-  cat_small_kernel<<<blocks_for(npix), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)y, ca, cb,
+  gcc_launch(cat_small_kernel, blocks_for(npix), 256, 0, (cudaStream_t)stream, (const uint4*)a, (const uint4*)b, (uint4*)y, ca, cb,
                                                                       npix);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_split_small_bf16(const void* dy, void* da, void* db, int ca, int cb, long long npix, void* stream) {
   if (ca < 0 || cb < 0 || ca + cb > 8) { gcc_set_error(__FILE__, __LINE__, "split_small: ca + cb must be <= 8"); return GCC_ERR_ARG; }
-  split_small_kernel<<<blocks_for(npix), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)da, (uint4*)db, ca, cb,
+  gcc_launch(split_small_kernel, blocks_for(npix), 256, 0, (cudaStream_t)stream, (const uint4*)dy, (uint4*)da, (uint4*)db, ca, cb,
                                                                         npix);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_act_fwd_bf16(const void* x, void* y, long long n, int mode, float slope, void* stream) {
   if (n % 8) { gcc_set_error(__FILE__, __LINE__, "act: element count must be a multiple of 8"); return GCC_ERR_ARG; }
-  act_fwd_kernel<<<blocks_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n / 8, mode, slope);
+  gcc_launch(act_fwd_kernel, blocks_for(n / 8), 256, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, n / 8, mode, slope);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_act_bwd_bf16(const void* ref, const void* dy, void* dx, long long n, int mode, float slope,
                                 void* stream) {
   if (n % 8) { gcc_set_error(__FILE__, __LINE__, "act: element count must be a multiple of 8"); return GCC_ERR_ARG; }
-  act_bwd_kernel<<<blocks_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)ref, (const bf16*)dy, (bf16*)dx,
+  gcc_launch(act_bwd_kernel, blocks_for(n / 8), 256, 0, (cudaStream_t)stream, (const bf16*)ref, (const bf16*)dy, (bf16*)dx,
                                                                       n / 8, mode, slope);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_dropout_bf16(const void* x, void* y, long long n, float p, const void* seed_dev, int salt,
                                 void* stream) {
-  dropout_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n, p,
+  gcc_launch(dropout_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, n, p,
                                                                   (const unsigned long long*)seed_dev,
                                                                   (unsigned int)salt);
   GCC_CHECK_LAUNCH();
@@ -705,13 +883,13 @@ extern "C" int gcc_dropout_bf16(const void* x, void* y, long long n, float p, co
 }
 extern "C" int gcc_add_bf16(const void* a, const void* b, void* y, long long n, void* stream) {
   if (n % 8) { gcc_set_error(__FILE__, __LINE__, "add: element count must be a multiple of 8"); return GCC_ERR_ARG; }
-  add_kernel<<<blocks_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n / 8);
+  gcc_launch(add_kernel, blocks_for(n / 8), 256, 0, (cudaStream_t)stream, (const bf16*)a, (const bf16*)b, (bf16*)y, n / 8);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_pack_weight_bf16(const float* src, void* direct, void* transposed, int D0, int T, int D1, int D1p,
                                     int D0p, void* stream) {
-  pack_weight_kernel<<<blocks_for((long long)D0 * T * D1), 256, 0, (cudaStream_t)stream>>>(
+  gcc_launch(pack_weight_kernel, blocks_for((long long)D0 * T * D1), 256, 0, (cudaStream_t)stream, 
       src, (bf16*)direct, (bf16*)transposed, D0, T, D1, D1p, D0p);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -731,7 +909,7 @@ extern "C" int gcc_bias_grad_bf16(const void* dy, long long npix, int Cp, int c_
   long long bx = (npix + lanes * 16 - 1) / (lanes * 16);
   if (bx > 148 * 8) bx = 148 * 8;
   if (bx < 1) bx = 1;
-  colsum_vec_kernel<<<(unsigned)bx, threads, sizeof(float) * lanes * G * 8, st>>>((const bf16*)dy, npix, Cp, c_off, C, G,
+  gcc_launch(colsum_vec_kernel, (unsigned)bx, threads, sizeof(float) * lanes * G * 8, st, (const bf16*)dy, npix, Cp, c_off, C, G,
                                                                                 lanes, out);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -742,34 +920,56 @@ extern "C" int gcc_reflect_pad_bf16(const void* x, void* y, int N, int H, int W,
   if (Cp % 8 || pad >= H || pad >= W) { gcc_set_error(__FILE__, __LINE__, "reflect_pad: bad arguments"); return GCC_ERR_ARG; }
   const int G = Cp / 8;
   if (!backward)
-    reflect_pad_kernel<<<blocks_for((long long)N * (H + 2 * pad) * (W + 2 * pad) * G), 256, 0, st>>>(
+    gcc_launch(reflect_pad_kernel, blocks_for((long long)N * (H + 2 * pad) * (W + 2 * pad) * G), 256, 0, st, 
         (const bf16*)x, (bf16*)y, N, H, W, G, pad);
   else  // x = dy on the padded grid [N, H+2p, W+2p, Cp], y = dx [N, H, W, Cp]
-    reflect_pad_bwd_kernel<<<blocks_for((long long)N * H * W * G), 256, 0, st>>>((const bf16*)x, (bf16*)y, N, H, W, G,
+    gcc_launch(reflect_pad_bwd_kernel, blocks_for((long long)N * H * W * G), 256, 0, st, (const bf16*)x, (bf16*)y, N, H, W, G,
                                                                                  pad);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
+// launch geometry of dw3x3_rows_kernel: lanes pixel lanes per CTA, row segments short enough to fill the machine
+static void dw_rows_geometry(int N, int H, int W, int G, int* lanes, int* threads, int* seg, long long* items, int* blocks) {
+  int l = 256 / G;
+  if (l < 1) l = 1;
+  int sg = 64;
+  while (sg > 8 && (long long)N * H * ((W + sg - 1) / sg) < 2LL * 148 * l) sg >>= 1;
+  if (sg > W) sg = W;
+  const long long it = (long long)N * H * ((W + sg - 1) / sg);
+  long long b = (it + l - 1) / l;
+  if (b > 148 * 8) b = 148 * 8;
+  *lanes = l;
+  *threads = (l * G + 31) / 32 * 32;
+  *seg = sg;
+  *items = it;
+  *blocks = (int)(b < 1 ? 1 : b);
+}
 extern "C" int gcc_dw3x3_fwd_bf16(const void* x, const float* w, const float* bias, void* y, int N, int H, int W,
                                   int Cp, int C, void* stream) {
-  if (Cp % 8) { gcc_set_error(__FILE__, __LINE__, "dw3x3: bad channel count"); return GCC_ERR_ARG; }
-  dw3x3_fwd_kernel<<<blocks_for((long long)N * H * W * (Cp / 8)), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, w, bias, (bf16*)y, N, H, W, Cp / 8, C);
+  if (Cp % 8 || Cp / 8 > 256 || H < 2 || W < 2) {
+    gcc_set_error(__FILE__, __LINE__, "dw3x3: bad channel count or extent");
+    return GCC_ERR_ARG;
+  }
+  int lanes, threads, seg, blocks;
+  long long items;
+  dw_rows_geometry(N, H, W, Cp / 8, &lanes, &threads, &seg, &items, &blocks);
+  gcc_launch(dw3x3_rows_kernel<0>, blocks, threads, 0, (cudaStream_t)stream, (const bf16*)x, w, bias, (bf16*)y, H, W,
+             Cp / 8, C, lanes, seg, items);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
-// dxp: scratch bf16 [N, H+2, W+2, Cp]; dx: [N, H, W, Cp]; dw fp32 [C][9]; dbias fp32 [C] (may be NULL)
 extern "C" int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w, void* dxp, void* dx, float* dw,
                                   float* dbias, int N, int H, int W, int Cp, int C, int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (Cp % 8 || Cp / 8 > 256) { gcc_set_error(__FILE__, __LINE__, "dw3x3: bad channel count"); return GCC_ERR_ARG; }
   const int G = Cp / 8;
   if (dx != nullptr) {
-    dw3x3_bwd_data_padded_kernel<<<blocks_for((long long)N * (H + 2) * (W + 2) * G), 256, 0, st>>>(
-        (const bf16*)dy, w, (bf16*)dxp, N, H, W, G, C);
-    GCC_CHECK_LAUNCH();
-    reflect_pad_bwd_kernel<<<blocks_for((long long)N * H * W * G), 256, 0, st>>>((const bf16*)dxp, (bf16*)dx, N, H, W,
-                                                                                 G, 1);
+    if (H < 2 || W < 2) { gcc_set_error(__FILE__, __LINE__, "dw3x3: extent"); return GCC_ERR_ARG; }
+    int lanes, threads, seg, blocks;
+    long long items;
+    dw_rows_geometry(N, H, W, G, &lanes, &threads, &seg, &items, &blocks);
+    gcc_launch(dw3x3_rows_kernel<1>, blocks, threads, 0, st, (const bf16*)dy, w, (const float*)nullptr, (bf16*)dx, H, W, G,
+               C, lanes, seg, items);
     GCC_CHECK_LAUNCH();
   }
   if (dw != nullptr) {
@@ -792,7 +992,7 @@ extern "C" int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w,
       cudaFuncSetAttribute(dw3x3_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       configured[dev] = true;
     }
-    dw3x3_bwd_weight_kernel<<<(unsigned)bx, threads, smem, st>>>((const bf16*)x, (const bf16*)dy, dw, dbias, N, H, W,
+    gcc_launch(dw3x3_bwd_weight_kernel, (unsigned)bx, threads, smem, st, (const bf16*)x, (const bf16*)dy, dw, dbias, N, H, W,
                                                                  G, C, lanes);
     GCC_CHECK_LAUNCH();
   }
@@ -801,7 +1001,7 @@ extern "C" int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w,
 
 extern "C" int gcc_im2col_k4s2_c8(const void* img, void* col, int N, int H, int W, void* stream) {
   if ((H % 2) || (W % 2)) { gcc_set_error(__FILE__, __LINE__, "im2col: H, W must be even"); return GCC_ERR_ARG; }
-  im2col_k4s2_c8_kernel<<<blocks_for((long long)N * (H / 2) * (W / 2) * 16), 256, 0, (cudaStream_t)stream>>>(
+  gcc_launch(im2col_k4s2_c8_kernel, blocks_for((long long)N * (H / 2) * (W / 2) * 16), 256, 0, (cudaStream_t)stream, 
       (const uint4*)img, (uint4*)col, N, H, W);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -812,14 +1012,14 @@ extern "C" int gcc_col2im_k4s2_c8(const void* col, int Ccol, int order, int C, c
     gcc_set_error(__FILE__, __LINE__, "col2im: bad arguments");
     return GCC_ERR_ARG;
   }
-  col2im_k4s2_c8_kernel<<<blocks_for((long long)N * H * W), 256, 0, (cudaStream_t)stream>>>(
+  gcc_launch(col2im_k4s2_c8_kernel, blocks_for((long long)N * H * W), 256, 0, (cudaStream_t)stream, 
       (const bf16*)col, Ccol, order, C, bias, act, (uint4*)img, N, H, W);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_unpad_wgrad_c8(const float* tmp, float* g, int R, int C, void* stream) {
   if (C > 8) { gcc_set_error(__FILE__, __LINE__, "unpad_wgrad: C must be <= 8"); return GCC_ERR_ARG; }
-  unpad_wgrad_c8_kernel<<<(R * 16 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tmp, g, R, C);
+  gcc_launch(unpad_wgrad_c8_kernel, (R * 16 * C + 255) / 256, 256, 0, (cudaStream_t)stream, tmp, g, R, C);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -827,20 +1027,20 @@ extern "C" int gcc_unpad_wgrad_c8(const float* tmp, float* g, int R, int C, void
 extern "C" int gcc_fold_k4s1_c8(const void* ycol, int Ccol, int C, const float* bias, void* y, int N, int H, int W,
                                 void* stream) {
   if (C > 8 || H < 2 || W < 2) { gcc_set_error(__FILE__, __LINE__, "fold_k4s1: bad arguments"); return GCC_ERR_ARG; }
-  fold_k4s1_kernel<<<blocks_for((long long)N * (H - 1) * (W - 1)), 256, 0, (cudaStream_t)stream>>>(
+  gcc_launch(fold_k4s1_kernel, blocks_for((long long)N * (H - 1) * (W - 1)), 256, 0, (cudaStream_t)stream, 
       (const bf16*)ycol, Ccol, C, bias, (uint4*)y, N, H, W);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_unfold_k4s1_c8(const void* dy, void* dcol, int N, int H, int W, void* stream) {
-  unfold_k4s1_kernel<<<blocks_for((long long)N * H * W * 16), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy,
+  gcc_launch(unfold_k4s1_kernel, blocks_for((long long)N * H * W * 16), 256, 0, (cudaStream_t)stream, (const uint4*)dy,
                                                                                             (uint4*)dcol, N, H, W);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_unpad_wgrad_rows(const float* tmp, float* g, int C, int K, void* stream) {
   if (C > 8) { gcc_set_error(__FILE__, __LINE__, "unpad_wgrad_rows: C must be <= 8"); return GCC_ERR_ARG; }
-  unpad_wgrad_rows_kernel<<<blocks_for((long long)C * 16 * K), 256, 0, (cudaStream_t)stream>>>(tmp, g, C, K);
+  gcc_launch(unpad_wgrad_rows_kernel, blocks_for((long long)C * 16 * K), 256, 0, (cudaStream_t)stream, tmp, g, C, K);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -853,14 +1053,14 @@ extern "C" int gcc_image_pool_query_bf16(const void* images, void* pool, long lo
     return GCC_ERR_ARG;
   }
   const long long vec = elems_per_image / 8;
-  image_pool_decide_kernel<<<1, 32, 0, st>>>(state_dev, pool_size, b, dec_ws);
+  gcc_launch(image_pool_decide_kernel, 1, 32, 0, st, state_dev, pool_size, b, dec_ws);
   GCC_CHECK_LAUNCH();
   long long bx = (vec + 255) / 256;
   if (bx > 148 * 4) bx = 148 * 4;
-  image_pool_gather_kernel<<<dim3((unsigned)bx, b), 256, 0, st>>>((const uint4*)images, (const uint4*)pool, dec_ws,
+  gcc_launch(image_pool_gather_kernel, dim3((unsigned)bx, b), 256, 0, st, (const uint4*)images, (const uint4*)pool, dec_ws,
                                                                   (uint4*)out, vec);
   GCC_CHECK_LAUNCH();
-  image_pool_scatter_kernel<<<dim3((unsigned)bx, b), 256, 0, st>>>((const uint4*)images, (uint4*)pool, dec_ws, vec);
+  gcc_launch(image_pool_scatter_kernel, dim3((unsigned)bx, b), 256, 0, st, (const uint4*)images, (uint4*)pool, dec_ws, vec);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

@@ -45,6 +45,8 @@ __device__ __forceinline__ float gan_term(float x, int mode, int kind, float* gr
 
 __global__ void gan_loss_fwd_kernel(const bf16* __restrict__ pred, long long npix, int Cp, int C, int mode, int kind,
                                     float inv_count, float* __restrict__ out) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   float acc = 0.f;
   const long long total = npix * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -59,6 +61,8 @@ __global__ void gan_loss_fwd_kernel(const bf16* __restrict__ pred, long long npi
 // dpred = gout * d(term)/dx / count   (pad channels get zero)
 __global__ void gan_loss_bwd_kernel(const bf16* __restrict__ pred, long long npix, int Cp, int C, int mode, int kind,
                                     float inv_count, const float* __restrict__ gout, bf16* __restrict__ dpred) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const float go = *gout * inv_count;
   const long long total = npix * Cp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -73,6 +77,8 @@ __global__ void gan_loss_bwd_kernel(const bf16* __restrict__ pred, long long npi
 // out[0] += sum |a-b| * inv_count   (mode 0)   or   sum (a-b)^2 * inv_count   (mode 1)
 __global__ void diff_reduce_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long npix,
                                         int Cp, int C, int mode, float inv_count, float* __restrict__ out) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   float acc = 0.f;
   if (C == Cp && (Cp % 8) == 0) {
     const long long nvec = npix * Cp / 8;
@@ -106,6 +112,8 @@ __global__ void diff_reduce_bf16_kernel(const bf16* __restrict__ a, const bf16* 
 __global__ void diff_bwd_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long npix, int Cp,
                                      int C, int mode, float inv_count, const float* __restrict__ gout,
                                      const float* __restrict__ msq, bf16* __restrict__ da) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   float go = *gout * inv_count;
   if (mode == 1) go /= fmaxf(sqrtf(*msq), 1e-20f);
   if (mode == 2) go *= 2.f;  // plain MSE
@@ -136,6 +144,8 @@ __global__ void diff_bwd_bf16_kernel(const bf16* __restrict__ a, const bf16* __r
 // fp32 matrices (Gram): out += sum (a-b)^2 * inv_count
 __global__ void sqdiff_reduce_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
                                          float inv_count, float* __restrict__ out) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float d = a[i] - b[i];
@@ -149,6 +159,8 @@ __global__ void sqdiff_reduce_f32_kernel(const float* __restrict__ a, const floa
 __global__ void gram_bwd_matrix_kernel(const float* __restrict__ gs, const float* __restrict__ gt, int B, int C,
                                        int Cp, float inv_count, float gram_scale, const float* __restrict__ gout,
                                        const float* __restrict__ msq, int mse, bf16* __restrict__ m) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   __shared__ float tile[32][33];
   const float coef = mse ? *gout * inv_count * 2.f * gram_scale
                          : *gout * inv_count / fmaxf(sqrtf(*msq), 1e-20f) * gram_scale;
@@ -176,7 +188,9 @@ __global__ void gram_bwd_matrix_kernel(const float* __restrict__ gs, const float
 }
 
 // tiny scalar program: out = sqrt(in)   (RMSE from mean-square, kept on device)
-__global__ void scalar_sqrt_kernel(const float* in, float* out) { *out = sqrtf(fmaxf(*in, 0.f)); }
+__global__ void scalar_sqrt_kernel(const float* in, float* out) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents(); *out = sqrtf(fmaxf(*in, 0.f)); }
 
 static inline int rblocks(long long n) {
   long long b = (n + 1023) / 1024;
@@ -191,7 +205,7 @@ using namespace gcc;
 extern "C" int gcc_gan_loss_fwd_bf16(const void* pred, long long npix, int Cp, int C, int mode, int kind, float* out,
                                      void* stream) {
   const float inv = 1.f / (float)(npix * C);
-  gan_loss_fwd_kernel<<<rblocks(npix * C), 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, npix, Cp, C, mode, kind,
+  gcc_launch(gan_loss_fwd_kernel, rblocks(npix * C), 256, 0, (cudaStream_t)stream, (const bf16*)pred, npix, Cp, C, mode, kind,
                                                                           inv, out);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -199,7 +213,7 @@ extern "C" int gcc_gan_loss_fwd_bf16(const void* pred, long long npix, int Cp, i
 extern "C" int gcc_gan_loss_bwd_bf16(const void* pred, long long npix, int Cp, int C, int mode, int kind,
                                      const float* gout, void* dpred, void* stream) {
   const float inv = 1.f / (float)(npix * C);
-  gan_loss_bwd_kernel<<<rblocks(npix * Cp), 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, npix, Cp, C, mode, kind,
+  gcc_launch(gan_loss_bwd_kernel, rblocks(npix * Cp), 256, 0, (cudaStream_t)stream, (const bf16*)pred, npix, Cp, C, mode, kind,
                                                                            inv, gout, (bf16*)dpred);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -208,7 +222,7 @@ extern "C" int gcc_gan_loss_bwd_bf16(const void* pred, long long npix, int Cp, i
 extern "C" int gcc_diff_reduce_bf16(const void* a, const void* b, long long npix, int Cp, int C, int mode, float* out,
                                     void* stream) {
   const float inv = 1.f / (float)(npix * C);
-  diff_reduce_bf16_kernel<<<rblocks(npix * Cp / 4), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b,
+  gcc_launch(diff_reduce_bf16_kernel, rblocks(npix * Cp / 4), 256, 0, (cudaStream_t)stream, (const bf16*)a, (const bf16*)b,
                                                                                    npix, Cp, C, mode, inv, out);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -220,26 +234,26 @@ extern "C" int gcc_diff_bwd_bf16(const void* a, const void* b, long long npix, i
   long long nb = (npix * (Cp / 8) + 255) / 256;
   if (nb > 148 * 16) nb = 148 * 16;
   if (nb < 1) nb = 1;
-  diff_bwd_bf16_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, npix, Cp, C, mode,
+  gcc_launch(diff_bwd_bf16_kernel, (unsigned)nb, 256, 0, (cudaStream_t)stream, (const bf16*)a, (const bf16*)b, npix, Cp, C, mode,
                                                                       inv, gout, msq, (bf16*)da);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_sqdiff_reduce_f32(const float* a, const float* b, long long n, float* out, void* stream) {
-  sqdiff_reduce_f32_kernel<<<rblocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, 1.f / (float)n, out);
+  gcc_launch(sqdiff_reduce_f32_kernel, rblocks(n), 256, 0, (cudaStream_t)stream, a, b, n, 1.f / (float)n, out);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_gram_bwd_matrix(const float* gs, const float* gt, int B, int C, int Cp, float gram_scale,
                                    const float* gout, const float* msq, int mse, void* m, void* stream) {
   const float inv = 1.f / ((float)B * C * C);
-  gram_bwd_matrix_kernel<<<dim3((Cp + 31) / 32, (C + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(
+  gcc_launch(gram_bwd_matrix_kernel, dim3((Cp + 31) / 32, (C + 31) / 32, B), 256, 0, (cudaStream_t)stream, 
       gs, gt, B, C, Cp, inv, gram_scale, gout, msq, mse, (bf16*)m);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_scalar_sqrt(const float* in, float* out, void* stream) {
-  scalar_sqrt_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(in, out);
+  gcc_launch(scalar_sqrt_kernel, 1, 1, 0, (cudaStream_t)stream, in, out);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

@@ -65,6 +65,8 @@ __device__ __forceinline__ float gate_value(const float* alpha, float thr, int c
 // sums[(n)][0:Cp) += sum x ; sums[(n)][Cp:2Cp) += sum x^2   (grid.y = n when per_sample)
 __global__ void __launch_bounds__(256, 4) norm_stats_kernel(const bf16* __restrict__ x, long long npix, int Cp, int G,
                                                             int lanes, float* __restrict__ sums) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   extern __shared__ float red[];  // [lanes][G][16]
   const int tid = threadIdx.x;
   const int g = tid % G, lane = tid / G;
@@ -157,6 +159,8 @@ template <bool DUAL>
 __global__ void __launch_bounds__(256, DUAL ? 2 : 4)
 norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp, int y2_coff, int act2,
                   float* running_mean, float* running_var, float momentum) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
   const int n = blockIdx.y;
@@ -215,6 +219,8 @@ norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict_
 __global__ void norm_apply_eval_kernel(NormArgs a, const float* __restrict__ rmean, const float* __restrict__ rvar,
                                        long long total_pix, bf16* __restrict__ y, bf16* __restrict__ y2, int y2_Cp,
                                        int y2_coff, int act2) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long nvec = total_pix * a.G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -250,6 +256,8 @@ __global__ void norm_apply_eval_kernel(NormArgs a, const float* __restrict__ rme
 __global__ void __launch_bounds__(256, 2)
 norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
                        const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2, float* __restrict__ red) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   extern __shared__ float sred[];  // [lanes][G][16]
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
@@ -337,6 +345,8 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
                                       int dy_coff, const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
                                       const float* __restrict__ red, const float* __restrict__ red_param,
                                       bf16* __restrict__ dx, float* dgamma, float* dbeta, float* dalpha) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
   const int n = blockIdx.y;
@@ -487,7 +497,7 @@ extern "C" int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, i
   const long long cap = (148LL * 4 + groups - 1) / groups;  // one resident wave: few same-address reductions
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  norm_stats_kernel<<<dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * G * 16, st>>>(
+  gcc_launch(norm_stats_kernel, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * G * 16, st, 
       (const bf16*)x, npix, Cp, G, lanes, sums);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -512,10 +522,10 @@ extern "C" int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, 
   const int threads = stats_threads(a.G, &lanes);
   const int bx = lane_blocks(a.npix, lanes, groups, 4);
   if (y2 != nullptr)
-    norm_apply_kernel<true><<<dim3(bx, groups), threads, 0, st>>>(a, lanes, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff, act2,
+    gcc_launch(norm_apply_kernel<true>, dim3(bx, groups), threads, 0, st, a, lanes, (bf16*)y, (bf16*)y2, y2_Cp, y2_coff, act2,
                                                                  running_mean, running_var, momentum);
   else
-    norm_apply_kernel<false><<<dim3(bx, groups), threads, 0, st>>>(a, lanes, (bf16*)y, nullptr, 0, 0, 0, running_mean,
+    gcc_launch(norm_apply_kernel<false>, dim3(bx, groups), threads, 0, st, a, lanes, (bf16*)y, nullptr, 0, 0, 0, running_mean,
                                                                   running_var, momentum);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -530,7 +540,7 @@ extern "C" int gcc_norm_apply_eval_bf16(const void* x, void* y, int N, long long
   int rc = fill_args(a, x, N, HW, Cp, C, 0, nullptr, gamma, beta, alpha, thr, eps, act, slope, 0);
   if (rc) return rc;
   const long long nvec = (long long)N * HW * a.G;
-  norm_apply_eval_kernel<<<ew_blocks(nvec), 256, 0, st>>>(a, running_mean, running_var, (long long)N * HW, (bf16*)y,
+  gcc_launch(norm_apply_eval_kernel, ew_blocks(nvec), 256, 0, st, a, running_mean, running_var, (long long)N * HW, (bf16*)y,
                                                           (bf16*)y2, y2_Cp, y2_coff, act2);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -568,7 +578,7 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
     const long long cap = (148LL * 2 + groups - 1) / groups;  // one resident wave (launch bounds: 2 CTAs / SM)
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    norm_bwd_reduce_kernel<<<dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st>>>(
+    gcc_launch(norm_bwd_reduce_kernel, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st, 
         a, lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
     GCC_CHECK_LAUNCH();
   }
@@ -577,11 +587,11 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
   const int athreads = stats_threads(a.G, &alanes);
   const int bx = dx ? lane_blocks(a.npix, alanes, groups, 2) : 1;
   if (dy2 != nullptr)
-    norm_bwd_apply_kernel<true><<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
+    gcc_launch(norm_bwd_apply_kernel<true>, dim3(bx, dx ? groups : 1), athreads, 0, st, 
         a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, red_param,
         (bf16*)dx, dgamma, dbeta, dalpha);
   else
-    norm_bwd_apply_kernel<false><<<dim3(bx, dx ? groups : 1), athreads, 0, st>>>(
+    gcc_launch(norm_bwd_apply_kernel<false>, dim3(bx, dx ? groups : 1), athreads, 0, st, 
         a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, nullptr, 0, 0, 0, red, red_param, (bf16*)dx, dgamma, dbeta,
         dalpha);
   GCC_CHECK_LAUNCH();

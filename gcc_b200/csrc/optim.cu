@@ -8,12 +8,16 @@ namespace gcc {
 
 // hyper (device memory): [0] lr, [1] beta1, [2] beta2, [3] eps, [4] step (as float bits of int)
 __global__ void adam_tick_kernel(float* hyper) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   int* step = reinterpret_cast<int*>(hyper + 4);
   *step += 1;
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, const float* __restrict__ hyper) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
   const int step = *reinterpret_cast<const int*>(hyper + 4);
   // bias corrections in double: 1 - beta^t = -expm1(t * log(beta))
@@ -50,6 +54,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 __global__ void l1_sparsity_kernel(const float* __restrict__ w, float* __restrict__ g, long long n, float lambda) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float x = w[i];
     g[i] += lambda * (x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f));
@@ -57,6 +63,8 @@ __global__ void l1_sparsity_kernel(const float* __restrict__ w, float* __restric
 }
 
 __global__ void clamp_kernel(float* __restrict__ x, long long n, float lo, float hi) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     x[i] = fminf(fmaxf(x[i], lo), hi);
 }
@@ -67,6 +75,8 @@ __global__ void clamp_kernel(float* __restrict__ x, long long n, float lo, float
 // coalesced bf16 writes of the direct pack along d1 and, through a shared-memory transpose, of the transposed
 // pack along d0.
 __global__ void pack_table_kernel(const long long* __restrict__ table, int count) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   __shared__ float tile[32][33];
   extern __shared__ long long cum[];  // [count + 1] running tile counts
   for (int i = threadIdx.x; i < count; i += blockDim.x) {
@@ -127,33 +137,33 @@ using namespace gcc;
 extern "C" int gcc_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float* hyper_dev,
                                  void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, st>>>(hyper_dev);
+  gcc_launch(adam_tick_kernel, 1, 1, 0, st, hyper_dev);
   GCC_CHECK_LAUNCH();
   long long b = (n / 4 + 255) / 256;
   if (b < 1) b = 1;
   if (b > 148 * 8) b = 148 * 8;
-  adam_kernel<<<(unsigned)b, 256, 0, st>>>(p, g, m, v, n, hyper_dev);
+  gcc_launch(adam_kernel, (unsigned)b, 256, 0, st, p, g, m, v, n, hyper_dev);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_l1_sparsity_f32(const float* w, float* g, long long n, float lambda, void* stream) {
   long long b = (n + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
-  l1_sparsity_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(w, g, n, lambda);
+  gcc_launch(l1_sparsity_kernel, (unsigned)b, 256, 0, (cudaStream_t)stream, w, g, n, lambda);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_clamp_f32(float* x, long long n, float lo, float hi, void* stream) {
   long long b = (n + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
-  clamp_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(x, n, lo, hi);
+  gcc_launch(clamp_kernel, (unsigned)b, 256, 0, (cudaStream_t)stream, x, n, lo, hi);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 // table: device int64 [count][8] = {src fp32 ptr, direct bf16 ptr, transposed bf16 ptr, D0, T, D1, D1p, D0p}
 extern "C" int gcc_pack_weights_table(const void* table_dev, int count, void* stream) {
   if (count <= 0) return GCC_OK;
-  pack_table_kernel<<<148 * 8, 256, sizeof(long long) * (count + 1), (cudaStream_t)stream>>>(
+  gcc_launch(pack_table_kernel, 148 * 8, 256, sizeof(long long) * (count + 1), (cudaStream_t)stream, 
       (const long long*)table_dev, count);
   GCC_CHECK_LAUNCH();
   return GCC_OK;

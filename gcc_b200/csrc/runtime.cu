@@ -11,6 +11,16 @@ void gcc_set_error(const char* file, int line, const char* msg) {
 
 extern "C" const char* gcc_last_error(void) { return g_err; }
 
+#include <stdlib.h>
+int gcc_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GCC_B200_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on;
+}
+
 unsigned long long g_gcc_launches = 0;
 extern "C" long long gcc_launch_count(void) { return (long long)g_gcc_launches; }
 

@@ -17,6 +17,8 @@ __device__ __forceinline__ uint4 pack8f(const float* f) {
 // y = x > 0 ? x : a * x, a = *slope (device memory: it is a learnable parameter)
 __global__ void prelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long nvec,
                                  const float* __restrict__ slope) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const float a = *slope;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -30,6 +32,8 @@ __global__ void prelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict_
 // dx = dy * (x > 0 ? 1 : a);  dslope += sum_{x <= 0} dy * x   (torch's prelu_backward: weight grad where x <= 0)
 __global__ void prelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
                                  long long nvec, const float* __restrict__ slope, float* __restrict__ dslope) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const float a = *slope;
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
@@ -66,6 +70,8 @@ __global__ void prelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __res
 // inverse = 1: in[n, h, w, c*4 + i*2 + j] = out[...] (the backward pass), pad channels of `in` zeroed.
 __global__ void pixel_shuffle2_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int N, int H, int W, int C,
                                       int Cin_p, int Cout_p, int inverse) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   if (!inverse) {
     const long long total = (long long)N * 2 * H * 2 * W * Cout_p;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -102,6 +108,8 @@ __global__ void pixel_shuffle2_kernel(const bf16* __restrict__ src, bf16* __rest
 
 // MaxPool2d(kernel 2, stride 2) on NHWC, H and W even.
 __global__ void maxpool2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int G) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2;
   const long long total = (long long)N * OH * OW * G;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -130,6 +138,8 @@ __global__ void maxpool2_fwd_kernel(const uint4* __restrict__ x, uint4* __restri
 // dx[window] = dy at the FIRST position (row-major scan, as ATen's max_pool2d) that holds the window maximum.
 __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
                                     int N, int H, int W, int G) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2;
   const long long total = (long long)N * OH * OW * G;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -164,6 +174,8 @@ __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __
 // y[., c] = x[., c] * scale[c] + shift[c] for c < C, 0 for pad channels (C <= 8 = one vector per pixel)
 __global__ void channel_affine8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long npix, int C,
                                        const float* __restrict__ scale, const float* __restrict__ shift) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   float sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -184,6 +196,8 @@ __global__ void channel_affine8_kernel(const uint4* __restrict__ x, uint4* __res
 __global__ void pool_linear_fwd_kernel(const float* __restrict__ sums, int Cp, int C, float inv_hw,
                                        const float* __restrict__ w, const float* __restrict__ b,
                                        bf16* __restrict__ logits) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const int n = blockIdx.x;
   float acc = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) acc += w[c] * sums[(long long)n * 2 * Cp + c] * inv_hw;
@@ -201,6 +215,8 @@ __global__ void pool_linear_fwd_kernel(const float* __restrict__ sums, int Cp, i
 // dx[n, pix, c] = dlogit[n] * w[c] / HW ;  dw[c] += sum_n dlogit[n] * sums[n][c] / HW ;  db += sum_n dlogit[n]
 __global__ void pool_linear_bwd_dx_kernel(const bf16* __restrict__ dlogit, const float* __restrict__ w, int N,
                                           long long HW, int Cp, int C, float inv_hw, bf16* __restrict__ dx) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   const long long total = (long long)N * HW * Cp;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -212,6 +228,8 @@ __global__ void pool_linear_bwd_dx_kernel(const bf16* __restrict__ dlogit, const
 __global__ void pool_linear_bwd_param_kernel(const bf16* __restrict__ dlogit, const float* __restrict__ sums, int N,
                                              int Cp, int C, float inv_hw, float* __restrict__ dw,
                                              float* __restrict__ db) {
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int n = 0; n < N; ++n) acc += __bfloat162float(dlogit[n * 8]) * sums[(long long)n * 2 * Cp + c];
@@ -237,7 +255,7 @@ using namespace gcc;
 
 extern "C" int gcc_prelu_fwd_bf16(const void* x, void* y, long long n, const float* slope_dev, void* stream) {
   if (n % 8) { gcc_set_error(__FILE__, __LINE__, "prelu: element count must be a multiple of 8"); return GCC_ERR_ARG; }
-  prelu_fwd_kernel<<<sr_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, n / 8, slope_dev);
+  gcc_launch(prelu_fwd_kernel, sr_blocks(n / 8), 256, 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)y, n / 8, slope_dev);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -246,7 +264,7 @@ extern "C" int gcc_prelu_bwd_bf16(const void* x, const void* dy, void* dx, long 
   if (n % 8) { gcc_set_error(__FILE__, __LINE__, "prelu: element count must be a multiple of 8"); return GCC_ERR_ARG; }
   int b = sr_blocks(n / 8);
   if (b > 148 * 4) b = 148 * 4;
-  prelu_bwd_kernel<<<b, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, n / 8,
+  gcc_launch(prelu_bwd_kernel, b, 256, 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)dy, (uint4*)dx, n / 8,
                                                         slope_dev, dslope);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -255,14 +273,14 @@ extern "C" int gcc_pixel_shuffle2_bf16(const void* src, void* dst, int N, int H,
                                        int inverse, void* stream) {
   if (4 * C > Cin_p || C > Cout_p) { gcc_set_error(__FILE__, __LINE__, "pixel_shuffle: bad channel counts"); return GCC_ERR_ARG; }
   const long long total = inverse ? (long long)N * H * W * Cin_p : (long long)N * 4 * H * W * Cout_p;
-  pixel_shuffle2_kernel<<<sr_blocks(total), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, N, H, W, C,
+  gcc_launch(pixel_shuffle2_kernel, sr_blocks(total), 256, 0, (cudaStream_t)stream, (const bf16*)src, (bf16*)dst, N, H, W, C,
                                                                            Cin_p, Cout_p, inverse);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_maxpool2_fwd_bf16(const void* x, void* y, int N, int H, int W, int Cp, void* stream) {
   if ((H % 2) || (W % 2) || (Cp % 8)) { gcc_set_error(__FILE__, __LINE__, "maxpool2: H, W even and Cp % 8 == 0"); return GCC_ERR_ARG; }
-  maxpool2_fwd_kernel<<<sr_blocks((long long)N * (H / 2) * (W / 2) * (Cp / 8)), 256, 0, (cudaStream_t)stream>>>(
+  gcc_launch(maxpool2_fwd_kernel, sr_blocks((long long)N * (H / 2) * (W / 2) * (Cp / 8)), 256, 0, (cudaStream_t)stream, 
       (const uint4*)x, (uint4*)y, N, H, W, Cp / 8);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -270,7 +288,7 @@ extern "C" int gcc_maxpool2_fwd_bf16(const void* x, void* y, int N, int H, int W
 extern "C" int gcc_maxpool2_bwd_bf16(const void* x, const void* dy, void* dx, int N, int H, int W, int Cp,
                                      void* stream) {
   if ((H % 2) || (W % 2) || (Cp % 8)) { gcc_set_error(__FILE__, __LINE__, "maxpool2: H, W even and Cp % 8 == 0"); return GCC_ERR_ARG; }
-  maxpool2_bwd_kernel<<<sr_blocks((long long)N * (H / 2) * (W / 2) * (Cp / 8)), 256, 0, (cudaStream_t)stream>>>(
+  gcc_launch(maxpool2_bwd_kernel, sr_blocks((long long)N * (H / 2) * (W / 2) * (Cp / 8)), 256, 0, (cudaStream_t)stream, 
       (const uint4*)x, (const uint4*)dy, (uint4*)dx, N, H, W, Cp / 8);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -278,14 +296,14 @@ extern "C" int gcc_maxpool2_bwd_bf16(const void* x, const void* dy, void* dx, in
 extern "C" int gcc_channel_affine8_bf16(const void* x, void* y, long long npix, int C, const float* scale_dev,
                                         const float* shift_dev, void* stream) {
   if (C > 8) { gcc_set_error(__FILE__, __LINE__, "channel_affine8: C must be <= 8"); return GCC_ERR_ARG; }
-  channel_affine8_kernel<<<sr_blocks(npix), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, npix, C,
+  gcc_launch(channel_affine8_kernel, sr_blocks(npix), 256, 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)y, npix, C,
                                                                            scale_dev, shift_dev);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
 extern "C" int gcc_pool_linear_fwd(const float* sums, int N, long long HW, int Cp, int C, const float* w,
                                    const float* b, void* logits, void* stream) {
-  pool_linear_fwd_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(sums, Cp, C, 1.f / (float)HW, w, b, (bf16*)logits);
+  gcc_launch(pool_linear_fwd_kernel, N, 128, 0, (cudaStream_t)stream, sums, Cp, C, 1.f / (float)HW, w, b, (bf16*)logits);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -293,12 +311,12 @@ extern "C" int gcc_pool_linear_bwd(const void* dlogit, const float* sums, const 
                                    int C, void* dx, float* dw, float* db, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (dx != nullptr) {
-    pool_linear_bwd_dx_kernel<<<sr_blocks((long long)N * HW * Cp), 256, 0, st>>>((const bf16*)dlogit, w, N, HW, Cp, C,
+    gcc_launch(pool_linear_bwd_dx_kernel, sr_blocks((long long)N * HW * Cp), 256, 0, st, (const bf16*)dlogit, w, N, HW, Cp, C,
                                                                                 1.f / (float)HW, (bf16*)dx);
     GCC_CHECK_LAUNCH();
   }
   if (dw != nullptr || db != nullptr) {
-    pool_linear_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>((const bf16*)dlogit, sums, N, Cp, C, 1.f / (float)HW, dw, db);
+    gcc_launch(pool_linear_bwd_param_kernel, (C + 127) / 128, 128, 0, st, (const bf16*)dlogit, sums, N, Cp, C, 1.f / (float)HW, dw, db);
     GCC_CHECK_LAUNCH();
   }
   return GCC_OK;

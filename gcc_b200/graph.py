@@ -119,8 +119,11 @@ class GraphedIteration:
             self.graph = self.segments[0][0]
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        # train-mode BatchNorm counts its forwards on the host (num_batches_tracked): replays add the captured count
+        # train-mode BatchNorm counts its forwards on the host (num_batches_tracked): the capture pass ran the Python
+        # code without executing a kernel (undo its count), every replay adds the captured count
         self._bn_delta = [(l, l.num_batches - b) for l, b in zip(layers, before) if l.num_batches != b]
+        for l, b in zip(layers, before):
+            l.num_batches = b
         return self
 
     # ------------------------------------------------------------------ replay

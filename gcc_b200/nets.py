@@ -117,8 +117,8 @@ class NormLayer:
         self.beta = self.arena.params[self.name + ".bias"] if self.mode == "bn" else None
         self.alpha = self.gate_arena.params[self.gate_name + ".alpha"] if self.gate_name else None
 
-    def __call__(self, x, act=ACT_NONE, act2=None, sums=None):
-        return ops.NormActFn.apply(x, self.gamma, self.beta, self.alpha, self, act, act2, sums)
+    def __call__(self, x, act=ACT_NONE, act2=None, sums=None, y_into=None, y2_into=None):
+        return ops.NormActFn.apply(x, self.gamma, self.beta, self.alpha, self, act, act2, sums, y_into, y2_into)
 
 
 class _Net(nn.Module):
@@ -282,7 +282,20 @@ class UnetGenertor(_Net):
         self._register(self._layers)
         self.seed = torch.zeros(1, dtype=torch.int64, device=self.arena.device)
 
-    def _block(self, i, a, a_relu, ca):
+    def _skip_buffer(self, i, like):
+        """Buffer of the concatenation cat[skip of level i, up output of the next level] (Pix2Pix.py:77) when both halves
+        are whole 8-channel groups and the child's up path has no dropout in between: the producers then write their
+        halves in place (zero-copy concat).  None = assemble with a copy (ops.CatFn)."""
+        j = self.next_level.get(i)
+        if j is None or not like.is_cuda:
+            return None
+        ca, uo = self.lv[i][1], self.lv[j][3]
+        if ca % 8 or uo % 8 or (self.use_dropout and self.training and j in (4, 5, 6)):
+            return None
+        n, h, w, _ = like.shape
+        return torch.empty(n, h, w, ca + uo, dtype=torch.bfloat16, device=like.device)
+
+    def _block(self, i, a, a_relu, ca, catbuf=None):
         """a = lrelu(parent activation) with ca logical channels, a_relu = relu of the same.
         Returns relu(cat[a, up_i]) and its logical channel count."""
         di, do, ui, uo = self.lv[i]
@@ -291,9 +304,10 @@ class UnetGenertor(_Net):
             rc, crc = ops.ActFn.apply(d, ACT_RELU, 0.0), do
         else:
             d, dsums = self.down[i].with_stats(a)
-            y, y2 = self.dnorm[i](d, ACT_LRELU, ACT_RELU, dsums)
+            buf = self._skip_buffer(i, d)
+            y, y2 = self.dnorm[i](d, ACT_LRELU, ACT_RELU, dsums, None, None if buf is None else (buf, 0))
             if i in self.next_level:
-                rc, crc = self._block(self.next_level[i], y, y2, do)
+                rc, crc = self._block(self.next_level[i], y, y2, do, buf)
                 feat = y
             else:                      # Identity submodule: the in-place uprelu also mutates the hooked tensor
                 rc, crc, feat = y2, do, y2
@@ -302,6 +316,9 @@ class UnetGenertor(_Net):
             if i == 3:
                 self.taps[1], self.taps[2] = (feat, do), (rc, crc)
         u, usums = self.up[i].with_stats(rc)
+        if catbuf is not None:
+            ub = self.unorm[i](u, ACT_RELU, None, usums, (catbuf, ca), None)
+            return ops.CatViewFn.apply(a_relu, ub, catbuf), ca + uo
         ub = self.unorm[i](u, ACT_RELU, None, usums)
         if self.use_dropout and i in (4, 5, 6) and self.training:
             self.seed_salt += 1
@@ -315,8 +332,9 @@ class UnetGenertor(_Net):
             self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
         di, do, ui, uo = self.lv[0]
         d0 = self.down[0](x)
-        a, a_relu = self.dnorm[0](d0, ACT_LRELU, ACT_RELU)
-        r, cr = self._block(self.next_level[0], a, a_relu, do)
+        buf = self._skip_buffer(0, d0)
+        a, a_relu = self.dnorm[0](d0, ACT_LRELU, ACT_RELU, None, None, None if buf is None else (buf, 0))
+        r, cr = self._block(self.next_level[0], a, a_relu, do, buf)
         return self.up[0](r, ACT_TANH)
 
 

@@ -353,26 +353,48 @@ class HeadConvFn(torch.autograd.Function):
 
 class NormActFn(torch.autograd.Function):
     """[BatchNorm | InstanceNorm | identity] -> [channel gate] -> activation, with an optional second
-    activation output (the U-Net's relu'd skip copy)."""
+    activation output (the U-Net's relu'd skip copy).
+
+    ``y_into`` / ``y2_into`` = (buffer [N,H,W,Ct], channel offset): the output is written straight into that channel
+    window of a wider NHWC buffer and returned as a view of it -- the U-Net writes both halves of every skip
+    concatenation (models/Pix2Pix.py:77) this way, so ``torch.cat`` costs no copy (see ``CatViewFn``)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, alpha, layer, act, act2, sums_in=None):
+    def forward(ctx, x, gamma, beta, alpha, layer, act, act2, sums_in=None, y_into=None, y2_into=None):
         _check(x)
         x = x.contiguous()
         n, h, w, cp = x.shape
         st = _st()
         mode = layer.mode  # 'bn', 'in', 'id'
         per_sample = 1 if mode == "in" else 0
-        y = torch.empty_like(x)
-        y2 = torch.empty_like(x) if act2 is not None else None
+        if y_into is not None and act2 is not None:
+            raise _lib.GccB200Error("a windowed primary output excludes a second output")
+        y = torch.empty_like(x) if y_into is None else None
+        # kernel slots: (y pointer, second pointer + pitch + offset + activation)
+        if y_into is not None:
+            buf, coff = y_into
+            k_y, k_y2, k_cp2, k_off2, k_act2 = None, buf.data_ptr(), buf.shape[3], coff, act
+            yret = buf[..., coff:coff + cp]
+            y2ret = None
+        elif act2 is not None:
+            if y2_into is not None:
+                buf, coff = y2_into
+                k_y2, k_cp2, k_off2 = buf.data_ptr(), buf.shape[3], coff
+                y2ret = buf[..., coff:coff + cp]
+            else:
+                y2ret = torch.empty_like(x)
+                k_y2, k_cp2, k_off2 = y2ret.data_ptr(), cp, 0
+            k_y, k_act2, yret = y.data_ptr(), act2, y
+        else:
+            k_y, k_y2, k_cp2, k_off2, k_act2, yret, y2ret = y.data_ptr(), None, cp, 0, 0, y, None
         gp = None if gamma is None else gamma.data_ptr()
         bp = None if beta is None else beta.data_ptr()
         ap = None if alpha is None else alpha.data_ptr()
         sums = None
         if mode == "bn" and not layer.training:
-            call("gcc_norm_apply_eval_bf16", x.data_ptr(), y.data_ptr(), n, h * w, cp, layer.c,
+            call("gcc_norm_apply_eval_bf16", x.data_ptr(), k_y, n, h * w, cp, layer.c,
                  layer.running_mean.data_ptr(), layer.running_var.data_ptr(), gp, bp, ap, layer.thr, BN_EPS, act,
-                 layer.slope, None if y2 is None else y2.data_ptr(), cp, 0, act2 or 0, st)
+                 layer.slope, k_y2, k_cp2, k_off2, k_act2, st)
             ctx.eval_bn = True
             ctx.stat_count = 0
         else:
@@ -394,17 +416,17 @@ class NormActFn(torch.autograd.Function):
             if mode == "bn" and layer.running_mean is not None:
                 rm, rv = layer.running_mean.data_ptr(), layer.running_var.data_ptr()
                 layer.num_batches += 1
-            call("gcc_norm_apply_bf16", x.data_ptr(), y.data_ptr(), n, h * w, cp, layer.c, per_sample,
+            call("gcc_norm_apply_bf16", x.data_ptr(), k_y, n, h * w, cp, layer.c, per_sample,
                  None if sums is None else sums.data_ptr(), gp, bp, ap, layer.thr, BN_EPS, rm, rv, BN_MOM, act,
                  layer.slope, 1 if (getattr(layer, "gate_after", mode == "id") and mode == "id" and alpha is not None) else 0,
-                 None if y2 is None else y2.data_ptr(), cp, 0, act2 or 0, stat_count, st)
+                 k_y2, k_cp2, k_off2, k_act2, stat_count, st)
             ctx.stat_count = stat_count
         ctx.layer, ctx.act, ctx.act2 = layer, act, act2
         ctx.save_for_backward(x, sums, gamma, beta, alpha)
         ctx.set_materialize_grads(False)
-        if y2 is None:
-            return y
-        return y, y2
+        if y2ret is None:
+            return yret
+        return yret, y2ret
 
     @staticmethod
     def backward(ctx, dy, dy2=None):
@@ -447,7 +469,28 @@ class NormActFn(torch.autograd.Function):
             bwd(2, red_local)
         else:
             bwd(0, None)
-        return dx, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None, None
+
+
+class CatViewFn(torch.autograd.Function):
+    """torch.cat([a, b], channel) where a and b already ARE the two channel windows of ``buf`` (written there by their
+    producers, ``NormActFn(..., y_into / y2_into)``): no copy in forward, channel-window views of the gradient in
+    backward."""
+
+    @staticmethod
+    def forward(ctx, a, b, buf):
+        ca, cb = a.shape[3], b.shape[3]
+        ok = (a.data_ptr() == buf.data_ptr() and b.data_ptr() == buf.data_ptr() + 2 * ca and ca + cb == buf.shape[3]
+              and a.stride() == b.stride() == buf.stride())
+        if not ok:
+            raise _lib.GccB200Error("CatViewFn: the inputs are not the two channel windows of the buffer")
+        ctx.ca = ca
+        return buf.view(buf.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        ca = ctx.ca
+        return dy[..., :ca], dy[..., ca:], None
 
 
 class ActFn(torch.autograd.Function):

@@ -17,7 +17,7 @@ from collections import OrderedDict
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .arena import ParamArena, rp8
 from .nets import ConvLayer, NormLayer, _Tree
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, GAN_MODES, _check, _st, call, conv_out_hw
@@ -122,8 +122,10 @@ class AttnFn(torch.autograd.Function):
         L = h * w
         probs = torch.empty(n, L, L, dtype=torch.bfloat16, device=v.device)
         out = torch.empty_like(v)
+        nb = _lib.lib().gcc_attn_workspace_bytes(n, L, q.shape[3], cp, 0)
+        ws = torch.empty(nb, dtype=torch.uint8, device=v.device)
         call("gcc_attn_fwd_bf16", q.data_ptr(), k.data_ptr(), v.data_ptr(), n, L, d, q.shape[3], c, cp, probs.data_ptr(),
-             out.data_ptr(), _st())
+             out.data_ptr(), ws.data_ptr(), nb, _st())
         ctx.args = (n, L, d, c)
         ctx.save_for_backward(q, k, v, probs)
         return out
@@ -135,8 +137,10 @@ class AttnFn(torch.autograd.Function):
         dout = dout.contiguous()
         de = torch.empty_like(probs)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        nb = _lib.lib().gcc_attn_workspace_bytes(n, L, q.shape[3], v.shape[3], 1)
+        ws = torch.empty(nb, dtype=torch.uint8, device=v.device)
         call("gcc_attn_bwd_bf16", q.data_ptr(), k.data_ptr(), v.data_ptr(), probs.data_ptr(), dout.data_ptr(), n, L, d,
-             q.shape[3], c, v.shape[3], de.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _st())
+             q.shape[3], c, v.shape[3], de.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), nb, _st())
         return dq, dk, dv, None, None
 
 

@@ -218,11 +218,17 @@ int gcc_spectral_norm_bwd(const float* dw_eff, const float* w_bar, const float* 
                           const float* t_saved, int height, int width, float* dw_bar, float* du, float* dv, float* scratch1,
                           void* stream);
 /* Self_Attn core (models/SAGAN.py:96-104): q, k bf16 [N][L][dp] (d logical channels), v bf16 [N][L][Cp];
- * probs bf16 [N][L][L] = softmax_j(q_i . k_j), out[n][i][c] = sum_j probs[i][j] v[j][c]. */
+ * probs bf16 [N][L][L] = softmax_j(q_i . k_j), out[n][i][c] = sum_j probs[i][j] v[j][c].
+ * The two matrix products run as batched tcgen05 GEMMs (one weight matrix per image), the logits stay fp32 until the
+ * softmax; backward: dprobs = dout v^T and dq = de k on the same kernel, dk = de^T q and dv = probs^T dout on the
+ * batched weight-gradient kernel.  ws: device scratch of gcc_attn_workspace_bytes(N, L, dp, Cp, backward) bytes;
+ * de_scratch: bf16 [N][L][L]. */
+long long gcc_attn_workspace_bytes(int N, int L, int dp, int Cp, int backward);
 int gcc_attn_fwd_bf16(const void* q, const void* k, const void* v, int N, int L, int d, int dp, int C, int Cp, void* probs,
-                      void* out, void* stream);
+                      void* out, void* ws, long long ws_bytes, void* stream);
 int gcc_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* probs, const void* dout, int N, int L,
-                      int d, int dp, int C, int Cp, void* de_scratch, void* dq, void* dk, void* dv, void* stream);
+                      int d, int dp, int C, int Cp, void* de_scratch, void* dq, void* dk, void* dv, void* ws,
+                      long long ws_bytes, void* stream);
 /* out = gamma * a + x (Self_Attn's residual, :106); bwd: da = gamma dy, dgamma += sum dy a (dx = dy) */
 int gcc_scale_add_bf16(const void* a, const void* x, const float* gamma_dev, void* y, long long n, void* stream);
 int gcc_scale_add_bwd_bf16(const void* dy, const void* a, const float* gamma_dev, void* da, float* dgamma, long long n,

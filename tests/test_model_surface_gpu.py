@@ -65,7 +65,8 @@ def test_checkpoint_roundtrip(cuda, tmp_path):
     a = Pix2PixModel(opt)
     a.save_models(3, str(tmp_path), fid=12.5)
     ckpt = torch.load(os.path.join(tmp_path, "model_3.pth"), map_location="cpu")
-    assert set(ckpt) == {"G", "D", "epoch", "cfg", "fid"} and ckpt["cfg"] == (None, None)
+    # the reference's keys (models/Pix2Pix.py:636-647) plus ONE extra entry with the resume state (optimizer moments, ...)
+    assert set(ckpt) == {"G", "D", "epoch", "cfg", "fid", "gcc_b200"} and ckpt["cfg"] == (None, None)
     w = ckpt["G"]["model.model.0.weight"]
     assert w.shape == (8, 3, 4, 4) and w.is_contiguous() and w.dtype == torch.float32  # reference layout: NCHW fp32
     b = Pix2PixModel(opt)

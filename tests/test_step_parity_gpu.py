@@ -105,6 +105,13 @@ def test_gcc_iteration_matches_oracle(name):
     # ---- oracle
     S.set_input(A, B)
     S.optimize_parameters()
+    # ---- the same step on the oracle with the B200 path's bf16 storage emulated (oracle/bf16_emulation.py): the
+    # reference arithmetic rounded where the kernels round -- the tight bound for the cancellation-prone gradients
+    from oracle import bf16_emulation as E
+    with E.emulating(O):
+        S16, T16 = O.build_pair(O.Opt(backbone=backbone, direction=S.opt.direction, **tiny), cfgs[0], cfgs[1])
+        S16.set_input(E.bf(A), E.bf(B))
+        S16.optimize_parameters()
     # ---- B200
     model.set_input({"A": A, "B": B, "A_paths": "", "B_paths": ""})
     model.optimize_parameters()
@@ -131,6 +138,14 @@ def test_gcc_iteration_matches_oracle(name):
                {k: v.grad for k, v in S.D.items() if v.dtype == torch.float32 and not k.endswith("alpha")})
     _cmp_grads(report, "T.G", _arena_grads(teacher.arena_G), {k: v.grad for k, v in T.G.items() if v.dtype == torch.float32})
     _cmp_grads(report, "T.D", _arena_grads(teacher.arena_D), {k: v.grad for k, v in T.D.items() if v.dtype == torch.float32})
+    emu = {}
+    _cmp_grads(emu, "S.G", _arena_grads(model.arena_G), {k: v.grad for k, v in S16.G.items() if v.dtype == torch.float32})
+    _cmp_grads(emu, "S.D", _arena_grads(model.arena_D),
+               {k: v.grad for k, v in S16.D.items() if v.dtype == torch.float32 and not k.endswith("alpha")})
+    _cmp_grads(emu, "T.G", _arena_grads(teacher.arena_G), {k: v.grad for k, v in T16.G.items() if v.dtype == torch.float32})
+    _cmp_grads(emu, "T.D", _arena_grads(teacher.arena_D), {k: v.grad for k, v in T16.D.items() if v.dtype == torch.float32})
+    emu.pop("_worst", None)
+    report["vs_bf16_oracle"] = emu
     # BN running statistics after the 11 D / 4 G forwards of the iteration
     sd = model.netD.state_dict()
     for k, v in S.D.items():
@@ -162,7 +177,7 @@ def test_gcc_iteration_matches_oracle(name):
 
     bad = []
     for k, v in report.items():
-        if k in ("losses", "_worst"):
+        if k in ("losses", "_worst", "vs_bf16_oracle"):
             continue
         if k.endswith(".cos"):
             if v < (0.99 if (".D." in k or backbone == "resnet") else 0.995):
