@@ -38,6 +38,7 @@ class ParamArena:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.finalized = False
         self.dirty = True
+        self.version = 0        # bumped by every re-pack: derived operand caches (ops.StemConvFn ...) key on it
 
     def add(self, name, shape, kind="vec"):
         """kind: 'conv' (O,I,KH,KW), 'convT' (I,O,KH,KW) or 'vec' (anything, stored contiguous); 'conv_nopack' /
@@ -121,6 +122,7 @@ class ParamArena:
             if self.table_count:
                 _lib.call("gcc_pack_weights_table", self.table.data_ptr(), self.table_count, _lib.current_stream())
             self.dirty = False
+            self.version += 1
 
     def state(self):
         return {"M": self.M, "V": self.V, "hyper": self.hyper}

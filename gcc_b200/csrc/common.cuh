@@ -28,11 +28,11 @@ extern unsigned long long g_gcc_launches;  // kernels launched by this library (
 
 void gcc_set_error(const char* file, int line, const char* msg);
 
-// Every kernel of the library is launched with the programmatic-stream-serialization attribute (programmatic
-// dependent launch): the grid may be scheduled while its predecessor in the stream drains; the kernel's first
-// instruction, griddepcontrol.wait, blocks until the predecessor has completed and its memory is visible.  With
-// ~800 launches per GCC iteration the launch latency and the ramp of each kernel overlap the tail of the previous
-// one instead of adding up.  GCC_B200_PDL=0 (read once) launches everything with plain stream order.
+// Every kernel of the library can be launched with the programmatic-stream-serialization attribute (programmatic
+// dependent launch, GCC_B200_PDL=1, read once): the grid may be scheduled while its predecessor in the stream drains;
+// the kernel's griddepcontrol.wait blocks until the predecessor has completed and its memory is visible.  Measured on
+// the captured pix2pix iteration (786 launches, round 2): 32.21 ms with, 32.02 ms without -- inside a CUDA graph the
+// kernel-to-kernel gaps are already below what the early launch saves, so plain stream order is the default.
 int gcc_pdl_enabled();
 template <typename... KArgs, typename... Args>
 static inline cudaError_t gcc_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -270,7 +270,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                          const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH, int KW,
                          int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
-                         long long ws_elems, float* stats, int stats_ld, int f32_out, void* stream);
+                         long long ws_elems, float* stats, int stats_ld, int f32_out, int rowwin, void* stream);
 extern "C" int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void* q, int H, int W, int Cq,
                                    float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched,
                                    int accumulate, float scale, void* stream);

@@ -721,6 +721,18 @@ static int make_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int 
   return gcc_make_tmap_bf16_sw(m, base, 4, dims, strides, box, c8 ? 0 : 1);
 }
 
+// Row-window view of an 8-channel NHWC image [N][Hrows][Wp][8] (see elementwise.cu, "stem / head convolutions"):
+// dim 0 = 64 contiguous elements = 8 pixels x 8 channels starting at a window position, dim 1 = window position
+// (stride ONE pixel = 16 bytes: the windows overlap), dim 2 = image row, dim 3 = image.  A window that starts in the
+// last 7 pixels of a row runs into the next row / image (finite data, multiplied by zero weights); the caller keeps
+// >= 128 readable bytes behind the last image.
+static int make_rowwin_map(CUtensorMap* m, const void* x, int N, int Hrows, int Wp, int lw, int lh, int ln) {
+  uint64_t dims[4] = {64, (uint64_t)Wp, (uint64_t)Hrows, (uint64_t)N};
+  uint64_t strides[3] = {16, (uint64_t)Wp * 16, (uint64_t)Hrows * Wp * 16};
+  uint32_t box[4] = {64u, 1u << lw, 1u << lh, 1u << ln};
+  return gcc_make_tmap_bf16_sw(m, x, 4, dims, strides, box, 1);
+}
+
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // per-device caches (one process may drive several devices): function attributes and the SM count
@@ -842,8 +854,15 @@ static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
 int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                          const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH, int KW,
                          int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
-                         long long ws_elems, float* stats, int stats_ld, int f32_out, void* stream) {
+                         long long ws_elems, float* stats, int stats_ld, int f32_out, int rowwin, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // rowwin = 1: x is a pre-padded 8-channel image [N][H][W][8] followed by >= 128 readable bytes, w = [R][KH * KB][64]
+  // with KB = ceil(KW / 8) (gcc_rowwin_weight_pack_bf16), T = KH * KB, Cw = 64, stride 1, pad 0.
+  if (rowwin && (transposed || w_per_image || Cx != 8 || Cw != 64 || stride != 1 || pad != 0 || T != KH * ((KW + 7) / 8) ||
+                 OH + KH - 1 > H || OW + KW - 1 > W)) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm: bad row-window arguments");
+    return GCC_ERR_ARG;
+  }
   if (f32_out && (splitk_ws == nullptr || stats != nullptr || bias != nullptr || act != 0)) {
     gcc_set_error(__FILE__, __LINE__, "conv gemm: fp32 output needs a workspace and excludes bias / activation / statistics");
     return GCC_ERR_ARG;
@@ -856,7 +875,7 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: per-image weights need a 1x1 stride-1 conv");
     return GCC_ERR_ARG;
   }
-  if ((Cx % 8) || (Cw % 8) || (Cy % 8) || (y_coff % 8) || T != KH * KW || (stride != 1 && stride != 2) ||
+  if ((Cx % 8) || (Cw % 8) || (Cy % 8) || (y_coff % 8) || (!rowwin && T != KH * KW) || (stride != 1 && stride != 2) ||
       KH * KW > kMaxTaps) {
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: bad arguments");
     return GCC_ERR_ARG;
@@ -871,10 +890,10 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     return GCC_ERR_ARG;
   }
   const int BN = pick_block_n(Rp);
-  const int Ck = Cx < Cw ? Cx : Cw;  // contraction extent (both are zero padded to their physical size)
+  const int Ck = rowwin ? 64 : (Cx < Cw ? Cx : Cw);  // contraction extent (both are zero padded to their physical size)
 
   // 8-channel image input with a multiple of 8 taps (k4 convs): gather taps x channels into K = T * 8
-  const int c8 = (!transposed && !w_per_image && Cx == 8 && Cw == 8 && (T % 8) == 0 && !(g_debug_flags & 128)) ? 1 : 0;
+  const int c8 = (!rowwin && !transposed && !w_per_image && Cx == 8 && Cw == 8 && (T % 8) == 0 && !(g_debug_flags & 128)) ? 1 : 0;
   ConvGeom2 g;
   memset(&g, 0, sizeof(g));
   g.c8 = c8;
@@ -897,7 +916,16 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
   for (int cls = 0; cls < classes; ++cls) {
     int GH, GW, qh = 0, qw = 0;
     const int tap_begin = ntap;
-    if (!transposed) {
+    if (rowwin) {
+      GH = OH; GW = OW;
+      const int KB = (KW + 7) / 8;
+      for (int kh = 0; kh < KH; ++kh)
+        for (int kb = 0; kb < KB; ++kb) {
+          g.tap_map[ntap] = 0; g.tap_dh[ntap] = (short)kh; g.tap_dw[ntap] = (short)(kb * 8);
+          g.tap_widx[ntap] = (short)(kh * KB + kb);
+          ++ntap;
+        }
+    } else if (!transposed) {
       GH = OH; GW = OW;
       GemmGeom tmp;
       int rc = fill_gather_taps(tmp, KH, KW, stride, pad);
@@ -948,7 +976,9 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
   const int m_total = g.cls_mtile_begin[ncls];
 
   int rc = 0;
-  if (!transposed && stride == 2) {
+  if (rowwin) {
+    rc |= make_rowwin_map(&g.a_maps[0], x, N, H, W, g.log_wt, g.log_ht, g.log_nt);
+  } else if (!transposed && stride == 2) {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
         rc |= make_act_map(&g.a_maps[ph * 2 + pw], x, N, H, W, Cx, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt, c8);
@@ -1047,16 +1077,29 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
                                   int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
                                   float* splitk_ws, long long ws_elems, float* stats, int stats_ld, void* stream) {
   return gcc_conv_gemm_launch(x, N, H, W, Cx, w, R, T, Cw, bias, y, OH, OW, Cy, y_coff, transposed, KH, KW, stride, pad,
-                              act, slope, w_per_image, splitk_ws, ws_elems, stats, stats_ld, 0, stream);
+                              act, slope, w_per_image, splitk_ws, ws_elems, stats, stats_ld, 0, 0, stream);
+}
+
+extern "C" int gcc_conv_rowwin_bf16(const void* x, int N, int Hrows, int Wp, const void* w_rowpack, int R, int KH, int KW,
+                                    const float* bias, void* y, int OH, int OW, int Cy, int act, float slope, float* stats,
+                                    int stats_ld, void* stream) {
+  return gcc_conv_gemm_launch(x, N, Hrows, Wp, 8, w_rowpack, R, KH * ((KW + 7) / 8), 64, bias, y, OH, OW, Cy, 0, 0, KH, KW, 1,
+                              0, act, slope, 0, nullptr, 0, stats, stats_ld, 0, 1, stream);
 }
 
 // dW[b][r][t][c] (+)= scale * sum_{pix} P[n, oh, ow, r] * Q[n, s*oh + kh - p, s*ow + kw - p, c]
 // P: [N, OH, OW, Cp] bf16, Q: [N, H, W, Cq] bf16, dW fp32 [batch?][R][KH*KW][C].
-extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int Cp, const void* qmat, int H, int W,
-                                   int Cq, float* dw, int R, int C, int KH, int KW, int stride, int pad,
-                                   int batched, int accumulate, float scale, void* stream) {
+static int gcc_wgrad_gemm_launch(const void* pmat, int N, int OH, int OW, int Cp, const void* qmat, int H, int W, int Cq,
+                                 float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched,
+                                 int accumulate, float scale, int rowwin, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if ((Cp % 8) || (Cq % 8) || (stride != 1 && stride != 2) || KH * KW > kMaxTaps || R > Cp || C > Cq) {
+  // rowwin = 1: q is the pre-padded 8-channel image of the row-window stem, C = 64 (8 taps x 8 channels per kernel-row
+  // block), dw = fp32 [R][KH * KB][64]
+  if (rowwin && (batched || Cq != 8 || C != 64 || stride != 1 || pad != 0 || OH + KH - 1 > H || OW + KW - 1 > W)) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_wgrad_gemm: bad row-window arguments");
+    return GCC_ERR_ARG;
+  }
+  if ((Cp % 8) || (Cq % 8) || (stride != 1 && stride != 2) || KH * KW > kMaxTaps || R > Cp || (!rowwin && C > Cq)) {
     gcc_set_error(__FILE__, __LINE__, "gcc_wgrad_gemm_bf16: bad arguments");
     return GCC_ERR_ARG;
   }
@@ -1066,7 +1109,18 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
   }
   GemmGeom g;
   memset(&g, 0, sizeof(g));
-  int rc = fill_gather_taps(g, KH, KW, stride, pad);
+  int rc = 0;
+  const int KB = (KW + 7) / 8;
+  if (rowwin) {
+    g.num_taps = KH * KB;
+    for (int kh = 0; kh < KH; ++kh)
+      for (int kb = 0; kb < KB; ++kb) {
+        const int t = kh * KB + kb;
+        g.tap_map[t] = 0; g.tap_dh[t] = (short)kh; g.tap_dw[t] = (short)(kb * 8); g.tap_widx[t] = (short)t;
+      }
+  } else {
+    rc = fill_gather_taps(g, KH, KW, stride, pad);
+  }
   if (rc) return rc;
   g.GN = N; g.GH = OH; g.GW = OW;
   if (batched) {
@@ -1085,10 +1139,12 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
 
   // 8-channel image on the Q side of a 16-tap conv: all taps become columns of ONE 128-wide tile
   // (dw is then the dense [R][16 * 8] matrix; the caller drops the padded channels)
-  const int c8 = (!batched && Cq == 8 && C == 8 && KH * KW == 16 && !(g_debug_flags & 128)) ? 1 : 0;
+  const int c8 = (!rowwin && !batched && Cq == 8 && C == 8 && KH * KW == 16 && !(g_debug_flags & 128)) ? 1 : 0;
   g.c8 = c8;
   rc = make_act_map(&g.p_map, pmat, N, OH, OW, Cp, 1, 0, 0, g.log_wt, g.log_ht, g.log_nt);
-  if (stride == 2) {
+  if (rowwin) {
+    rc |= make_rowwin_map(&g.a_maps[0], qmat, N, H, W, g.log_wt, g.log_ht, g.log_nt);
+  } else if (stride == 2) {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
         rc |= make_act_map(&g.a_maps[ph * 2 + pw], qmat, N, H, W, Cq, 2, ph, pw, g.log_wt, g.log_ht, g.log_nt, c8);
@@ -1139,9 +1195,9 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
   g.dw = dw;
   g.R = R;
   g.C = C;
-  g.T_total = KH * KW;
+  g.T_total = rowwin ? KH * KB : KH * KW;
   if (splits > 1 && !accumulate) {
-    const size_t bytes = (size_t)(batched ? N : 1) * R * KH * KW * C * sizeof(float);
+    const size_t bytes = (size_t)(batched ? N : 1) * R * g.T_total * C * sizeof(float);
     if (cudaMemsetAsync(dw, 0, bytes, st) != cudaSuccess) return GCC_ERR_CUDA;
   }
   dim3 grid(r_tiles, c_tiles, g.num_taps * splits * (batched ? N : 1));
@@ -1154,4 +1210,15 @@ extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int 
   trace_end(st, "wgrad", N, H, W, C, R, OH, OW, KH, stride, batched, BN * 10 + MT, base_ctas, splits, total_pb, 0,
             2.0 * N * OH * OW * (double)R * C * KH * KW);
   return rc;
+}
+
+extern "C" int gcc_wgrad_gemm_bf16(const void* pmat, int N, int OH, int OW, int Cp, const void* qmat, int H, int W,
+                                   int Cq, float* dw, int R, int C, int KH, int KW, int stride, int pad,
+                                   int batched, int accumulate, float scale, void* stream) {
+  return gcc_wgrad_gemm_launch(pmat, N, OH, OW, Cp, qmat, H, W, Cq, dw, R, C, KH, KW, stride, pad, batched, accumulate, scale,
+                               0, stream);
+}
+extern "C" int gcc_wgrad_rowwin_bf16(const void* dy, int N, int OH, int OW, int Cp, const void* x, int Hrows, int Wp, float* dw,
+                                     int R, int KH, int KW, void* stream) {
+  return gcc_wgrad_gemm_launch(dy, N, OH, OW, Cp, x, Hrows, Wp, 8, dw, R, 64, KH, KW, 1, 0, 0, 0, 1.f, 1, stream);
 }

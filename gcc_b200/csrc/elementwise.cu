@@ -522,6 +522,93 @@ __global__ void dw3x3_bwd_data_padded_kernel(const bf16* __restrict__ dy, const 
                                                   pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
   }
 }
+// Row-sliding weight / bias gradient of the depthwise conv (same thread layout and items as dw3x3_rows_kernel): the
+// 3 x 3 window of x slides along the row (3 new loads + one dy load per pixel), 72 + 8 accumulators per thread, one
+// shared-memory reduction over the CTA's pixel lanes and one atomic per (CTA, channel, tap).
+__global__ void __launch_bounds__(256)
+dw3x3_wgrad_rows_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
+                        float* __restrict__ dbias, int H, int W, int G, int C, int lanes, int seg, long long items) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ float sred[];  // [lanes][G][80]
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  float acc[3][3][8], accb[8];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[a][b][k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) accb[k] = 0.f;
+  if (lane < lanes) {
+    const int segs = (W + seg - 1) / seg;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const uint4* dv = reinterpret_cast<const uint4*>(dy);
+    for (long long it = (long long)blockIdx.x * lanes + lane; it < items; it += (long long)gridDim.x * lanes) {
+      const int sgi = (int)(it % segs);
+      const long long t = it / segs;
+      const int r = (int)(t % H);
+      const long long n = t / H;
+      const int w0 = sgi * seg, w1 = min(W, w0 + seg);
+      long long rowoff[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) rowoff[a] = ((n * H + reflect(r + a - 1, H)) * (long long)W) * G + g;
+      const long long dyoff = ((n * H + r) * (long long)W) * G + g;
+      uint4 win[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        win[a][0] = xv[rowoff[a] + (long long)reflect(w0 - 1, W) * G];
+        win[a][1] = xv[rowoff[a] + (long long)w0 * G];
+      }
+      for (int ow = w0; ow < w1; ++ow) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) win[a][2] = xv[rowoff[a] + (long long)reflect(ow + 1, W) * G];
+        const uint4 du = dv[dyoff + (long long)ow * G];
+        const float d8[8] = {bf16_lo(du.x), bf16_hi(du.x), bf16_lo(du.y), bf16_hi(du.y),
+                             bf16_lo(du.z), bf16_hi(du.z), bf16_lo(du.w), bf16_hi(du.w)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) accb[k] += d8[k];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            const uint4 u = win[a][b];
+            const float x8[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                                 bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[a][b][k] += d8[k] * x8[k];
+          }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          win[a][0] = win[a][1];
+          win[a][1] = win[a][2];
+        }
+      }
+    }
+    float* rr = sred + ((long long)lane * G + g) * 80;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) rr[k * 10 + a * 3 + b] = acc[a][b][k];
+      rr[k * 10 + 9] = accb[k];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < G * 80; e += blockDim.x) {
+    const int gg = e / 80, kj = e % 80;
+    const int k = kj / 10, j = kj % 10;
+    const int c = gg * 8 + k;
+    if (c >= C) continue;
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += sred[((long long)l * G + gg) * 80 + kj];
+    if (j < 9) atomicAdd(dw + c * 9 + j, a);
+    else if (dbias) atomicAdd(dbias + c, a);
+  }
+}
+
 // weight / bias gradient: dw[c][k] = sum_{n,h,w} dy[n,h,w,c] * x[n, refl(h+kh-1), refl(w+kw-1), c]
 // block = (G groups) x lanes; per-thread 8 channels x 10 accumulators; smem reduce; atomics.
 __global__ void dw3x3_bwd_weight_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
@@ -813,6 +900,202 @@ __global__ void image_pool_scatter_kernel(const uint4* __restrict__ images, uint
     o[v] = s[v];
 }
 
+// ---- stem / head convolutions with <= 4 (8) channels on the image side and a large kernel (k7 of the MobileResNet
+// generator, Pix2Pix.py:216,259; k9 of the SRResNet, SRGAN.py:150,190; k3 of VGG's first conv) ---------------------
+// As implicit GEMMs these layers waste the tensor cores: the stem has K = 3 channels per tap (a 64-wide k-block per tap
+// is 95 % zeros), the head has N = 3 output columns.  Instead:
+//   stem ("row window"):  the taps of one kernel ROW are contiguous in an 8-channel NHWC image (kw pixels x 8
+//        channels = 16 kw bytes), so a TMA tensor map with a 16-byte stride between window positions delivers, per
+//        kernel row, a K-major [pixels][8 kw x 8 c] operand tile; K = KH x ceil(KW / 8) x 64 (conv_gemm.cu, rowwin).
+//   head ("fold"):        one 1x1 GEMM over the (padded) input computes every tap's partial dot product,
+//        ycol[pix][(tap, c)] = x[pix, :] . w[c][tap][:], and fold sums the KH*KW shifted partials per output pixel.
+// Column index of a (tap, channel) pair: tap * CG + c with CG = 4 or 8 channels per group.
+
+// y[n,oy,ox,c] = act(bias[c] + sum_{kh,kw} ycol[n, oy + dir*kh + off, ox + dir*kw + off, (kh*KW+kw)*CG + c])
+// (terms outside the ycol grid are skipped).  dir = +1, off = 0: forward of a stride-1 conv over a pre-padded input;
+// dir = -1, off = 0 with a ycol grid of the OUTPUT size: its data gradient on the padded input grid.
+template <int CG>
+__global__ void fold_taps_kernel(const bf16* __restrict__ ycol, int Ccol, int KH, int KW, int C, const float* __restrict__ bias,
+                                 int act, uint4* __restrict__ y, int N, int GH, int GW, int OH, int OW, int dir, int off) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long total = (long long)N * OH * OW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW);
+    long long t = i / OW;
+    const int oy = (int)(t % OH);
+    const long long n = t / OH;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = (bias != nullptr && c < C) ? bias[c] : 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int gy = oy + dir * kh + off;
+      if (gy < 0 || gy >= GH) continue;
+      const bf16* rowp = ycol + ((n * GH + gy) * (long long)GW) * Ccol + kh * KW * CG;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int gx = ox + dir * kw + off;
+        if (gx < 0 || gx >= GW) continue;
+        const bf16* p = rowp + (long long)gx * Ccol + kw * CG;
+        if (CG == 4) {
+          const uint2 u = *reinterpret_cast<const uint2*>(p);
+          acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+        } else {
+          const uint4 u = *reinterpret_cast<const uint4*>(p);
+          acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+          acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = (c < C) ? (act == 2 ? tanhf(acc[c]) : acc[c]) : 0.f;
+    y[i] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                      pack_bf16(acc[6], acc[7]));
+  }
+}
+// dcol[n,gy,gx,(kh*KW+kw)*CG + c] = dy[n, gy - kh - off, gx - kw - off, c] (zero outside the dy grid and in the column padding):
+// the operand of the head conv's data- and weight-gradient GEMMs.  One thread per (pixel, 16-byte column chunk).
+template <int CG>
+__global__ void unfold_taps_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dcol, int Ccol, int KH, int KW, int N,
+                                   int GH, int GW, int OH, int OW, int off) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int chunks = Ccol / 8;
+  const long long total = (long long)N * GH * GW * chunks;
+  constexpr int TPC = 8 / CG;  // taps per 16-byte chunk
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    long long t = i / chunks;
+    const int gx = (int)(t % GW); t /= GW;
+    const int gy = (int)(t % GH);
+    const long long n = t / GH;
+    uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < TPC; ++j) {
+      const int tap = ch * TPC + j;
+      if (tap >= KH * KW) break;
+      const int oy = gy - tap / KW - off, ox = gx - tap % KW - off;
+      if (oy < 0 || oy >= OH || ox < 0 || ox >= OW) continue;
+      const bf16* p = dy + ((n * OH + oy) * (long long)OW + ox) * 8;
+      if (CG == 4) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        o[2 * j] = u.x;
+        o[2 * j + 1] = u.y;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        o[0] = u.x; o[1] = u.y; o[2] = u.z; o[3] = u.w;
+      }
+    }
+    reinterpret_cast<uint4*>(dcol)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+// Weight operands of the fold path from the arena's bf16 packs:
+//   mode 0: out[(t*CG + c)][k]   = direct[c][t][k]       (c < C, k < Kp)     rows = round8(T*CG), pitch Kp
+//   mode 1: out[k][t*CG + c]     = transposed[k][t][c]   (c < C)             rows = K, pitch round8(T*CG); src pitch Cp
+__global__ void fold_weight_pack_kernel(const bf16* __restrict__ src, bf16* __restrict__ out, int mode, int C, int T, int CG,
+                                        int K, int Kp, int Cp, int rows_p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (mode == 0) {
+    const long long total = (long long)rows_p * Kp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int k = (int)(i % Kp);
+      const int row = (int)(i / Kp);
+      const int t = row / CG, c = row % CG;
+      out[i] = (t < T && c < C) ? src[((long long)c * T + t) * Kp + k] : __float2bfloat16(0.f);
+    }
+  } else {
+    const long long total = (long long)K * rows_p;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int col = (int)(i % rows_p);
+      const int k = (int)(i / rows_p);
+      const int t = col / CG, c = col % CG;
+      out[i] = (t < T && c < C) ? src[((long long)k * T + t) * Cp + c] : __float2bfloat16(0.f);
+    }
+  }
+}
+// g[c][t][k] += tmp[(t*CG + c)][k]  (c < C): fp32 weight gradient of the head GEMM back into the arena layout [C][T][K]
+__global__ void fold_wgrad_unpack_kernel(const float* __restrict__ tmp, float* __restrict__ g, int C, int T, int CG, int K) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long total = (long long)C * T * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long long ct = i / K;
+    const int t = (int)(ct % T), c = (int)(ct / T);
+    g[i] += tmp[((long long)t * CG + c) * K + k];
+  }
+}
+// Row-window stem: weights [R][KH*KW][8] (the arena's direct pack, Cin padded to 8) -> [R][KH*KB][64] with the kernel
+// row split into KB = ceil(KW / 8) blocks of 8 taps x 8 channels (zeros beyond KW); and the fp32 gradient back:
+// g[r][kh*KW + kw][c] += tmp[r][kh*KB + kw/8][(kw%8)*8 + c]  (c < Cin), arena layout [R][T][Cin].
+__global__ void rowwin_weight_pack_kernel(const bf16* __restrict__ src, bf16* __restrict__ out, int R, int KH, int KW, int KB) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long total = (long long)R * KH * KB * 64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 64);
+    long long t = i / 64;
+    const int kb = (int)(t % KB); t /= KB;
+    const int kh = (int)(t % KH);
+    const long long r = t / KH;
+    const int kw = kb * 8 + e / 8, c = e % 8;
+    out[i] = (kw < KW) ? src[((r * KH + kh) * KW + kw) * 8 + c] : __float2bfloat16(0.f);
+  }
+}
+__global__ void rowwin_wgrad_unpack_kernel(const float* __restrict__ tmp, float* __restrict__ g, int R, int KH, int KW, int KB,
+                                           int Cin) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long total = (long long)R * KH * KW * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cin);
+    long long t = i / Cin;
+    const int kw = (int)(t % KW); t /= KW;
+    const int kh = (int)(t % KH);
+    const long long r = t / KH;
+    g[i] += tmp[((r * KH + kh) * KB + kw / 8) * 64 + (kw % 8) * 8 + c];
+  }
+}
+// zero padding of an NHWC tensor (SRGAN's k9 p4 / VGG's k3 p1 convs feed the row-window stem, which wants a pre-padded
+// image) and its backward (crop); `slack` extra zero rows at the end of every image keep the window reads in bounds.
+__global__ void zero_pad_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int G, int pad,
+                                int slack, int backward) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int PH = H + 2 * pad + slack, PW = W + 2 * pad;
+  if (!backward) {
+    const long long total = (long long)N * PH * PW * G;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int g = (int)(i % G);
+      long long t = i / G;
+      const int pw = (int)(t % PW); t /= PW;
+      const int ph = (int)(t % PH);
+      const long long n = t / PH;
+      const int h = ph - pad, w = pw - pad;
+      y[i] = (h >= 0 && h < H && w >= 0 && w < W) ? x[((n * H + h) * W + w) * G + g] : make_uint4(0, 0, 0, 0);
+    }
+  } else {  // x = gradient on the padded grid, y = gradient on the original grid
+    const long long total = (long long)N * H * W * G;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int g = (int)(i % G);
+      long long t = i / G;
+      const int w = (int)(t % W); t /= W;
+      const int h = (int)(t % H);
+      const long long n = t / H;
+      y[i] = x[((n * PH + h + pad) * PW + w + pad) * G + g];
+    }
+  }
+}
+
 }  // namespace gcc
 
 using namespace gcc;
@@ -977,23 +1260,21 @@ extern "C" int gcc_dw3x3_bwd_bf16(const void* x, const void* dy, const float* w,
       if (cudaMemsetAsync(dw, 0, sizeof(float) * C * 9, st) != cudaSuccess) return GCC_ERR_CUDA;
       if (dbias && cudaMemsetAsync(dbias, 0, sizeof(float) * C, st) != cudaSuccess) return GCC_ERR_CUDA;
     }
-    int lanes = 128 / G;
-    if (lanes < 1) lanes = 1;
-    const int threads = (lanes * G + 31) / 32 * 32;
-    const long long npix = (long long)N * H * W;
-    long long bx = (npix + lanes * 16 - 1) / (lanes * 16);
-    if (bx > 148 * 4) bx = 148 * 4;
+    int lanes, threads, seg, blocks;
+    long long items;
+    dw_rows_geometry(N, H, W, G, &lanes, &threads, &seg, &items, &blocks);
+    if (blocks > 148 * 2) blocks = 148 * 2;      // every CTA ends with G * 80 atomics
     const size_t smem = sizeof(float) * lanes * G * 80;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (!configured[dev]) {
-      cudaFuncSetAttribute(dw3x3_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(dw3x3_wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       configured[dev] = true;
     }
-    gcc_launch(dw3x3_bwd_weight_kernel, (unsigned)bx, threads, smem, st, (const bf16*)x, (const bf16*)dy, dw, dbias, N, H, W,
-                                                                 G, C, lanes);
+    gcc_launch(dw3x3_wgrad_rows_kernel, blocks, threads, smem, st, (const bf16*)x, (const bf16*)dy, dw, dbias, H, W, G, C, lanes,
+               seg, items);
     GCC_CHECK_LAUNCH();
   }
   return GCC_OK;
@@ -1061,6 +1342,77 @@ extern "C" int gcc_image_pool_query_bf16(const void* images, void* pool, long lo
                                                                   (uint4*)out, vec);
   GCC_CHECK_LAUNCH();
   gcc_launch(image_pool_scatter_kernel, dim3((unsigned)bx, b), 256, 0, st, (const uint4*)images, (uint4*)pool, dec_ws, vec);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+
+extern "C" int gcc_fold_taps_bf16(const void* ycol, int Ccol, int CG, int KH, int KW, int C, const float* bias, int act,
+                                  void* y, int N, int GH, int GW, int OH, int OW, int dir, int off, void* stream) {
+  if ((CG != 4 && CG != 8) || C > CG || (Ccol % 8) || Ccol < KH * KW * CG || (dir != 1 && dir != -1)) {
+    gcc_set_error(__FILE__, __LINE__, "fold_taps: bad arguments");
+    return GCC_ERR_ARG;
+  }
+  const long long total = (long long)N * OH * OW;
+  if (CG == 4)
+    gcc_launch(fold_taps_kernel<4>, blocks_for(total), 256, 0, (cudaStream_t)stream, (const bf16*)ycol, Ccol, KH, KW, C, bias,
+               act, (uint4*)y, N, GH, GW, OH, OW, dir, off);
+  else
+    gcc_launch(fold_taps_kernel<8>, blocks_for(total), 256, 0, (cudaStream_t)stream, (const bf16*)ycol, Ccol, KH, KW, C, bias,
+               act, (uint4*)y, N, GH, GW, OH, OW, dir, off);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_unfold_taps_bf16(const void* dy, void* dcol, int Ccol, int CG, int KH, int KW, int N, int GH, int GW,
+                                    int OH, int OW, int off, void* stream) {
+  if ((CG != 4 && CG != 8) || (Ccol % 8) || Ccol < KH * KW * CG) {
+    gcc_set_error(__FILE__, __LINE__, "unfold_taps: bad arguments");
+    return GCC_ERR_ARG;
+  }
+  const long long total = (long long)N * GH * GW * (Ccol / 8);
+  if (CG == 4)
+    gcc_launch(unfold_taps_kernel<4>, blocks_for(total), 256, 0, (cudaStream_t)stream, (const bf16*)dy, (bf16*)dcol, Ccol, KH,
+               KW, N, GH, GW, OH, OW, off);
+  else
+    gcc_launch(unfold_taps_kernel<8>, blocks_for(total), 256, 0, (cudaStream_t)stream, (const bf16*)dy, (bf16*)dcol, Ccol, KH,
+               KW, N, GH, GW, OH, OW, off);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_fold_weight_pack_bf16(const void* src, void* out, int mode, int C, int T, int CG, int K, int Kp, int Cp,
+                                         void* stream) {
+  const int rows_p = (T * CG + 7) / 8 * 8;
+  const long long total = mode == 0 ? (long long)rows_p * Kp : (long long)K * rows_p;
+  gcc_launch(fold_weight_pack_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, (const bf16*)src, (bf16*)out, mode, C, T,
+             CG, K, Kp, Cp, rows_p);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_fold_wgrad_unpack_f32(const float* tmp, float* g, int C, int T, int CG, int K, void* stream) {
+  gcc_launch(fold_wgrad_unpack_kernel, blocks_for((long long)C * T * K), 256, 0, (cudaStream_t)stream, tmp, g, C, T, CG, K);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_rowwin_weight_pack_bf16(const void* src, void* out, int R, int KH, int KW, void* stream) {
+  const int KB = (KW + 7) / 8;
+  gcc_launch(rowwin_weight_pack_kernel, blocks_for((long long)R * KH * KB * 64), 256, 0, (cudaStream_t)stream, (const bf16*)src,
+             (bf16*)out, R, KH, KW, KB);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_rowwin_wgrad_unpack_f32(const float* tmp, float* g, int R, int KH, int KW, int Cin, void* stream) {
+  const int KB = (KW + 7) / 8;
+  gcc_launch(rowwin_wgrad_unpack_kernel, blocks_for((long long)R * KH * KW * Cin), 256, 0, (cudaStream_t)stream, tmp, g, R, KH,
+             KW, KB, Cin);
+  GCC_CHECK_LAUNCH();
+  return GCC_OK;
+}
+extern "C" int gcc_zero_pad_bf16(const void* x, void* y, int N, int H, int W, int Cp, int pad, int slack, int backward,
+                                 void* stream) {
+  if (Cp % 8) { gcc_set_error(__FILE__, __LINE__, "zero_pad: bad channel count"); return GCC_ERR_ARG; }
+  const int G = Cp / 8;
+  const long long total = backward ? (long long)N * H * W * G : (long long)N * (H + 2 * pad + slack) * (W + 2 * pad) * G;
+  gcc_launch(zero_pad_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)y, N, H, W, G, pad, slack,
+             backward);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }

@@ -16,7 +16,7 @@ int gcc_pdl_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("GCC_B200_PDL");
-    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return on;
 }

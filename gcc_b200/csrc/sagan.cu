@@ -298,7 +298,7 @@ extern "C" int gcc_attn_fwd_bf16(const void* q, const void* k, const void* v, in
   bf16* vT = (bf16*)((char*)ws + al256(nll * 4));
   // energy[n][i][j] = sum_c q[n][i][c] k[n][j][c]: pixel-major GEMM over the L positions, weights = this image's keys
   int rc = gcc_conv_gemm_launch(q, N, 1, L, dp, k, L, 1, dp, nullptr, energy, 1, L, L, 0, 0, 1, 1, 1, 0, 0, 0.f, 1, energy,
-                                nll, nullptr, 0, 1, stream);
+                                nll, nullptr, 0, 1, 0, stream);
   if (rc) return rc;
   const long long rows = (long long)N * L;
   gcc_launch(attn_softmax_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, (const float*)energy, (bf16*)probs, rows, L);
@@ -307,7 +307,7 @@ extern "C" int gcc_attn_fwd_bf16(const void* q, const void* k, const void* v, in
   GCC_CHECK_LAUNCH();
   // out[n][i][c] = sum_j probs[n][i][j] v[n][j][c]: weights = this image's values, transposed to [C][L]
   return gcc_conv_gemm_launch(probs, N, 1, L, L, vT, C, 1, L, nullptr, out, 1, L, Cp, 0, 0, 1, 1, 1, 0, 0, 0.f, 1, nullptr, 0,
-                              nullptr, 0, 0, stream);
+                              nullptr, 0, 0, 0, stream);
 }
 extern "C" int gcc_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* probs, const void* dout, int N,
                                  int L, int d, int dp, int C, int Cp, void* de_scratch, void* dq, void* dk, void* dv,
@@ -329,7 +329,7 @@ extern "C" int gcc_attn_bwd_bf16(const void* q, const void* k, const void* v, co
   float* dk32 = (float*)w8;
   // dprobs[n][i][j] = sum_c dout[n][i][c] v[n][j][c]
   int rc = gcc_conv_gemm_launch(dout, N, 1, L, Cp, v, L, 1, Cp, nullptr, dprobs, 1, L, L, 0, 0, 1, 1, 1, 0, 0, 0.f, 1, dprobs,
-                                nll, nullptr, 0, 1, stream);
+                                nll, nullptr, 0, 1, 0, stream);
   if (rc) return rc;
   gcc_launch(attn_softmax_bwd_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, (const bf16*)probs, (const float*)dprobs,
              (bf16*)de_scratch, rows, L);
@@ -338,7 +338,7 @@ extern "C" int gcc_attn_bwd_bf16(const void* q, const void* k, const void* v, co
   gcc_launch(attn_transpose_kernel, dim3((L + 31) / 32, (d + 31) / 32, N), 256, 0, st, (const bf16*)k, kT, L, dp, d);
   GCC_CHECK_LAUNCH();
   rc = gcc_conv_gemm_launch(de_scratch, N, 1, L, L, kT, d, 1, L, nullptr, dq, 1, L, dp, 0, 0, 1, 1, 1, 0, 0, 0.f, 1, nullptr, 0,
-                            nullptr, 0, 0, stream);
+                            nullptr, 0, 0, 0, stream);
   if (rc) return rc;
   // dk[n][j][c] = sum_i de[n][i][j] q[n][i][c];  dv[n][j][c] = sum_i probs[n][i][j] dout[n][i][c]: contractions over
   // the query positions = the batched weight-gradient GEMM (MN-major operands straight from the row-major tensors)

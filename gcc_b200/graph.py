@@ -30,6 +30,8 @@ class GraphedIteration:
         self.replays = 0
         self.has_arch = bool(getattr(model.opt, "darts_discriminator", False)) and model.teacher_model is not None
         self._bn_delta = []
+        self.pace = True
+        self._pace_ev = torch.cuda.Event()
 
     # ------------------------------------------------------------------ inputs
     def _make_static(self, batch):
@@ -87,7 +89,8 @@ class GraphedIteration:
         if not base.dist_on() or pix2pix.capture_collectives():
             # one graph; under data parallel the NCCL all-reduces are captured as graph nodes
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
+            mode = "thread_local" if base.dist_on() else "global"
+            with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode):
                 self._iteration()
             self.segments = [(self.graph, None)]
         else:
@@ -138,3 +141,9 @@ class GraphedIteration:
         for l, d in self._bn_delta:
             l.num_batches += d
         self.replays += 1
+        if len(self.segments) > 1 and self.pace:
+            # data parallel with eager collectives between graph segments: keep the host at most one iteration ahead
+            # (measured on 4 and 8 GPUs in round 1: an unpaced host, with all iterations' segments and collectives
+            # queued at once, runs 1-4 ms per iteration slower)
+            self._pace_ev.record()
+            self._pace_ev.synchronize()

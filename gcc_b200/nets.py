@@ -53,6 +53,10 @@ class ConvLayer:
                         ((kind == "conv" and cin <= 8) or (kind == "convT" and cout <= 8)))
         # k4 s1 p1 convs with <= 8 output channels (PatchGAN logits head) run as a 1x1 GEMM + fold (ops.HeadConvFn)
         self.headpath = (kind == "conv" and k == 4 and stride == 1 and pad == 1 and cout <= 8 and cin >= 64)
+        # stride-1 convs with a large kernel and <= 8 channels on one side (k7 / k9 stem and head of the MobileResNet /
+        # SRResNet generators, VGG's first conv): row-window GEMM (ops.StemConvFn) / 1x1 GEMM + fold (ops.FoldConvFn)
+        self.stempath = (kind == "conv" and stride == 1 and 3 <= k <= 16 and cin <= 8 and cout >= 16 and outpad == 0)
+        self.foldpath = (kind == "conv" and stride == 1 and 3 <= k <= 9 and cout <= 8 and cin >= 16 and not self.headpath)
 
     def bind(self):
         self.weight = self.arena.params[self.wname]
@@ -60,7 +64,8 @@ class ConvLayer:
         self.packs = self.arena.packs[self.wname]
 
     def __call__(self, x, act=ACT_NONE, slope=0.2):
-        fn = ops.ColConvFn if self.colpath else (ops.HeadConvFn if self.headpath else ops.ConvFn)
+        fn = ops.ColConvFn if self.colpath else (ops.HeadConvFn if self.headpath else (
+            ops.StemConvFn if self.stempath else (ops.FoldConvFn if self.foldpath else ops.ConvFn)))
         return fn.apply(x, self.weight, self.bias, self, act, slope)
 
     def with_stats(self, x):
@@ -68,7 +73,7 @@ class ConvLayer:
         Returns (y, sums) with sums = None when the layer shape does not take the fused path."""
         n, h, w, _ = x.shape
         oh, ow = ops.conv_out_hw(h, w, self.k, self.stride, self.pad, self.kind == "convT", self.outpad)
-        if self.colpath or self.headpath or n * oh * ow <= 16384 or not x.is_cuda:
+        if self.colpath or self.headpath or self.stempath or self.foldpath or n * oh * ow <= 16384 or not x.is_cuda:
             return self(x), None
         sums = ops.zero_pool.take(2 * rp8(self.cout), x.device)
         return ops.ConvFn.apply(x, self.weight, self.bias, self, ACT_NONE, 0.2, sums), sums

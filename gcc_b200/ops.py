@@ -351,6 +351,203 @@ class HeadConvFn(torch.autograd.Function):
         return dx, None, None, None, None, None
 
 
+def alloc_slack(shape, device, zero=False):
+    """bf16 tensor of `shape` whose storage continues for >= 128 bytes behind the last element (the row-window stem's
+    tensor map reads up to 7 pixels past a row end, against zero weights)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    flat = (torch.zeros if zero else torch.empty)(n + 64, dtype=torch.bfloat16, device=device)
+    if not zero:
+        flat[n:].zero_()
+    return flat[:n].view(*shape)
+
+
+def _has_slack(t):
+    return t.is_contiguous() and t.untyped_storage().nbytes() - (t.storage_offset() + t.numel()) * 2 >= 128
+
+
+def _derived(layer, key, build):
+    """Per-layer operand derived from the arena's bf16 packs, rebuilt when the packs were refreshed."""
+    layer.arena.ensure_packed()
+    cache = layer.__dict__.setdefault("_derived_ops", {})
+    ent = cache.get(key)
+    if ent is None or ent[0] != layer.arena.version:
+        buf = build(None if ent is None else ent[1])
+        cache[key] = (layer.arena.version, buf)
+        return buf
+    return ent[1]
+
+
+class StemConvFn(torch.autograd.Function):
+    """Stride-1 Conv2d whose INPUT has <= 8 channels and whose kernel is large (k7 stem of the MobileResNet generator,
+    k9 stem of the SRResNet, VGG's first k3 conv): row-window implicit GEMM (gcc_conv_rowwin_bf16) instead of one
+    7/8-empty k-block per tap; the data gradient (needed when the input is itself generated, e.g. CycleGAN's
+    G_B(G_A(x))) is a 1x1 GEMM + fold."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, act, slope):
+        _check(x)
+        st = _st()
+        n, h, w, cx = x.shape
+        k, p = layer.k, layer.pad
+        if cx != 8:
+            raise _lib.GccB200Error("stem conv expects an 8-channel (padded) image")
+        if p > 0:
+            xp = alloc_slack((n, h + 2 * p, w + 2 * p, 8), x.device)
+            call("gcc_zero_pad_bf16", x.contiguous().data_ptr(), xp.data_ptr(), n, h, w, 8, p, 0, 0, st)
+        else:
+            xp = x if _has_slack(x) else alloc_slack(x.shape, x.device).copy_(x)
+        hp, wp = h + 2 * p, w + 2 * p
+        oh, ow = hp - k + 1, wp - k + 1
+        kb = (k + 7) // 8
+        pk = layer.packs
+
+        def build(old):
+            buf = old if old is not None else torch.empty(layer.cout, k * kb, 64, dtype=torch.bfloat16, device=x.device)
+            call("gcc_rowwin_weight_pack_bf16", pk.direct.data_ptr(), buf.data_ptr(), layer.cout, k, k, st)
+            return buf
+        wrow = _derived(layer, "rowwin", build)
+        cop = rp8(layer.cout)
+        y = torch.empty(n, oh, ow, cop, dtype=torch.bfloat16, device=x.device)
+        epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
+        call("gcc_conv_rowwin_bf16", xp.data_ptr(), n, hp, wp, wrow.data_ptr(), layer.cout, k, k,
+             None if bias is None else bias.data_ptr(), y.data_ptr(), oh, ow, cop, epi, slope, None, 0, st)
+        ctx.layer, ctx.act, ctx.slope, ctx.has_bias = layer, act, slope, bias is not None
+        ctx.geom = (n, h, w, hp, wp, oh, ow, cop)
+        ctx.save_for_backward(xp, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        xp, y = ctx.saved_tensors
+        n, h, w, hp, wp, oh, ow, cop = ctx.geom
+        k, p = layer.k, layer.pad
+        kb = (k + 7) // 8
+        st = _st()
+        dev = dy.device
+        dy = dy.contiguous()
+        if ctx.act != ACT_NONE:
+            dpre = torch.empty_like(dy)
+            call("gcc_act_bwd_bf16", y.data_ptr(), dy.data_ptr(), dpre.data_ptr(), dy.numel(),
+                 1 if ctx.act == ACT_LRELU else 3, ctx.slope, st)
+        else:
+            dpre = dy
+        dx = None
+        if ctx.needs_input_grad[0]:
+            cg = 4 if layer.cin <= 4 else 8
+            T = k * k
+            ccol = rp8(T * cg)
+            pk = layer.packs
+
+            def build(old):
+                buf = old if old is not None else torch.empty(ccol, pk.d0p, dtype=torch.bfloat16, device=dev)
+                call("gcc_fold_weight_pack_bf16", pk.transposed.data_ptr(), buf.data_ptr(), 0, layer.cin, T, cg, layer.cout,
+                     pk.d0p, 0, st)
+                return buf
+            w2 = _derived(layer, "stem_dgrad", build)           # [(tap, c_in)][cout_p]
+            ycol = torch.empty(n, oh, ow, ccol, dtype=torch.bfloat16, device=dev)
+            call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, w2.data_ptr(), ccol, 1, w2.shape[1], None,
+                 ycol.data_ptr(), oh, ow, ccol, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
+            dxp = torch.empty(n, hp, wp, 8, dtype=torch.bfloat16, device=dev)
+            call("gcc_fold_taps_bf16", ycol.data_ptr(), ccol, cg, k, k, layer.cin, None, 0, dxp.data_ptr(), n, oh, ow, hp, wp,
+                 -1, 0, st)
+            if p > 0:
+                dx = torch.empty(n, h, w, 8, dtype=torch.bfloat16, device=dev)
+                call("gcc_zero_pad_bf16", dxp.data_ptr(), dx.data_ptr(), n, h, w, 8, p, 0, 1, st)
+            else:
+                dx = dxp
+        if ctx.needs_input_grad[1]:
+            tmp = torch.empty(layer.cout, k * kb, 64, dtype=torch.float32, device=dev)
+            call("gcc_wgrad_rowwin_bf16", dpre.data_ptr(), n, oh, ow, cop, xp.data_ptr(), hp, wp, tmp.data_ptr(), layer.cout,
+                 k, k, st)
+            call("gcc_rowwin_wgrad_unpack_f32", tmp.data_ptr(), layer.arena.flat_grad[layer.wname].data_ptr(), layer.cout, k,
+                 k, layer.cin, st)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            call("gcc_bias_grad_bf16", dpre.data_ptr(), n * oh * ow, cop, 0, layer.cout,
+                 layer.arena.flat_grad[layer.bname].data_ptr(), 1, st)
+        return dx, None, None, None, None, None
+
+
+class FoldConvFn(torch.autograd.Function):
+    """Stride-1 Conv2d with <= 8 OUTPUT channels and a large kernel (k7 head of the MobileResNet generator, k9 head of
+    the SRResNet): ONE 1x1 GEMM over the input computes every tap's partial dot product, gcc_fold_taps_bf16 sums the
+    shifted partials (+ bias, + tanh); backward = unfold of dy + two 1x1 GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, act, slope):
+        _check(x)
+        if act not in (ACT_NONE, ACT_TANH):
+            raise _lib.GccB200Error("fold-path conv supports none / tanh epilogues")
+        x = x.contiguous()
+        st = _st()
+        n, h, w, cx = x.shape
+        k, p = layer.k, layer.pad
+        T = k * k
+        cg = 4 if layer.cout <= 4 else 8
+        ccol = rp8(T * cg)
+        oh, ow = h + 2 * p - k + 1, w + 2 * p - k + 1
+        pk = layer.packs
+
+        def build(old):
+            buf = old if old is not None else torch.empty(ccol, pk.d1p, dtype=torch.bfloat16, device=x.device)
+            call("gcc_fold_weight_pack_bf16", pk.direct.data_ptr(), buf.data_ptr(), 0, layer.cout, T, cg, layer.cin, pk.d1p,
+                 0, st)
+            return buf
+        w2 = _derived(layer, "fold_fwd", build)                  # [(tap, c_out)][cin_p]
+        ycol = torch.empty(n, h, w, ccol, dtype=torch.bfloat16, device=x.device)
+        call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, w2.data_ptr(), ccol, 1, w2.shape[1], None, ycol.data_ptr(), h, w,
+             ccol, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
+        y = torch.empty(n, oh, ow, 8, dtype=torch.bfloat16, device=x.device)
+        call("gcc_fold_taps_bf16", ycol.data_ptr(), ccol, cg, k, k, layer.cout, None if bias is None else bias.data_ptr(),
+             2 if act == ACT_TANH else 0, y.data_ptr(), n, h, w, oh, ow, 1, -p, st)
+        ctx.layer, ctx.act, ctx.has_bias = layer, act, bias is not None
+        ctx.geom = (n, h, w, cx, oh, ow, cg, ccol)
+        ctx.save_for_backward(x, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        x, y = ctx.saved_tensors
+        n, h, w, cx, oh, ow, cg, ccol = ctx.geom
+        k, p = layer.k, layer.pad
+        T = k * k
+        st = _st()
+        dev = dy.device
+        dy = dy.contiguous()
+        if ctx.act != ACT_NONE:
+            dpre = torch.empty_like(dy)
+            call("gcc_act_bwd_bf16", y.data_ptr(), dy.data_ptr(), dpre.data_ptr(), dy.numel(), 3, 0.0, st)
+        else:
+            dpre = dy
+        dcol = torch.empty(n, h, w, ccol, dtype=torch.bfloat16, device=dev)
+        call("gcc_unfold_taps_bf16", dpre.data_ptr(), dcol.data_ptr(), ccol, cg, k, k, n, h, w, oh, ow, -p, st)
+        pk = layer.packs
+        dx = None
+        if ctx.needs_input_grad[0]:
+            def build(old):
+                buf = old if old is not None else torch.empty(layer.cin, ccol, dtype=torch.bfloat16, device=dev)
+                call("gcc_fold_weight_pack_bf16", pk.transposed.data_ptr(), buf.data_ptr(), 1, layer.cout, T, cg, layer.cin, 0,
+                     pk.d0p, st)
+                return buf
+            w3 = _derived(layer, "fold_dgrad", build)            # [cin][(tap, c_out)]
+            dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=dev)
+            call("gcc_conv_gemm_bf16", dcol.data_ptr(), n, h, w, ccol, w3.data_ptr(), layer.cin, 1, ccol, None, dx.data_ptr(),
+                 h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
+        if ctx.needs_input_grad[1]:
+            tmp = torch.empty(ccol, layer.cin, dtype=torch.float32, device=dev)
+            call("gcc_wgrad_gemm_bf16", dcol.data_ptr(), n, h, w, ccol, x.data_ptr(), h, w, cx, tmp.data_ptr(), ccol, layer.cin,
+                 1, 1, 1, 0, 0, 0, 1.0, st)
+            call("gcc_fold_wgrad_unpack_f32", tmp.data_ptr(), layer.arena.flat_grad[layer.wname].data_ptr(), layer.cout, T, cg,
+                 layer.cin, st)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            call("gcc_bias_grad_bf16", dpre.data_ptr(), n * oh * ow, 8, 0, layer.cout,
+                 layer.arena.flat_grad[layer.bname].data_ptr(), 1, st)
+        return dx, None, None, None, None, None
+
+
 class NormActFn(torch.autograd.Function):
     """[BatchNorm | InstanceNorm | identity] -> [channel gate] -> activation, with an optional second
     activation output (the U-Net's relu'd skip copy).
@@ -602,7 +799,7 @@ class ReflectPadFn(torch.autograd.Function):
     def forward(ctx, x, pad):
         x = _check(x).contiguous()
         n, h, w, cp = x.shape
-        y = torch.empty(n, h + 2 * pad, w + 2 * pad, cp, dtype=torch.bfloat16, device=x.device)
+        y = alloc_slack((n, h + 2 * pad, w + 2 * pad, cp), x.device)   # (slack: the row-window stem may read it)
         call("gcc_reflect_pad_bf16", x.data_ptr(), y.data_ptr(), n, h, w, cp, pad, 0, _st())
         ctx.pad, ctx.shape = pad, (n, h, w, cp)
         return y
@@ -638,8 +835,7 @@ class DwConvFn(torch.autograd.Function):
         n, h, w, cp = x.shape
         dx = dxp = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            dxp = torch.empty(n, h + 2, w + 2, cp, dtype=torch.bfloat16, device=x.device)
+            dx = torch.empty_like(x)      # (the mirrored border taps are folded into the kernel: no padded scratch)
         gw = layer.arena.flat_grad[layer.wname].data_ptr() if ctx.needs_input_grad[1] else None
         gb = layer.arena.flat_grad[layer.bname].data_ptr() if (layer.bname and ctx.needs_input_grad[2]) else None
         call("gcc_dw3x3_bwd_bf16", x.data_ptr(), dy.data_ptr(), weight.data_ptr(),

@@ -146,6 +146,39 @@ int gcc_unpad_wgrad_rows(const float* tmp, float* g, int C, int K, void* stream)
 int gcc_image_pool_query_bf16(const void* images, void* pool, long long* state_dev, int* dec_ws, void* out, int b,
                               long long elems_per_image, int pool_size, void* stream);
 
+/* ---- stem / head convolutions: <= 8 channels on the image side, large kernels, stride 1 ----
+ * (k7 stem / head of the MobileResNet generator, models/Pix2Pix.py:216,259 and CycleGAN; k9 stem / head of the SRResNet,
+ * models/SRGAN.py:150,190; VGG19's first k3 conv, models/GANLoss.py:110).
+ * Stem ("row window"): x is a PRE-PADDED 8-channel NHWC image [N][Hrows][Wp][8] followed by >= 128 readable bytes (windows
+ * at the end of a row run 7 pixels into the next one, against zero weights); the taps of one kernel row are contiguous there, so a tensor map whose window positions are
+ * one pixel (16 bytes) apart delivers K-major [pixels][8 kw x 8 c] tiles: K = KH * ceil(KW/8) * 64 instead of KH*KW
+ * k-blocks that are 7/8 zeros.  w_rowpack: bf16 [R][KH*ceil(KW/8)][64] from gcc_rowwin_weight_pack_bf16 (src = the
+ * arena's direct pack [R][KH*KW][8]); the weight gradient comes back as fp32 [R][KH*ceil(KW/8)][64] and is accumulated
+ * into the arena layout [R][KH*KW][Cin] by gcc_rowwin_wgrad_unpack_f32.  OH = padded rows - KH + 1, OW = Wp - KW + 1. */
+int gcc_conv_rowwin_bf16(const void* x, int N, int Hrows, int Wp, const void* w_rowpack, int R, int KH, int KW,
+                         const float* bias, void* y, int OH, int OW, int Cy, int act, float slope, float* stats, int stats_ld,
+                         void* stream);
+int gcc_wgrad_rowwin_bf16(const void* dy, int N, int OH, int OW, int Cp, const void* x, int Hrows, int Wp, float* dw, int R,
+                          int KH, int KW, void* stream);
+int gcc_rowwin_weight_pack_bf16(const void* src, void* out, int R, int KH, int KW, void* stream);
+int gcc_rowwin_wgrad_unpack_f32(const float* tmp, float* g, int R, int KH, int KW, int Cin, void* stream);
+/* Head ("fold"): C <= CG (4 or 8) output channels.  One 1x1 GEMM (gcc_conv_gemm_bf16) over the pre-padded input computes
+ * ycol[pix][(kh*KW+kw)*CG + c] = x[pix,:] . w[c][kh][kw][:]; gcc_fold_taps_bf16 sums the shifted partials:
+ *   y[n,oy,ox,c] = act(bias[c] + sum ycol[n, oy + dir*kh + off, ox + dir*kw + off, (kh*KW+kw)*CG + c])   (act 2 = tanh)
+ * over the ycol grid [N][GH][GW][Ccol] (terms outside are skipped); dir = +1: the conv itself, dir = -1: the data gradient
+ * of a stem conv on its padded input grid.  gcc_unfold_taps_bf16 builds dcol[n,gy,gx,(tap)*CG+c] = dy[n,gy-kh-off,gx-kw-off,c]
+ * for the head's data / weight gradient GEMMs; gcc_fold_weight_pack_bf16 builds the GEMM weight operands from the arena
+ * packs (mode 0: [(tap,c)][K] from direct [C][T][Kp]; mode 1: [K][(tap,c)] from transposed [K][T][Cp]);
+ * gcc_fold_wgrad_unpack_f32: g[c][t][k] += tmp[(t*CG+c)][k]. */
+int gcc_fold_taps_bf16(const void* ycol, int Ccol, int CG, int KH, int KW, int C, const float* bias, int act, void* y, int N,
+                       int GH, int GW, int OH, int OW, int dir, int off, void* stream);
+int gcc_unfold_taps_bf16(const void* dy, void* dcol, int Ccol, int CG, int KH, int KW, int N, int GH, int GW, int OH, int OW,
+                         int off, void* stream);
+int gcc_fold_weight_pack_bf16(const void* src, void* out, int mode, int C, int T, int CG, int K, int Kp, int Cp, void* stream);
+int gcc_fold_wgrad_unpack_f32(const float* tmp, float* g, int C, int T, int CG, int K, void* stream);
+/* nn.Conv2d zero padding made explicit for the stem path (backward = 1: crop the gradient); `slack` extra zero rows per image */
+int gcc_zero_pad_bf16(const void* x, void* y, int N, int H, int W, int Cp, int pad, int slack, int backward, void* stream);
+
 /* ---- loss reductions (loss.cu) ---- */
 /* GANLoss (models/GANLoss.py:38-59). mode: 0 hinge, 1 lsgan, 2 vanilla, 3 wgangp.
  * kind: 0 D-real, 1 D-fake, 2 G.  out is an fp32 device scalar that the caller zeroes. */

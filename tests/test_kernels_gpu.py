@@ -1,5 +1,7 @@
 """Per-kernel parity on the B200: every C-ABI kernel against a plain torch fp32 computation of the same
-op on the same bf16-rounded inputs (tolerances are bf16 output rounding: 2^-8 relative)."""
+op on the same bf16-rounded inputs.  Metric: relative L2 per tensor (|a - b|_2 / |b|_2); tolerance 6e-3 for bf16
+outputs (rounding alone is 2^-9 / sqrt(3) = 1.1e-3), 2e-3 for fp32 outputs.  The torch reference runs in true fp32
+(TF32 off for cuDNN and matmul)."""
 import math
 
 import pytest
@@ -7,8 +9,10 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
-BF16_TOL = 1.2e-2
+BF16_TOL = 6e-3
 
 
 @pytest.fixture(scope="module")
@@ -40,7 +44,8 @@ def nchw(x, c, G):
 
 
 def rel_err(a, b):
-    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
 
 
 def bf(x):
@@ -70,6 +75,12 @@ CONV_CASES = [
     (2, 8, 8, 45, 3, 4, 2, 1, 1, 0),
     (3, 31, 31, 256, 1, 4, 1, 1, 0, 0),   # head path: 1x1 GEMM + fold
     (2, 15, 17, 72, 3, 4, 1, 1, 0, 0),
+    (2, 30, 26, 3, 32, 7, 1, 0, 0, 0),    # stem path (row-window GEMM): k7 on a pre-padded image
+    (2, 20, 24, 3, 64, 9, 1, 4, 0, 0),    # stem path: k9 p4 (SRResNet), two 8-tap blocks per kernel row
+    (2, 16, 16, 3, 64, 3, 1, 1, 0, 0),    # stem path: k3 p1 (VGG19 / SRGAN discriminator first conv)
+    (3, 22, 22, 24, 3, 7, 1, 0, 0, 0),    # fold path: k7 head, 3 output channels
+    (2, 16, 20, 64, 3, 9, 1, 4, 0, 0),    # fold path: k9 p4 head (SRResNet)
+    (2, 12, 12, 40, 6, 3, 1, 1, 0, 0),    # fold path with an 8-channel group
 ]
 
 
