@@ -431,8 +431,8 @@ def run_b200(args):
     e2e = None
     if not args.skip_e2e:
         # end to end through the public API with HOST buffers: every step's inputs go pinned host memory -> device
-        # (gcc_b200.prefetch.Prefetcher: bf16 staging, copy stream) inside the timed region, every step's losses are
-        # read back to the host.
+        # (gcc_b200.prefetch.Prefetcher: copy stream, double-buffered device slots) inside the timed region, every
+        # step's losses are read back to the host.
         def stream_of(n):
             for i in range(n):
                 yield host[i % nbatch]
@@ -443,7 +443,7 @@ def run_b200(args):
         h2d = (pf.h2d_bytes - b0) / max(1, args.steps)
         pf.close()
         e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-               "h2d_note": "bf16 staging of the fp32 host batch (fp32 would be %d bytes)" % h2d_fp32,
+               "h2d_note": "fp32 host batch from pinned memory on a copy stream, overlapped with the previous step",
                "d2h_bytes_per_step": 4 * len(model.loss_names), "ms_per_step": ms_e2e / args.steps}
 
     if rank != 0:

@@ -5,11 +5,14 @@ the 1000+ images/s step fed from host memory.
 NCHW tensors in [-1, 1] plus path strings) -- or of tuples of such dicts, e.g. (train batch, validation batch) of one
 GCC iteration -- and yields the same structure with the tensors already on the device:
 
-  * a background thread converts each float32 tensor to bf16 while copying it into a PINNED staging buffer (the
-    network rounds its input to bf16 anyway: same values, half the PCIe bytes; ``dtype=None`` keeps float32);
-  * the host->device copy of batch i+1 runs on a dedicated copy stream while the step of batch i computes
-    (``depth`` staging slots on both sides, events in both directions: the copy stream does not overwrite a device
-    slot before the consumer's stream is done with it, and the consumer's stream waits for the copy).
+  * a background thread stages each tensor in a PINNED buffer (tensors that already are pinned are copied from where
+    they lie) and issues the host->device copy of batch i+1 on a dedicated copy stream while the step of batch i
+    computes (``depth`` slots on both sides, events in both directions: the copy stream does not overwrite a device
+    slot before the consumer's stream is done with it, and the consumer's stream waits for the copy);
+  * ``dtype=torch.bfloat16`` converts float32 tensors to bf16 while staging (the network rounds its input to bf16
+    anyway: same values, half the PCIe bytes).  Off by default: measured on the pix2pix step (100 MB of fp32 input per
+    iteration), the host-side conversion costs ~25 ms per iteration on one core -- more than the overlapped PCIe copy
+    it saves -- so it only pays when the host has cores to spare and the link is the bottleneck.
 
 The device tensors are NCHW like the host ones; ``set_input`` / ``GraphedIteration.run`` accept them unchanged.
 """
@@ -20,7 +23,7 @@ import torch
 
 
 class Prefetcher:
-    def __init__(self, batches, device, depth=2, dtype=torch.bfloat16):
+    def __init__(self, batches, device, depth=2, dtype=None):
         self.src = iter(batches)
         self.device = torch.device(device)
         self.depth = depth
@@ -66,9 +69,13 @@ class Prefetcher:
                         for k, v in part.items():
                             if torch.is_tensor(v):
                                 pinned, dev = self._buffers(slot, (pi, k), v)
-                                pinned.copy_(v)                  # fp32 -> bf16 on the host, into pinned memory
-                                dev.copy_(pinned, non_blocking=True)
-                                self.h2d_bytes += pinned.numel() * pinned.element_size()
+                                if v.is_pinned() and v.dtype == dev.dtype:
+                                    src = v                      # already page-locked: copy from where it lies
+                                else:
+                                    pinned.copy_(v)              # (dtype conversion, if any, happens here on the host)
+                                    src = pinned
+                                dev.copy_(src, non_blocking=True)
+                                self.h2d_bytes += src.numel() * src.element_size()
                                 out[k] = dev
                             else:
                                 out[k] = v

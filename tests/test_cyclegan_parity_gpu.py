@@ -35,20 +35,32 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
-def test_cyclegan_iteration_matches_oracle():
+C3 = {"ngf": 24, "teacher_ngf": 64, "ndf": 64, "teacher_ndf": 64}
+C3_A = [24, 48, 86, 72, 86, 47, 86, 44, 86, 43, 86, 43, 86, 29, 86, 30, 86, 37, 86, 36, 86, 48, 24]
+C3_B = [24, 48, 96, 91, 96, 73, 96, 62, 96, 61, 96, 74, 96, 54, 96, 51, 96, 58, 96, 81, 96, 48, 24]
+
+
+@pytest.mark.parametrize("case", ["tiny", "c3_widths"])
+def test_cyclegan_iteration_matches_oracle(case):
+    """tiny: widths 8 / 16, one pruned generator (the bounds of the module docstring).  c3_widths: BASELINE configs[2]'s
+    real widths (student ngf 24 with the channel lists of utils/prune_util.py:120-121, teacher ngf 64, ndf 64) where the
+    near-cancellation of the tiny nets is gone: generators rel-L2 <= 5e-2 / cos >= 0.998, discriminators <= 3e-2 /
+    0.9995, reconstructions <= 5e-2."""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
+    global TINY, CFG
+    widths, cfg_a, cfg_b = (TINY, CFG, None) if case == "tiny" else (C3, C3_A, C3_B)
     from gcc_b200 import options
     from gcc_b200.cyclegan import MobileCycleGANModel, build_cycle_teacher
     from oracle import gcc_oracle as O
     opt = options.parse(["--dataroot", "x/horse2zebra", "--model", "cyclegan", "--darts_discriminator",
                          "--online_distillation", "--lambda_content", "0.01", "--lambda_gram", "10", "--gpu_ids", "0"])
     assert opt.gan_mode == "lsgan" and opt.lambda_L1 == 0.0
-    for k, v in TINY.items():
+    for k, v in widths.items():
         setattr(opt, k, v)
-    model = MobileCycleGANModel(opt, cfg_AtoB=CFG, cfg_BtoA=None)
+    model = MobileCycleGANModel(opt, cfg_AtoB=cfg_a, cfg_BtoA=cfg_b)
     teacher = build_cycle_teacher(model, opt)
-    S, T = O.build_cycle_pair(O.CycleOpt(direction=opt.direction, **TINY), CFG, None)
+    S, T = O.build_cycle_pair(O.CycleOpt(direction=opt.direction, **widths), cfg_a, cfg_b)
     for mine, orc in ((model, S), (teacher, T)):
         for k in "AB":
             getattr(mine, "netG_" + k).load_state_dict({n: v.detach() for n, v in orc.G[k].items()})
@@ -114,19 +126,28 @@ def test_cyclegan_iteration_matches_oracle():
     rep["losses"] = {k: {"b200": a, "oracle": b} for k, (a, b) in losses.items()}
     print("WORST", json.dumps(worst, indent=0))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "step_parity_cyclegan.json"), "w"), indent=1)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "step_parity_cyclegan%s.json" % ("" if case == "tiny" else "_c3")), "w"),
+              indent=1)
     print(json.dumps(rep, indent=1))
     bad = []
     for k, v in rep.items():
         if k == "losses":
             continue
+        if case == "tiny":
+            lim_cos = 0.9 if ".G_" in k else 0.99
+            lim_rel = 0.5 if ".G_" in k else 0.15
+            lim_img = 0.15 if k.startswith("rec_") else 5e-2
+        else:
+            lim_cos = 0.998 if ".G_" in k else 0.9995
+            lim_rel = 5e-2 if ".G_" in k else 3e-2
+            lim_img = 5e-2
         if k.endswith(".cos"):
-            if v < (0.9 if ".G_" in k else 0.99):
+            if v < lim_cos:
                 bad.append((k, v))
         elif k.endswith(".rel"):
-            if v > (0.5 if ".G_" in k else 0.15):
+            if v > lim_rel:
                 bad.append((k, v))
-        elif v > (0.15 if k.startswith("rec_") else 5e-2):
+        elif v > lim_img:
             bad.append((k, v))
     for k, (a, b) in losses.items():
         if abs(a - b) > 5e-2 * abs(b) + 1e-2:

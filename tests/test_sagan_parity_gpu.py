@@ -71,8 +71,13 @@ def test_spectral_norm_and_attention_kernels(cuda):
     call("gcc_spectral_norm_bwd", dWeff.cuda().data_ptr(), Wd.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(),
          t.data_ptr(), h, wd, dW.data_ptr(), du.data_ptr(), dv.data_ptr(), scr.data_ptr(), st)
     assert _rel(dW.cpu(), Wr.grad) < 1e-4 and _rel(du.cpu(), ur.grad) < 1e-4 and _rel(dv.cpu(), vr.grad) < 1e-4
-    # attention core forward / backward
-    n, hh, ww, c, d = 2, 6, 5, 24, 3
+    # attention core forward / backward (batched tcgen05 GEMMs + row softmax; L must be a multiple of 8: the
+    # reference's attention maps are 16 / 64 / 256 / 1024 positions).  Cases: L < one 128-pixel tile, and L spanning tiles.
+    for (n, hh, ww, c, d) in ((2, 6, 4, 24, 3), (3, 16, 24, 40, 5)):
+        _attn_case(cuda, AttnFn, n, hh, ww, c, d)
+
+
+def _attn_case(cuda, AttnFn, n, hh, ww, c, d):
     L = hh * ww
     q = torch.randn(n, hh, ww, 8, device=cuda).to(torch.bfloat16); q[..., d:] = 0
     k = torch.randn(n, hh, ww, 8, device=cuda).to(torch.bfloat16); k[..., d:] = 0

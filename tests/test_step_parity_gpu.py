@@ -5,7 +5,12 @@ parameters and inputs: one full GCC iteration = optimize_parameters() + optimize
 Tolerances (bf16 activations / fp32 accumulation vs the fp32 oracle; SURVEY.md 8d "tolerance guidance"):
   activations / taps ..... relative L2 <= 3e-2
   losses ................. |rel| <= 3e-2 (+2e-3 abs; +1e-2 abs for the GAN / arch terms, means of O(1) logits)
-  per-network gradients .. global relative L2 <= 8e-2 and cosine >= 0.995 (discriminators: 0.15 / 0.99)
+  per-network gradients at BASELINE's widths (unet_c2*: ngf 32 / 64, ndf 128) .. rel L2 <= 2e-2, cosine >= 0.9995 for
+  EVERY network (measured: generators 0.5-0.7 %, discriminators 0.9-1.1 %, cos >= 0.99995) = SURVEY 8d's bf16 guidance
+  per-network gradients at the tiny widths (ngf 8 / 16, ndf 16) .. rel L2 <= 8e-2 / cos >= 0.995, discriminators
+  0.15 / 0.99: their real- and fake-batch gradient terms cancel 22:1 (tests/test_grad_terms_gpu.py checks each term at
+  0.5 %), which the reference's own arithmetic shows as soon as its storage is rounded to bf16 (the report's
+  `vs_bf16_oracle` entry; oracle/bf16_emulation.py)
   (MobileResNet generator: 0.12 / 0.99 -- 41 bf16-rounded InstanceNorm stages in series)
   gate masks ............. bit exact
 """
@@ -176,16 +181,16 @@ def test_gcc_iteration_matches_oracle(name):
     print(json.dumps(report, indent=1))
 
     bad = []
+    full_width = name.startswith("unet_c2")
     for k, v in report.items():
         if k in ("losses", "_worst", "vs_bf16_oracle"):
             continue
         if k.endswith(".cos"):
-            if v < (0.99 if (".D." in k or backbone == "resnet") else 0.995):
+            if v < (0.9995 if full_width else (0.99 if (".D." in k or backbone == "resnet") else 0.995)):
                 bad.append((k, v))
         elif k.endswith(".grad.rel_l2"):
-            # discriminator gradients pass through BatchNorm backward with a nearly constant upstream
-            # gradient (hinge): dy - mean(dy) cancels most of the bf16 mantissa, see DESIGN.md "tolerances"
-            if v > (0.15 if ".D." in k else (0.12 if backbone == "resnet" else 8e-2)):
+            # tiny widths: the discriminator's real / fake gradient terms cancel 22:1 (see the module docstring)
+            if v > (2e-2 if full_width else (0.15 if ".D." in k else (0.12 if backbone == "resnet" else 8e-2))):
                 bad.append((k, v))
         elif v > 3e-2:
             bad.append((k, v))
