@@ -63,6 +63,8 @@ def parse_args():
     p.add_argument("--batch", type=int, default=0, help="images per GPU per step (0 = the config's)")
     p.add_argument("--trace", type=int, default=0, help="debug: after warm-up run one eager step with per-GEMM-launch "
                    "event timing logged to stderr (GCCTRACE lines) and exit without a bench line")
+    p.add_argument("--profile", default="", help="debug: after warm-up run one eager step under torch.profiler (CUPTI kernel "
+                   "times, no replay overhead), write the per-kernel table to this file and exit without a bench line")
     p.add_argument("--clock_ms", type=int, default=200, help="nvidia-smi sampling interval during the timed region")
     p.add_argument("--watchdog_s", type=int, default=900, help="abort the whole process after this many seconds")
     p.add_argument("--no_dropout", action="store_true")
@@ -347,6 +349,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     os.environ.setdefault("NCCL_DEBUG", "WARN")     # never overrides the caller's setting (e.g. NCCL_DEBUG=INFO)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs go to stderr: stdout = one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gcc_b200 import _lib, factory
@@ -403,6 +406,23 @@ def run_b200(args):
             ms = float(t)
         return ms, _lib.lib().gcc_launch_count() - l0
 
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        for i in range(2):
+            step(devb[i % nbatch], False)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(devb[0], False)
+            torch.cuda.synchronize()
+        rows = sorted(((e.key, e.count, e.device_time_total) for e in prof.key_averages()), key=lambda r: -r[2])
+        tot = sum(r[2] for r in rows)
+        with open(args.profile, "w") as f:
+            f.write("%s: one eager step, %d kernels launches, %.3f ms of device time (torch.profiler / CUPTI)\n" % (
+                args.config, sum(r[1] for r in rows), tot / 1e3))
+            f.write("%-90s %7s %10s %7s %9s\n" % ("kernel", "count", "ms", "share", "avg_us"))
+            for k, c, t in rows:
+                f.write("%-90s %7d %10.3f %6.1f%% %9.1f\n" % (k[:90], c, t / 1e3, 100.0 * t / max(tot, 1e-9), t / max(c, 1)))
+        return
     if args.trace:
         for i in range(3):
             step(devb[i % nbatch], False)
@@ -436,8 +456,9 @@ def run_b200(args):
         def stream_of(n):
             for i in range(n):
                 yield host[i % nbatch]
-        pf = Prefetcher(stream_of(args.steps + 1), torch.device("cuda", local))
-        step(next(pf), True)     # warm the host-input path once
+        pf = Prefetcher(stream_of(args.steps + 3), torch.device("cuda", local))
+        for _ in range(3):       # warm the host-input path: every prefetch slot is allocated and used once
+            step(next(pf), True)
         b0 = pf.h2d_bytes
         ms_e2e, _ = timed(args.steps, lambda i: next(pf), True)
         h2d = (pf.h2d_bytes - b0) / max(1, args.steps)

@@ -86,18 +86,18 @@ class GraphedIteration:
         torch.cuda.synchronize()
         layers = [l for m in self._models() for l in m._gcc_norm_layers()]
         before = [l.num_batches for l in layers]
-        if not base.dist_on() or pix2pix.capture_collectives():
-            # one graph; under data parallel the NCCL all-reduces are captured as graph nodes
+        if not base.dist_on():
             self.graph = torch.cuda.CUDAGraph()
-            mode = "thread_local" if base.dist_on() else "global"
-            with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode):
+            with torch.cuda.graph(self.graph, stream=side):
                 self._iteration()
             self.segments = [(self.graph, None)]
         else:
-            # Data parallel without captured collectives: a chain of graphs cut at every gradient exchange; run()
-            # replays a segment, launches the NCCL all-reduce of that optimizer group's flat gradient arena eagerly on
-            # the same stream, replays the next segment (which starts with the Adam step).  All segments share one
-            # memory pool and are always replayed in capture order.
+            # Data parallel: a chain of graphs cut at every gradient exchange; run() replays a segment, launches the NCCL
+            # all-reduce of that optimizer group's flat gradient arena eagerly on the same stream, replays the next
+            # segment (which starts with the Adam step).  All segments share one memory pool and are always replayed
+            # in capture order.  (Capturing the collectives as graph nodes was tried twice in round 2 -- global and
+            # thread-local capture mode -- and dead-locks against ProcessGroupNCCL's watchdog thread with torch 2.11 /
+            # NCCL 2.28: not offered.)
             pool = torch.cuda.graph_pool_handle()
             state = {"g": None}
 

@@ -48,13 +48,6 @@ class _ArenaOptimizer:
 _dist_on = dist_on
 
 
-def capture_collectives():
-    """Whether a data-parallel iteration is captured as ONE CUDA graph with the NCCL all-reduces as graph nodes
-    (GCC_B200_CAPTURE_NCCL=1, experimental: needs a thread-local capture mode because ProcessGroupNCCL's watchdog
-    thread queries events during the capture) or, the default, as graph segments with eager collectives in between."""
-    return os.environ.get("GCC_B200_CAPTURE_NCCL", "0") == "1" and torch.distributed.get_backend() == "nccl"
-
-
 # Set by gcc_b200.graph.GraphedIteration while it captures a data-parallel iteration: the gradient exchange is a
 # cut point between two CUDA graphs (the collective itself is launched eagerly between the replays).
 _graph_segmenter = None

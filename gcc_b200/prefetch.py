@@ -46,9 +46,13 @@ class Prefetcher:
         self.slots[slot] = ent
         dt = self.dtype if (self.dtype is not None and t.is_floating_point()) else t.dtype
         cur = ent.get(key)
-        if cur is None or cur[0].shape != t.shape or cur[0].dtype != dt:
-            cur = (torch.empty(t.shape, dtype=dt).pin_memory(), torch.empty(t.shape, dtype=dt, device=self.device))
+        if cur is None or cur[1].shape != t.shape or cur[1].dtype != dt:
+            cur = [None, torch.empty(t.shape, dtype=dt, device=self.device)]
             ent[key] = cur
+        if cur[0] is None and not (t.is_pinned() and t.dtype == dt):
+            # page-locked staging only for sources that are not page-locked themselves (cudaHostAlloc is slow and
+            # synchronises the device: it happens once per slot, on the first batches)
+            cur[0] = torch.empty(t.shape, dtype=dt).pin_memory()
         return cur
 
     def _produce(self):
