@@ -427,9 +427,16 @@ class MobileResnetGenerator(_Net):
                     self.taps.append((h, s[1].cout))
             elif kind == "block":
                 r = h
-                for j, (dw, n1, pw, n2) in enumerate(s[1]):
-                    r = n2(pw(n1(dw(r), ACT_NONE)), ACT_RELU if j == 0 else ACT_NONE)
-                h = ops.AddFn.apply(h, r)
+                if ops.slab_ok(h):
+                    # 64 x 64 (and smaller) blocks: dw3x3 -> IN and IN -> ReLU / IN + skip as single launches (slab.cu)
+                    for j, (dw, n1, pw, n2) in enumerate(s[1]):
+                        t = pw(ops.DwInSlabFn.apply(r, dw.weight, dw.bias, dw))
+                        r = ops.InActSlabFn.apply(t, None if j == 0 else h, pw.cout, 2 if j == 0 else 0, 0.0)
+                    h = r
+                else:
+                    for j, (dw, n1, pw, n2) in enumerate(s[1]):
+                        r = n2(pw(n1(dw(r), ACT_NONE)), ACT_RELU if j == 0 else ACT_NONE)
+                    h = ops.AddFn.apply(h, r)
                 if s[2] in ("model.12", "model.15", "model.18"):
                     self.taps.append((h, s[3]))
             elif kind == "up":
@@ -520,6 +527,12 @@ class NLayerDiscriminator(_Net):
                 h = self.convs[0](h, ACT_LRELU, 0.2)        # plain D: LeakyReLU fused into the conv epilogue
             elif li == 0:
                 h = self.norms[0](self.convs[0](h), ACT_LRELU)
+            elif self.norms[li].mode == "in" and self.norms[li].alpha is None:
+                c = self.convs[li](h)
+                if ops.slab_ok(c):
+                    h = ops.InActSlabFn.apply(c, None, self.ch[li + 1], 1, 0.2)      # InstanceNorm + LeakyReLU, one launch
+                else:
+                    h = self.norms[li](c, ACT_LRELU)
             else:
                 c, csums = self.convs[li].with_stats(h)
                 h = self.norms[li](c, ACT_LRELU, None, csums)

@@ -844,6 +844,73 @@ class DwConvFn(torch.autograd.Function):
         return dx, None, None, None
 
 
+def slab_ok(x):
+    """The slab kernels (csrc/slab.cu) cover NHWC tensors whose H * W pixels of 8 channels fit one CTA (<= 4096)."""
+    return x.is_cuda and x.dim() == 4 and 4 <= x.shape[1] * x.shape[2] <= 4096 and x.shape[1] >= 2 and x.shape[2] >= 2
+
+
+class DwInSlabFn(torch.autograd.Function):
+    """InstanceNorm2d(depthwise3x3(ReflectionPad2d(1)(x)) + b) in ONE launch (SeparableConv2d's conv.0 + conv.1,
+    models/Pix2Pix.py:137-141); backward recomputes the depthwise output from x (saved: x and the 2 statistics per
+    (sample, channel)) and produces dx, dw, db in one launch."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer):
+        x = _check(x).contiguous()
+        n, h, w, cp = x.shape
+        z = torch.empty_like(x)
+        stats = torch.empty(n, cp, 2, dtype=torch.float32, device=x.device)
+        call("gcc_dw_in_slab_fwd_bf16", x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
+             z.data_ptr(), stats.data_ptr(), n, h, w, cp, layer.c, BN_EPS, _st())
+        ctx.layer = layer
+        ctx.save_for_backward(x, weight, bias, stats)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        layer = ctx.layer
+        x, weight, bias, stats = ctx.saved_tensors
+        dz = dz.contiguous()
+        n, h, w, cp = x.shape
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = layer.arena.flat_grad[layer.wname].data_ptr() if ctx.needs_input_grad[1] else None
+        gb = layer.arena.flat_grad[layer.bname].data_ptr() if (layer.bname and ctx.needs_input_grad[2]) else None
+        call("gcc_dw_in_slab_bwd_bf16", x.data_ptr(), dz.data_ptr(), weight.data_ptr(),
+             None if bias is None else bias.data_ptr(), stats.data_ptr(), None if dx is None else dx.data_ptr(), gw, gb,
+             n, h, w, cp, layer.c, _st())
+        return dx, None, None, None
+
+
+class InActSlabFn(torch.autograd.Function):
+    """act(InstanceNorm2d(y)) (+ residual) in ONE launch (the norm after the pointwise conv, the ReLU, and the block's
+    skip addition, models/Pix2Pix.py:166-197; also the InstanceNorm + LeakyReLU of CycleGAN's plain discriminator)."""
+
+    @staticmethod
+    def forward(ctx, y, res, c, act, slope):
+        y = _check(y).contiguous()
+        n, h, w, cp = y.shape
+        z = torch.empty_like(y)
+        stats = torch.empty(n, cp, 2, dtype=torch.float32, device=y.device)
+        call("gcc_in_act_slab_fwd_bf16", y.data_ptr(), None if res is None else res.contiguous().data_ptr(), z.data_ptr(),
+             stats.data_ptr(), n, h * w, cp, c, BN_EPS, act, slope, _st())
+        ctx.args = (c, act, slope, res is not None)
+        ctx.save_for_backward(y, stats)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, stats = ctx.saved_tensors
+        c, act, slope, has_res = ctx.args
+        dz = dz.contiguous()
+        n, h, w, cp = y.shape
+        dy = None
+        if ctx.needs_input_grad[0]:
+            dy = torch.empty_like(y)
+            call("gcc_in_act_slab_bwd_bf16", y.data_ptr(), dz.data_ptr(), stats.data_ptr(), dy.data_ptr(), n, h * w, cp, c,
+                 act, slope, _st())
+        return dy, (dz if (has_res and ctx.needs_input_grad[1]) else None), None, None, None
+
+
 # ------------------------------------------------------------------------------------- losses
 GAN_MODES = {"hinge": 0, "lsgan": 1, "vanilla": 2, "wgangp": 3}
 

@@ -179,6 +179,25 @@ int gcc_fold_wgrad_unpack_f32(const float* tmp, float* g, int C, int T, int CG, 
 /* nn.Conv2d zero padding made explicit for the stem path (backward = 1: crop the gradient); `slack` extra zero rows per image */
 int gcc_zero_pad_bf16(const void* x, void* y, int N, int H, int W, int Cp, int pad, int slack, int backward, void* stream);
 
+/* ---- "slab" kernels of the InstanceNorm networks (slab.cu) ----
+ * MobileResnetBlock (models/Pix2Pix.py:147-197) and CycleGAN's InstanceNorm PatchGAN (models/CycleGAN.py:140-178) at the
+ * resolutions where one CTA owns all H*W <= 4096 pixels of 8 channels of one sample: InstanceNorm2d's statistics become a
+ * block reduction and each chain is ONE launch reading its input once (gcc_slab_supported tells whether a shape fits).
+ *   gcc_dw_in_slab_fwd:  z = InstanceNorm(depthwise3x3(ReflectionPad2d(1)(x)) + b)     (SeparableConv2d conv.0 + conv.1)
+ *   gcc_dw_in_slab_bwd:  dx, dw += , dbias += from dz; the depthwise output is recomputed from x (saved: x, stats)
+ *   gcc_in_act_slab_fwd: z = act(InstanceNorm(y)) (+ res)   act 0 none / 1 leaky-relu(slope) / 2 relu; res = block skip
+ *   gcc_in_act_slab_bwd: dy from dz (the skip's own gradient is dz)
+ * stats: fp32 [N][Cp][2] = (mean, rstd) per (sample, channel), written by the forward kernels for their backward. */
+int gcc_slab_supported(int H, int W);
+int gcc_dw_in_slab_fwd_bf16(const void* x, const float* w, const float* bias, void* z, float* stats, int N, int H, int W,
+                            int Cp, int C, float eps, void* stream);
+int gcc_dw_in_slab_bwd_bf16(const void* x, const void* dz, const float* w, const float* bias, const float* stats, void* dx,
+                            float* dw, float* dbias, int N, int H, int W, int Cp, int C, void* stream);
+int gcc_in_act_slab_fwd_bf16(const void* y, const void* res, void* z, float* stats, int N, long long HW, int Cp, int C,
+                             float eps, int act, float slope, void* stream);
+int gcc_in_act_slab_bwd_bf16(const void* y, const void* dz, const float* stats, void* dy, int N, long long HW, int Cp, int C,
+                             int act, float slope, void* stream);
+
 /* ---- loss reductions (loss.cu) ---- */
 /* GANLoss (models/GANLoss.py:38-59). mode: 0 hinge, 1 lsgan, 2 vanilla, 3 wgangp.
  * kind: 0 D-real, 1 D-fake, 2 G.  out is an fp32 device scalar that the caller zeroes. */

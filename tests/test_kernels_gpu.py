@@ -390,3 +390,54 @@ def test_adam_arena_matches_torch(G):
     pk = A.packs["w"]
     assert torch.equal(pk.direct[..., :5].float(), bf(A.params["w"].detach().permute(0, 2, 3, 1).reshape(8, 9, 5)))
     assert torch.equal(pk.transposed[..., :8].float(), bf(A.params["w"].detach().permute(1, 2, 3, 0).reshape(5, 9, 8)))
+
+
+# ------------------------------------------------------------------------------------ slab kernels
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 24), (3, 9, 7, 13), (2, 64, 64, 40), (1, 2, 3, 8)])
+def test_dw_in_slab_matches_torch(G, N, H, W, C):
+    """InstanceNorm(dw3x3(ReflectionPad(x)) + b) in one launch and its one-launch backward (csrc/slab.cu)."""
+    A = G.arena.ParamArena("cuda")
+    dw = G.nets.DwConvLayer(A, "dw", C)
+    A.finalize()
+    dw.bind()
+    w0, b0 = rnd((C, 1, 3, 3), 1, 0.5), rnd((C,), 2)
+    with torch.no_grad():
+        dw.weight.copy_(w0)
+        dw.bias.copy_(b0)
+    x = rnd((N, C, H, W), 3)
+    xh = nhwc(x, G).requires_grad_(True)
+    z = G.ops.DwInSlabFn.apply(xh, dw.weight, dw.bias, dw)
+    gz = rnd((N, C, H, W), 4)
+    A.zero_grad()
+    z.backward(nhwc(gz, G))
+    xr, wr, br = bf(x).requires_grad_(True), w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    yr = F.conv2d(F.pad(xr, (1, 1, 1, 1), mode="reflect"), wr, br, groups=C)
+    zr = F.instance_norm(yr, eps=1e-5)
+    zr.backward(bf(gz))
+    assert rel_err(nchw(z.detach(), C, G), zr.detach()) < BF16_TOL
+    assert rel_err(nchw(xh.grad, C, G), xr.grad) < 1.2e-2     # (dy1 is rounded to bf16 before the data-gradient taps)
+    assert rel_err(dw.weight.grad, wr.grad) < 1e-2
+    if C % 8:
+        assert bool((z.detach()[..., C:] == 0).all())
+
+
+@pytest.mark.parametrize("N,H,W,C,act,res", [(2, 16, 16, 24, 2, False), (3, 9, 7, 13, 0, True), (2, 64, 64, 40, 1, False),
+                                             (2, 31, 31, 64, 1, False)])
+def test_in_act_slab_matches_torch(G, N, H, W, C, act, res):
+    y = rnd((N, C, H, W), 5, 2.0) + 0.3
+    yh = nhwc(y, G).requires_grad_(True)
+    r = rnd((N, C, H, W), 6)
+    rh = nhwc(r, G).requires_grad_(True) if res else None
+    z = G.ops.InActSlabFn.apply(yh, rh, C, act, 0.2)
+    gz = rnd((N, C, H, W), 7)
+    z.backward(nhwc(gz, G))
+    yr = bf(y).requires_grad_(True)
+    rr = bf(r).requires_grad_(True)
+    t = F.instance_norm(yr, eps=1e-5)
+    t = F.leaky_relu(t, 0.2) if act == 1 else (F.relu(t) if act == 2 else t)
+    zr = t + rr if res else t
+    zr.backward(bf(gz))
+    assert rel_err(nchw(z.detach(), C, G), zr.detach()) < BF16_TOL
+    assert rel_err(nchw(yh.grad, C, G), yr.grad) < 1.2e-2
+    if res:
+        assert rel_err(nchw(rh.grad, C, G), rr.grad) < BF16_TOL
