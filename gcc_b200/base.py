@@ -106,7 +106,14 @@ class GccModelMixin:
                 net._seed_ranked = True
 
     # ---- resume -----------------------------------------------------------------------------------------------
+    def finish_pending_steps(self):
+        """Complete deferred data-parallel optimizer steps before parameters are read from outside the step."""
+        for o in self._gcc_optimizers().values():
+            if hasattr(o, "finish"):
+                o.finish()
+
     def resume_state(self, with_teacher=True):
+        self.finish_pending_steps()
         cpu = lambda t: t.detach().to("cpu", copy=True)
         st = {"arenas": {}, "buffers": {}, "ema": {k: cpu(v) for k, v in self._ema_states.items()},
               "ema_beta": float(self.opt.ema_beta), "seeds": {}, "lr": {}, "sched": []}

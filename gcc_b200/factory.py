@@ -37,6 +37,8 @@ def build_pair(opt, cfgs=(None, None)):
         topt.online_distillation = False
         topt.generator_only = False
         teacher = cls(topt)
+        if opt.model == "pix2pix":
+            teacher._defer_G_step = True   # data parallel: the teacher generator's exchange overlaps the student's steps
         teacher.model_train()
         setattr(model, "teacher_model", teacher)
         model.init_distillation()

@@ -31,6 +31,7 @@ class GraphedIteration:
         self.has_arch = bool(getattr(model.opt, "darts_discriminator", False)) and model.teacher_model is not None
         self._bn_delta = []
         self.pace = True
+        self._async = {}
         self._pace_ev = torch.cuda.Event()
 
     # ------------------------------------------------------------------ inputs
@@ -57,6 +58,8 @@ class GraphedIteration:
             m.set_input(self.static_val)
             m.clipping_mask_alpha()
             m.optimizer_netD_arch()
+        for mm in self._models():          # an iteration ends with no optimizer step in flight
+            mm.finish_pending_steps()
 
     def _models(self):
         return [m for m in (self.model, self.model.teacher_model) if m is not None]
@@ -105,9 +108,9 @@ class GraphedIteration:
                 state["g"] = torch.cuda.CUDAGraph()
                 state["g"].capture_begin(pool=pool)
 
-            def cut(arena):
+            def cut(arena, action="allreduce"):
                 state["g"].capture_end()
-                self.segments.append((state["g"], arena))
+                self.segments.append((state["g"], (arena, action)))
                 begin()
 
             with torch.cuda.stream(side):
@@ -134,10 +137,16 @@ class GraphedIteration:
         from . import pix2pix
         self.load(train, val)
         self._refresh()
-        for g, arena in self.segments:
+        for g, boundary in self.segments:
             g.replay()
-            if arena is not None:
-                pix2pix._allreduce_grads(arena)
+            if boundary is not None:
+                arena, action = boundary
+                if action == "allreduce":
+                    pix2pix._allreduce_grads(arena)
+                elif action == "allreduce_async":        # deferred step: the exchange overlaps the next segments
+                    self._async[id(arena)] = pix2pix._allreduce_grads(arena, asynchronous=True)
+                else:                                    # "wait": the next segment starts with that arena's Adam step
+                    self._async.pop(id(arena)).wait()
         for l, d in self._bn_delta:
             l.num_batches += d
         self.replays += 1

@@ -26,7 +26,12 @@ from .ops import GAN_MODES
 
 
 class _ArenaOptimizer:
-    """torch.optim-like facade over a ParamArena (zero_grad / step / param_groups[0]['lr'])."""
+    """torch.optim-like facade over a ParamArena (zero_grad / step / param_groups[0]['lr']).
+
+    ``step(defer=True)`` (data parallel only): the gradient all-reduce is launched asynchronously and the Adam update
+    waits until ``finish()`` -- called before the parameters are next read.  The teacher generator's arena (60 % of the
+    exchanged bytes) uses it: its new weights are first needed by the gate step's teacher forward, so the exchange
+    hides behind the student's discriminator / generator steps."""
 
     def __init__(self, arena, lr, betas):
         self.arena = arena
@@ -34,15 +39,31 @@ class _ArenaOptimizer:
         if arena.finalized:
             arena._write_hyper()
         self.param_groups = [{"lr": lr, "initial_lr": lr, "betas": betas}]
+        self._pending = None
 
     def zero_grad(self):
+        self.finish()
         self.arena.zero_grad()
 
-    def step(self):
+    def step(self, defer=False):
+        self.finish()
         if not capturing():
             self.arena.set_lr(self.param_groups[0]["lr"])
+        if defer and _dist_on():
+            self._pending = _allreduce_grads(self.arena, asynchronous=True)
+            return
         _allreduce_grads(self.arena)
         self.arena.step()
+
+    def finish(self):
+        """Complete a deferred step: wait for the exchange, run the fused Adam update."""
+        if self._pending is not None:
+            pending, self._pending = self._pending, None
+            if pending == "segment":
+                _graph_segmenter(self.arena, "wait")       # capture: cut; run() waits for the exchange here
+            else:
+                pending.wait()
+            self.arena.step()
 
 
 _dist_on = dist_on
@@ -50,22 +71,33 @@ _dist_on = dist_on
 
 # Set by gcc_b200.graph.GraphedIteration while it captures a data-parallel iteration: the gradient exchange is a
 # cut point between two CUDA graphs (the collective itself is launched eagerly between the replays).
+# Called as _graph_segmenter(arena, action) with action in {"allreduce", "allreduce_async", "wait"}.
 _graph_segmenter = None
 
 
-def _allreduce_grads(arena):
-    """Data parallel: average the flat gradient arena over ranks (NCCL over NVLink) before the step."""
+def _allreduce_grads(arena, asynchronous=False):
+    """Data parallel: average the flat gradient arena over ranks (NCCL over NVLink) before the step.  Asynchronous:
+    returns a handle (``.wait()`` before the gradients are consumed); the collective runs on NCCL's own stream and
+    overlaps whatever is queued on the compute stream meanwhile."""
     if not _dist_on():
-        return
+        return None
     if _graph_segmenter is not None:
-        _graph_segmenter(arena)
-        return
+        _graph_segmenter(arena, "allreduce_async" if asynchronous else "allreduce")
+        return "segment" if asynchronous else None
     dist = torch.distributed
     if dist.get_backend() == "nccl":
-        dist.all_reduce(arena.G, op=dist.ReduceOp.AVG)
+        work = dist.all_reduce(arena.G, op=dist.ReduceOp.AVG, async_op=asynchronous)
     else:
-        dist.all_reduce(arena.G, op=dist.ReduceOp.SUM)
+        work = dist.all_reduce(arena.G, op=dist.ReduceOp.SUM, async_op=False)
         arena.G.mul_(1.0 / dist.get_world_size())
+        if asynchronous:
+            work = _DoneWork()
+    return work if asynchronous else None
+
+
+class _DoneWork:
+    def wait(self):
+        return True
 
 
 class _LambdaLR:
@@ -284,6 +316,7 @@ class Pix2PixModel(GccModelMixin, nn.Module):
         return ops.to_nchw(self.fake_B_nhwc.detach(), 3)
 
     def forward(self):
+        self.optimizer_G.finish()          # (a deferred data-parallel generator step completes before its weights are read)
         self.fake_B_nhwc = self.netG(self.real_A_nhwc)
         self.g_taps = list(self.netG.taps)
 
@@ -408,7 +441,7 @@ class Pix2PixModel(GccModelMixin, nn.Module):
         self.set_requires_grad(self.netD, False)
         self.optimizer_G.zero_grad()
         self.backward_G()
-        self.optimizer_G.step()
+        self.optimizer_G.step(defer=getattr(self, "_defer_G_step", False))
         self._release_graphs()
 
     def optimizer_netD_arch(self):
@@ -503,6 +536,7 @@ class Pix2PixModel(GccModelMixin, nn.Module):
         return self.filter_cfgs, self.channel_cfgs
 
     def save_models(self, epoch, save_dir, fid=None, isbest=False, direction="AtoB"):
+        self.finish_pending_steps()
         os.makedirs(save_dir, exist_ok=True)
         ckpt = {"G": self.netG.state_dict(), "D": self.netD.state_dict(), "epoch": epoch,
                 "cfg": (self.filter_cfgs, self.channel_cfgs), "fid": fid}
@@ -550,6 +584,7 @@ def build_teacher(model, opt):
     topt.online_distillation = False
     topt.generator_only = False
     teacher = Pix2PixModel(topt)
+    teacher._defer_G_step = True           # data parallel: its generator exchange overlaps the student's steps
     teacher.model_train()
     setattr(model, "teacher_model", teacher)
     model.init_distillation()
