@@ -880,7 +880,9 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: bad arguments");
     return GCC_ERR_ARG;
   }
-  const int Rp = (R + 7) / 8 * 8;
+  // physical output columns: the whole row of y when the conv owns it (y_coff == 0: pad channels are written as
+  // zeros, whatever multiple of 8 the caller pads to), round8(R) inside a channel window of a wider buffer
+  const int Rp = (y_coff == 0 && Cy >= R) ? Cy : (R + 7) / 8 * 8;
   if (y_coff + Rp > Cy) {
     gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: output channel window out of range");
     return GCC_ERR_ARG;

@@ -1379,8 +1379,8 @@ extern "C" int gcc_unfold_taps_bf16(const void* dy, void* dcol, int Ccol, int CG
   return GCC_OK;
 }
 extern "C" int gcc_fold_weight_pack_bf16(const void* src, void* out, int mode, int C, int T, int CG, int K, int Kp, int Cp,
-                                         void* stream) {
-  const int rows_p = (T * CG + 7) / 8 * 8;
+                                         int rows_p, void* stream) {
+  if (rows_p < T * CG || (rows_p % 8)) { gcc_set_error(__FILE__, __LINE__, "fold_weight_pack: bad rows_p"); return GCC_ERR_ARG; }
   const long long total = mode == 0 ? (long long)rows_p * Kp : (long long)K * rows_p;
   gcc_launch(fold_weight_pack_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, (const bf16*)src, (bf16*)out, mode, C, T,
              CG, K, Kp, Cp, rows_p);

@@ -295,7 +295,7 @@ class UnetGenertor(_Net):
         if j is None or not like.is_cuda:
             return None
         ca, uo = self.lv[i][1], self.lv[j][3]
-        if ca % 8 or uo % 8 or (self.use_dropout and self.training and j in (4, 5, 6)):
+        if rp8(ca) != ca or rp8(uo) != uo or (self.use_dropout and self.training and j in (4, 5, 6)):
             return None
         n, h, w, _ = like.shape
         return torch.empty(n, h, w, ca + uo, dtype=torch.bfloat16, device=like.device)

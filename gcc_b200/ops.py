@@ -444,7 +444,7 @@ class StemConvFn(torch.autograd.Function):
             def build(old):
                 buf = old if old is not None else torch.empty(ccol, pk.d0p, dtype=torch.bfloat16, device=dev)
                 call("gcc_fold_weight_pack_bf16", pk.transposed.data_ptr(), buf.data_ptr(), 0, layer.cin, T, cg, layer.cout,
-                     pk.d0p, 0, st)
+                     pk.d0p, 0, ccol, st)
                 return buf
             w2 = _derived(layer, "stem_dgrad", build)           # [(tap, c_in)][cout_p]
             ycol = torch.empty(n, oh, ow, ccol, dtype=torch.bfloat16, device=dev)
@@ -493,7 +493,7 @@ class FoldConvFn(torch.autograd.Function):
         def build(old):
             buf = old if old is not None else torch.empty(ccol, pk.d1p, dtype=torch.bfloat16, device=x.device)
             call("gcc_fold_weight_pack_bf16", pk.direct.data_ptr(), buf.data_ptr(), 0, layer.cout, T, cg, layer.cin, pk.d1p,
-                 0, st)
+                 0, ccol, st)
             return buf
         w2 = _derived(layer, "fold_fwd", build)                  # [(tap, c_out)][cin_p]
         ycol = torch.empty(n, h, w, ccol, dtype=torch.bfloat16, device=x.device)
@@ -530,7 +530,7 @@ class FoldConvFn(torch.autograd.Function):
             def build(old):
                 buf = old if old is not None else torch.empty(layer.cin, ccol, dtype=torch.bfloat16, device=dev)
                 call("gcc_fold_weight_pack_bf16", pk.transposed.data_ptr(), buf.data_ptr(), 1, layer.cout, T, cg, layer.cin, 0,
-                     pk.d0p, st)
+                     pk.d0p, ccol, st)
                 return buf
             w3 = _derived(layer, "fold_dgrad", build)            # [cin][(tap, c_out)]
             dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=dev)

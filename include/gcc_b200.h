@@ -168,13 +168,15 @@ int gcc_rowwin_wgrad_unpack_f32(const float* tmp, float* g, int R, int KH, int K
  * over the ycol grid [N][GH][GW][Ccol] (terms outside are skipped); dir = +1: the conv itself, dir = -1: the data gradient
  * of a stem conv on its padded input grid.  gcc_unfold_taps_bf16 builds dcol[n,gy,gx,(tap)*CG+c] = dy[n,gy-kh-off,gx-kw-off,c]
  * for the head's data / weight gradient GEMMs; gcc_fold_weight_pack_bf16 builds the GEMM weight operands from the arena
- * packs (mode 0: [(tap,c)][K] from direct [C][T][Kp]; mode 1: [K][(tap,c)] from transposed [K][T][Cp]);
+ * packs (mode 0: [(tap,c)][K] from direct [C][T][Kp]; mode 1: [K][(tap,c)] from transposed [K][T][Cp]; rows_p = padded
+ * number of (tap,c) rows / columns);
  * gcc_fold_wgrad_unpack_f32: g[c][t][k] += tmp[(t*CG+c)][k]. */
 int gcc_fold_taps_bf16(const void* ycol, int Ccol, int CG, int KH, int KW, int C, const float* bias, int act, void* y, int N,
                        int GH, int GW, int OH, int OW, int dir, int off, void* stream);
 int gcc_unfold_taps_bf16(const void* dy, void* dcol, int Ccol, int CG, int KH, int KW, int N, int GH, int GW, int OH, int OW,
                          int off, void* stream);
-int gcc_fold_weight_pack_bf16(const void* src, void* out, int mode, int C, int T, int CG, int K, int Kp, int Cp, void* stream);
+int gcc_fold_weight_pack_bf16(const void* src, void* out, int mode, int C, int T, int CG, int K, int Kp, int Cp, int rows_p,
+                              void* stream);
 int gcc_fold_wgrad_unpack_f32(const float* tmp, float* g, int C, int T, int CG, int K, void* stream);
 /* nn.Conv2d zero padding made explicit for the stem path (backward = 1: crop the gradient); `slack` extra zero rows per image */
 int gcc_zero_pad_bf16(const void* x, void* y, int N, int H, int W, int Cp, int pad, int slack, int backward, void* stream);
