@@ -10,6 +10,8 @@
 //
 // All kernels are HBM-bound: 16-byte vector accesses, channel index = vector index % (Cp/8), fp32
 // statistics accumulated per block in shared memory then one atomicAdd per (block, channel).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gcc {
@@ -253,6 +255,7 @@ __global__ void norm_apply_eval_kernel(NormArgs a, const float* __restrict__ rme
 
 // ------------------------------------------------------------------------------------- backward
 // red[(n)][0:Cp) += sum dg ; red[(n)][Cp:2Cp) += sum dg * xhat      dg = dy*act'(g) + dy2*act2'(g)
+template <int U, bool HAS_D2>
 __global__ void __launch_bounds__(256, 2)
 norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
                        const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2, float* __restrict__ red) {
@@ -281,7 +284,7 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
     }
     const bf16* xb = a.x + pix0 * a.Cp + g * 8;
     const bf16* d1b = dy ? dy + pix0 * dy_Cp + dy_coff + g * 8 : nullptr;
-    const bf16* d2b = dy2 ? dy2 + pix0 * dy2_Cp + dy2_coff + g * 8 : nullptr;
+    const bf16* d2b = (HAS_D2 && dy2) ? dy2 + pix0 * dy2_Cp + dy2_coff + g * 8 : nullptr;
     auto accum = [&](const uint4 ux, const uint4 u1, const uint4 u2) {
       const Vec8 xv = unpack8(ux), d1 = unpack8(u1), d2 = unpack8(u2);
 #pragma unroll
@@ -290,11 +293,11 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
         const float gg = xh * cg[k] + cb[k];
         float dg = 0.f;
         if (d1b) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
-        if (d2b) dg += d2.v[k] * act_grad(gg, act2, a.slope);
+        if (HAS_D2 && d2b) dg += d2.v[k] * act_grad(gg, act2, a.slope);
         s1[k] += dg;
         if (a.gate_after) {  // S2 = sum dy * act(z): the gate gradient of y = mask * act(z)
           if (d1b) s2[k] += d1.v[k] * act_fwd(gg, a.act, a.slope);
-          if (d2b) s2[k] += d2.v[k] * act_fwd(gg, act2, a.slope);
+          if (HAS_D2 && d2b) s2[k] += d2.v[k] * act_fwd(gg, act2, a.slope);
         } else {
           s2[k] += dg * xh;
         }
@@ -304,18 +307,18 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
     const long long step = (long long)gridDim.x * lanes;
     auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * a.Cp) : zero; };
     auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * dy_Cp) : zero; };
-    auto ld2 = [&](long long q) { return (d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
-    // register double buffer over pairs of pixels (out-of-range pixels load zeros and contribute nothing)
+    auto ld2 = [&](long long q) { return (HAS_D2 && d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
+    // register double buffer over groups of U pixels (out-of-range pixels load zeros and contribute nothing)
     long long p = (long long)blockIdx.x * lanes + lane;
-    uint4 cx[2], c1[2], c2[2], nx[2], n1[2], n2[2];
+    uint4 cx[U], c1[U], c2[U], nx[U], n1[U], n2[U];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) { cx[j] = ldx(p + j * step); c1[j] = ld1(p + j * step); c2[j] = ld2(p + j * step); }
+    for (int j = 0; j < U; ++j) { cx[j] = ldx(p + j * step); c1[j] = ld1(p + j * step); c2[j] = ld2(p + j * step); }
     while (p < a.npix) {
-      p += 2 * step;
+      p += U * step;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { nx[j] = ldx(p + j * step); n1[j] = ld1(p + j * step); n2[j] = ld2(p + j * step); }
+      for (int j = 0; j < U; ++j) { nx[j] = ldx(p + j * step); n1[j] = ld1(p + j * step); n2[j] = ld2(p + j * step); }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < U; ++j) {
         accum(cx[j], c1[j], c2[j]);
         cx[j] = nx[j]; c1[j] = n1[j]; c2[j] = n2[j];
       }
@@ -340,7 +343,7 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
 // dx = gamma*rstd*mask * (dg - (S1 + xhat*S2)/M)   [norm]   or   dx = mask*dg [identity]
 // with per-thread register coefficients: gg = x*p + q, dx = c1*dg - c2 - c3*x  (thread = channel group x lane).
 // block (0,0) also accumulates dgamma += mask*S2, dbeta += mask*S1, dalpha += gamma*S2 + beta*S1 (summed over n).
-template <bool HAS_D2>
+template <bool HAS_D2, int U>
 __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int nimg, int lanes, const bf16* __restrict__ dy, int dy_Cp,
                                       int dy_coff, const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2,
                                       const float* __restrict__ red, const float* __restrict__ red_param,
@@ -395,17 +398,17 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
     auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * a.Cp) : zero; };
     auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * dy_Cp) : zero; };
     auto ld2 = [&](long long q) { return (HAS_D2 && d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
-    // register double buffer over pairs of pixels
+    // register double buffer over groups of U pixels
     long long p = (long long)blockIdx.x * lanes + lane;
-    uint4 cx[2], e1[2], e2[2], nx[2], n1[2], n2[2];
+    uint4 cx[U], e1[U], e2[U], nx[U], n1[U], n2[U];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) { cx[j] = ldx(p + j * step); e1[j] = ld1(p + j * step); e2[j] = ld2(p + j * step); }
+    for (int j = 0; j < U; ++j) { cx[j] = ldx(p + j * step); e1[j] = ld1(p + j * step); e2[j] = ld2(p + j * step); }
     while (p < a.npix) {
-      const long long pn = p + 2 * step;
+      const long long pn = p + U * step;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { nx[j] = ldx(pn + j * step); n1[j] = ld1(pn + j * step); n2[j] = ld2(pn + j * step); }
+      for (int j = 0; j < U; ++j) { nx[j] = ldx(pn + j * step); n1[j] = ld1(pn + j * step); n2[j] = ld2(pn + j * step); }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < U; ++j) {
         if (p + j * step < a.npix) emit(cx[j], e1[j], e2[j], p + j * step);
         cx[j] = nx[j]; e1[j] = n1[j]; e2[j] = n2[j];
       }
@@ -466,9 +469,13 @@ static int fill_args(NormArgs& a, const void* x, int N, long long HW, int Cp, in
 }
 
 // blocks for a (group, lane) kernel: each thread visits >= `per` pixels, whole grid <= ~16 CTAs per SM
-static int lane_blocks(long long npix, int lanes, int groups, int per) {
+// `waves` = CTAs per SM the grid is capped at.  The forward apply kernel (4 resident CTAs per SM, 4 B / element) does
+// not care (16); the backward apply kernel (2 resident CTAs, 6 B / element, a dependent coefficient prologue per CTA)
+// wants exactly ONE resident wave: measured on the PatchGAN activations at batch 32 (scripts/exp_norm_unroll.py,
+// L2 flushed): 96 -> 76 us (134 MB tensors), 66 -> 45, 39 -> 29, 62 -> 43 us with the cap at 2 and 4 pixels in flight.
+static int lane_blocks(long long npix, int lanes, int groups, int per, int waves = 16) {
   long long b = (npix + (long long)lanes * per * 4 - 1) / ((long long)lanes * per * 4);
-  long long cap = (148LL * 16 + groups - 1) / groups;
+  long long cap = (148LL * waves + groups - 1) / groups;
   if (cap < 1) cap = 1;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
@@ -578,20 +585,24 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
     const long long cap = (148LL * 2 + groups - 1) / groups;  // one resident wave (launch bounds: 2 CTAs / SM)
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    gcc_launch(norm_bwd_reduce_kernel, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st, 
-        a, lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
+    if (dy2 == nullptr)   // (4 pixels in flight spill in this kernel and measured 25 % slower)
+      gcc_launch(norm_bwd_reduce_kernel<2, false>, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st, a,
+                 lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
+    else
+      gcc_launch(norm_bwd_reduce_kernel<2, true>, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st, a,
+                 lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
     GCC_CHECK_LAUNCH();
   }
   if (phase == 1) return GCC_OK;
   int alanes;
   const int athreads = stats_threads(a.G, &alanes);
-  const int bx = dx ? lane_blocks(a.npix, alanes, groups, 2) : 1;
+  const int bx = dx ? lane_blocks(a.npix, alanes, groups, 2, 2) : 1;
   if (dy2 != nullptr)
-    gcc_launch(norm_bwd_apply_kernel<true>, dim3(bx, dx ? groups : 1), athreads, 0, st, 
+    gcc_launch(norm_bwd_apply_kernel<true, 2>, dim3(bx, dx ? groups : 1), athreads, 0, st, 
         a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red, red_param,
         (bf16*)dx, dgamma, dbeta, dalpha);
   else
-    gcc_launch(norm_bwd_apply_kernel<false>, dim3(bx, dx ? groups : 1), athreads, 0, st, 
+    gcc_launch(norm_bwd_apply_kernel<false, 4>, dim3(bx, dx ? groups : 1), athreads, 0, st, 
         a, N, alanes, (const bf16*)dy, dy_Cp, dy_coff, nullptr, 0, 0, 0, red, red_param, (bf16*)dx, dgamma, dbeta,
         dalpha);
   GCC_CHECK_LAUNCH();

@@ -51,23 +51,56 @@ __device__ __forceinline__ void block_sum16(float (&v)[16], float* red /* [NWARP
     v[i] = a;
   }
 }
-// depthwise 3x3 with reflection padding 1 at pixel (r, c) from the shared-memory slab
-__device__ __forceinline__ void dw_at(const uint4* sx, int r, int c, int H, int W, const float (&we)[3][3][8],
-                                      const float (&bs)[8], float (&y)[8]) {
+// Slab index of pixel i: one 16-byte pad after every 16 pixels, so that threads walking consecutive 16-pixel row
+// segments (start addresses 272 bytes apart) hit distinct shared-memory banks.
+__device__ __forceinline__ int sidx(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int slab_elems(int hw) { return hw + (hw >> 4) + 1; }
+
+// Depthwise 3x3 with reflection padding 1 over the pixels [c0, c1) of row r, from the shared-memory slab: a 3 x 3
+// window of unpacked fp32 vectors slides along the row (3 shared-memory loads and 24 conversions per pixel instead of
+// 9 and 72; the loop is unrolled by 3 so that the window columns rotate by index, not by register moves).
+// f(c, y, win, left, mid, right): y[8] = conv result at column c, win[a][col][8] the input window (col indices given).
+template <typename F>
+__device__ __forceinline__ void dw_row_run(const uint4* sx, int r, int c0, int c1, int H, int W, const float (&we)[3][3][8],
+                                           const float (&bs)[8], F&& f) {
+  int rowoff[3];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) y[k] = bs[k];
+  for (int a = 0; a < 3; ++a) rowoff[a] = refl(r + a - 1, H) * W;
+  float win[3][3][8];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const int rr = refl(r + a - 1, H);
+    unpack8f(sx[sidx(rowoff[a] + refl(c0 - 1, W))], win[a][0]);
+    unpack8f(sx[sidx(rowoff[a] + c0)], win[a][1]);
+  }
+  for (int c = c0; c < c1; c += 3) {
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int cc = refl(c + b - 1, W);
-      float xv[8];
-      unpack8f(sx[rr * W + cc], xv);
+    for (int ph = 0; ph < 3; ++ph) {
+      const int cc = c + ph;
+      if (cc < c1) {
+        constexpr int kL[3] = {0, 1, 2}, kM[3] = {1, 2, 0}, kR[3] = {2, 0, 1};
+        const int L = kL[ph], M = kM[ph], R = kR[ph];
+        const int cn = refl(cc + 1, W);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) y[k] += xv[k] * we[a][b][k];
+        for (int a = 0; a < 3; ++a) unpack8f(sx[sidx(rowoff[a] + cn)], win[a][R]);
+        float y[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = bs[k];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            y[k] += win[a][L][k] * we[a][0][k] + win[a][M][k] * we[a][1][k] + win[a][R][k] * we[a][2][k];
+        f(cc, y, win, L, M, R);
+      }
     }
   }
+}
+// segment length so that the CTA's threads share the H * W pixels as row segments
+__device__ __forceinline__ int slab_seg(int H, int W) {
+  int sg = (H * W + kSlabThreads - 1) / kSlabThreads;
+  if (sg < 1) sg = 1;
+  if (sg > W) sg = W;
+  return sg;
 }
 
 // stats: fp32 [N][Cp][2] = (mean, rstd) of the depthwise output, saved for the backward pass
@@ -80,7 +113,7 @@ dw_in_slab_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, c
   __shared__ float red[8 * 16];
   const int g = blockIdx.x, n = blockIdx.y, HW = H * W;
   const uint4* xg = reinterpret_cast<const uint4*>(x) + (long long)n * HW * G + g;
-  for (int p = threadIdx.x; p < HW; p += kSlabThreads) slab[p] = xg[(long long)p * G];
+  for (int p = threadIdx.x; p < HW; p += kSlabThreads) slab[sidx(p)] = xg[(long long)p * G];
   float we[3][3][8], bs[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -92,17 +125,20 @@ dw_in_slab_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, c
       for (int b = 0; b < 3; ++b) we[a][b][k] = c < C ? w[c * 9 + a * 3 + b] : 0.f;
   }
   __syncthreads();
+  const int seg = slab_seg(H, W), segs = (W + seg - 1) / seg, nseg = H * segs;
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int p = threadIdx.x; p < HW; p += kSlabThreads) {
-    float y[8];
-    dw_at(slab, p / W, p % W, H, W, we, bs, y);
+  for (int sgi = threadIdx.x; sgi < nseg; sgi += kSlabThreads) {
+    const int r = sgi / segs, c0 = (sgi % segs) * seg;
+    dw_row_run(slab, r, c0, min(W, c0 + seg), H, W, we, bs,
+               [&](int, const float (&y)[8], const float (&)[3][3][8], int, int, int) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[k] += y[k];
-      acc[8 + k] += y[k] * y[k];
-    }
+                 for (int k = 0; k < 8; ++k) {
+                   acc[k] += y[k];
+                   acc[8 + k] += y[k] * y[k];
+                 }
+               });
   }
   block_sum16<kSlabThreads / 32>(acc, red);
   float mean[8], rstd[8];
@@ -119,12 +155,15 @@ dw_in_slab_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, c
     so[1] = rstd[threadIdx.x];
   }
   uint4* zg = reinterpret_cast<uint4*>(z) + (long long)n * HW * G + g;
-  for (int p = threadIdx.x; p < HW; p += kSlabThreads) {
-    float y[8];
-    dw_at(slab, p / W, p % W, H, W, we, bs, y);
+  for (int sgi = threadIdx.x; sgi < nseg; sgi += kSlabThreads) {
+    const int r = sgi / segs, c0 = (sgi % segs) * seg;
+    dw_row_run(slab, r, c0, min(W, c0 + seg), H, W, we, bs,
+               [&](int c, const float (&y)[8], const float (&)[3][3][8], int, int, int) {
+                 float o[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) y[k] = (y[k] - mean[k]) * rstd[k];
-    zg[(long long)p * G] = pack8f(y);
+                 for (int k = 0; k < 8; ++k) o[k] = (y[k] - mean[k]) * rstd[k];
+                 zg[(long long)(r * W + c) * G] = pack8f(o);
+               });
   }
 }
 
@@ -137,12 +176,13 @@ dw_in_slab_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, c
   pdl_launch_dependents();
   extern __shared__ uint4 slab[];  // [H*W] x, then [H*W] dy1 (gradient of the depthwise output, bf16)
   __shared__ float red[8 * 16];
+  __shared__ float fr[8 * 80];     // per-warp partial sums of the 72 + 8 parameter gradients
   const int g = blockIdx.x, n = blockIdx.y, HW = H * W;
   uint4* sx = slab;
-  uint4* sd = slab + HW;
+  uint4* sd = slab + slab_elems(HW);
   const uint4* xg = reinterpret_cast<const uint4*>(x) + (long long)n * HW * G + g;
   const uint4* dzg = reinterpret_cast<const uint4*>(dz) + (long long)n * HW * G + g;
-  for (int p = threadIdx.x; p < HW; p += kSlabThreads) sx[p] = xg[(long long)p * G];
+  for (int p = threadIdx.x; p < HW; p += kSlabThreads) sx[sidx(p)] = xg[(long long)p * G];
   float we[3][3][8], bs[8], mean[8], rstd[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -157,60 +197,99 @@ dw_in_slab_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, c
       for (int b = 0; b < 3; ++b) we[a][b][k] = c < C ? w[c * 9 + a * 3 + b] : 0.f;
   }
   __syncthreads();
+  const int seg = slab_seg(H, W), segs = (W + seg - 1) / seg, nseg = H * segs;
   // pass 1: S1 = sum dz, S2 = sum dz * xhat  (xhat from the recomputed depthwise output)
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int p = threadIdx.x; p < HW; p += kSlabThreads) {
-    float y[8], d[8];
-    dw_at(sx, p / W, p % W, H, W, we, bs, y);
-    unpack8f(dzg[(long long)p * G], d);
+  for (int sgi = threadIdx.x; sgi < nseg; sgi += kSlabThreads) {
+    const int r = sgi / segs, c0 = (sgi % segs) * seg;
+    dw_row_run(sx, r, c0, min(W, c0 + seg), H, W, we, bs,
+               [&](int c, const float (&y)[8], const float (&)[3][3][8], int, int, int) {
+                 float d[8];
+                 unpack8f(dzg[(long long)(r * W + c) * G], d);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[k] += d[k];
-      acc[8 + k] += d[k] * (y[k] - mean[k]) * rstd[k];
-    }
+                 for (int k = 0; k < 8; ++k) {
+                   acc[k] += d[k];
+                   acc[8 + k] += d[k] * (y[k] - mean[k]) * rstd[k];
+                 }
+               });
   }
   block_sum16<kSlabThreads / 32>(acc, red);
   const float inv = 1.f / (float)HW;
   // pass 2: dy1 = rstd (dz - S1/M - xhat S2/M) into shared memory; weight / bias gradient accumulators
-  float gw[3][3][8], gb[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    gb[k] = 0.f;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b) gw[a][b][k] = 0.f;
-  }
-  for (int p = threadIdx.x; p < HW; p += kSlabThreads) {
-    const int r = p / W, c = p % W;
-    float y[8], d[8];
-    dw_at(sx, r, c, H, W, we, bs, y);
-    unpack8f(dzg[(long long)p * G], d);
+  {
+    float gw[3][3][8], gb[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xh = (y[k] - mean[k]) * rstd[k];
-      d[k] = rstd[k] * (d[k] - acc[k] * inv - xh * acc[8 + k] * inv);
+      gb[k] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) gw[a][b][k] = 0.f;
     }
-    const uint4 packed = pack8f(d);
-    sd[p] = packed;
-    unpack8f(packed, d);  // the bf16 values the data-gradient pass reads
+    for (int sgi = threadIdx.x; sgi < nseg; sgi += kSlabThreads) {
+      const int r = sgi / segs, c0 = (sgi % segs) * seg;
+      dw_row_run(sx, r, c0, min(W, c0 + seg), H, W, we, bs,
+                 [&](int c, const float (&y)[8], const float (&win)[3][3][8], int L, int M, int R) {
+                   float d[8];
+                   unpack8f(dzg[(long long)(r * W + c) * G], d);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) gb[k] += d[k];
+                   for (int k = 0; k < 8; ++k) {
+                     const float xh = (y[k] - mean[k]) * rstd[k];
+                     d[k] = rstd[k] * (d[k] - acc[k] * inv - xh * acc[8 + k] * inv);
+                   }
+                   const uint4 packed = pack8f(d);
+                   sd[sidx(r * W + c)] = packed;
+                   unpack8f(packed, d);  // the bf16 values the data-gradient pass reads
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int rr = refl(r + a - 1, H);
+                   for (int k = 0; k < 8; ++k) gb[k] += d[k];
 #pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        float xv[8];
-        unpack8f(sx[rr * W + refl(c + b - 1, W)], xv);
+                   for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) gw[a][b][k] += d[k] * xv[k];
+                     for (int k = 0; k < 8; ++k) {
+                       gw[a][0][k] += d[k] * win[a][L][k];
+                       gw[a][1][k] += d[k] * win[a][M][k];
+                       gw[a][2][k] += d[k] * win[a][R][k];
+                     }
+                 });
+    }
+    // block reduction of the 72 + 8 parameter gradients: warp shuffles, per-warp partials, one atomic per value
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      gb[k] = warp_sum(gb[k]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) gw[a][b][k] = warp_sum(gw[a][b][k]);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) fr[warp * 80 + k * 10 + a * 3 + b] = gw[a][b][k];
+        fr[warp * 80 + k * 10 + 9] = gb[k];
       }
     }
   }
-  __syncthreads();
+  __syncthreads();   // dy1 slab and the per-warp partials are complete
+  if (threadIdx.x < 80) {
+    float a = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < kSlabThreads / 32; ++wp) a += fr[wp * 80 + threadIdx.x];
+    const int k = threadIdx.x / 10, j = threadIdx.x % 10;
+    const int c = g * 8 + k;
+    if (c < C) {
+      if (j < 9) {
+        if (dw != nullptr) atomicAdd(dw + c * 9 + j, a);
+      } else if (dbias != nullptr) {
+        atomicAdd(dbias + c, a);
+      }
+    }
+  }
   // pass 3: data gradient = zero-padded correlation of dy1 with the flipped taps + the mirrored border taps of the
   // fused ReflectionPad2d(1) (dx[1] += w[kh=0] dy1[0], dx[H-2] += w[kh=2] dy1[H-1]; same for columns)
   if (dx != nullptr) {
@@ -231,7 +310,7 @@ dw_in_slab_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, c
           const int cc = c + b - 1;
           if (cc < 0 || cc >= W) continue;
           float dv[8];
-          unpack8f(sd[rr * W + cc], dv);
+          unpack8f(sd[sidx(rr * W + cc)], dv);
           const bool lft = (b == 0 && c == 1), rgt = (b == 2 && c == W - 2);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -254,44 +333,6 @@ dw_in_slab_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, c
         }
       }
       dxg[(long long)p * G] = pack8f(o);
-    }
-  }
-  // block reduction of the 72 + 8 parameter-gradient accumulators (reusing the slab), one atomic per value
-  __syncthreads();
-  float* fr = reinterpret_cast<float*>(slab);  // [256][80] floats = 80 KB <= 2 * HW * 16 B only when HW >= 2560 ...
-  // ... so reduce through warp shuffles first: 8 warps x 80 values
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    gb[k] = warp_sum(gb[k]);
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b) gw[a][b][k] = warp_sum(gw[a][b][k]);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) fr[warp * 80 + k * 10 + a * 3 + b] = gw[a][b][k];
-      fr[warp * 80 + k * 10 + 9] = gb[k];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 80) {
-    float a = 0.f;
-#pragma unroll
-    for (int wp = 0; wp < kSlabThreads / 32; ++wp) a += fr[wp * 80 + threadIdx.x];
-    const int k = threadIdx.x / 10, j = threadIdx.x % 10;
-    const int c = g * 8 + k;
-    if (c < C) {
-      if (j < 9) {
-        if (dw != nullptr) atomicAdd(dw + c * 9 + j, a);
-      } else if (dbias != nullptr) {
-        atomicAdd(dbias + c, a);
-      }
     }
   }
 }
@@ -462,7 +503,7 @@ extern "C" int gcc_dw_in_slab_fwd_bf16(const void* x, const float* w, const floa
     if (int rc = slab_smem_attr((const void*)dw_in_slab_fwd_kernel)) return rc;
     configured[dev] = true;
   }
-  gcc_launch(dw_in_slab_fwd_kernel, dim3(Cp / 8, N), kSlabThreads, (size_t)H * W * 16, (cudaStream_t)stream, (const bf16*)x, w,
+  gcc_launch(dw_in_slab_fwd_kernel, dim3(Cp / 8, N), kSlabThreads, (size_t)slab_elems(H * W) * 16, (cudaStream_t)stream, (const bf16*)x, w,
              bias, (bf16*)z, stats, H, W, Cp / 8, C, eps);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
@@ -478,8 +519,7 @@ extern "C" int gcc_dw_in_slab_bwd_bf16(const void* x, const void* dz, const floa
     if (int rc = slab_smem_attr((const void*)dw_in_slab_bwd_kernel)) return rc;
     configured[dev] = true;
   }
-  size_t smem = (size_t)H * W * 32;
-  if (smem < 8 * 80 * sizeof(float)) smem = 8 * 80 * sizeof(float);
+  const size_t smem = (size_t)slab_elems(H * W) * 32;
   gcc_launch(dw_in_slab_bwd_kernel, dim3(Cp / 8, N), kSlabThreads, smem, (cudaStream_t)stream, (const bf16*)x, (const bf16*)dz,
              w, bias, stats, (bf16*)dx, dw, dbias, H, W, Cp / 8, C);
   GCC_CHECK_LAUNCH();

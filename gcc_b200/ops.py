@@ -178,17 +178,17 @@ class ConvFn(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
-def _tap_major_weight(layer, pack, c):
+def _tap_major_weight(layer, pack, c, key):
     """Rows of ``pack`` ([c][16 taps][K] bf16) re-ordered tap-major with the channels padded to a group of 4
-    or 8 (zero rows): the GEMM then writes columns col2im can read with one 8/16-byte load per tap.  The
-    buffer lives on the layer (allocated once, refreshed from the current pack on every call)."""
+    or 8 (zero rows): the GEMM then writes columns col2im can read with one 8/16-byte load per tap.  Built by one
+    kernel when the arena's packs were refreshed (cached per layer on the pack version)."""
     cg = 4 if c <= 4 else 8
-    buf = getattr(layer, "_tapw", None)
-    if buf is None or buf.shape[2] != pack.shape[2] or buf.device != pack.device:
-        buf = torch.zeros(16, cg, pack.shape[2], dtype=torch.bfloat16, device=pack.device)
-        layer._tapw = buf
-    buf[:, :c].copy_(pack[:c].permute(1, 0, 2))
-    return buf, cg, (2 if cg == 4 else 0)
+
+    def build(old):
+        buf = old if old is not None else torch.empty(16, cg, pack.shape[2], dtype=torch.bfloat16, device=pack.device)
+        call("gcc_fold_weight_pack_bf16", pack.data_ptr(), buf.data_ptr(), 0, c, 16, cg, 0, pack.shape[2], 0, 16 * cg, _st())
+        return buf
+    return _derived(layer, key, build), cg, (2 if cg == 4 else 0)
 
 
 class ColConvFn(torch.autograd.Function):
@@ -219,7 +219,7 @@ class ColConvFn(torch.autograd.Function):
             saved = x
         else:
             oh, ow = 2 * h, 2 * w
-            wp, cg, order = _tap_major_weight(layer, pk.transposed, layer.cout)  # [16*cg][cin_p]
+            wp, cg, order = _tap_major_weight(layer, pk.transposed, layer.cout, "tapmajor_fwd")  # [16*cg][cin_p]
             ycol = torch.empty(n, h, w, 16 * cg, dtype=torch.bfloat16, device=x.device)
             call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), 16 * cg, 1, wp.shape[2], None,
                  ycol.data_ptr(), h, w, 16 * cg, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
@@ -255,7 +255,7 @@ class ColConvFn(torch.autograd.Function):
             _, oh, ow, cop = dpre.shape
             if ctx.needs_input_grad[0]:
                 layer.arena.ensure_packed()
-                wp, cg, order = _tap_major_weight(layer, pk.transposed, layer.cin)  # [16*cg][cout_p]
+                wp, cg, order = _tap_major_weight(layer, pk.transposed, layer.cin, "tapmajor_dgrad")  # [16*cg][cout_p]
                 dcol = torch.empty(n, oh, ow, 16 * cg, dtype=torch.bfloat16, device=dev)
                 call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), 16 * cg, 1,
                      wp.shape[2], None, dcol.data_ptr(), oh, ow, 16 * cg, 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0,

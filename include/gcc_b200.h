@@ -9,6 +9,10 @@
  * physical channel count that is a multiple of 8 (extra channels are zero); `stream` is a
  * cudaStream_t passed as void*; every function returns 0 on success, non-zero on failure
  * (gcc_last_error() describes it).  No function allocates or keeps caller memory.
+ *
+ * Data parallel: there are no gcc_nccl_* entry points.  The gradient exchange (and, with --sync_bn, the statistics /
+ * loss-mean exchange) goes through torch.distributed's NCCL process group on the flat gradient arenas that these
+ * kernels accumulate into (gcc_b200/pix2pix.py::_allreduce_grads); the library itself never talks to NCCL.
  */
 #ifndef GCC_B200_H
 #define GCC_B200_H
