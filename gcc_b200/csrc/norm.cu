@@ -255,7 +255,7 @@ __global__ void norm_apply_eval_kernel(NormArgs a, const float* __restrict__ rme
 
 // ------------------------------------------------------------------------------------- backward
 // red[(n)][0:Cp) += sum dg ; red[(n)][Cp:2Cp) += sum dg * xhat      dg = dy*act'(g) + dy2*act2'(g)
-template <int U, bool HAS_D2>
+template <int U, bool HAS_D2, bool PIPE = true>
 __global__ void __launch_bounds__(256, 2)
 norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int dy_Cp, int dy_coff,
                        const bf16* __restrict__ dy2, int dy2_Cp, int dy2_coff, int act2, float* __restrict__ red) {
@@ -270,17 +270,17 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
   if (lane < lanes) {
-    // xhat = x*rs + ms ;  z = xhat*gam + bet ;  gg = gate_after ? z : z*mask
-    float rs[8], ms[8], cg[8], cb[8];
+    // xhat = x*rs + ms ;  z = xhat*gam + bet ;  gg = gate_after ? z : z*mask  ==  x*cg + cb.
+    // The loop accumulates S1 = sum dg and sum dg*x on the RAW x (two coefficient arrays live instead of four);
+    // sum dg*xhat = rs * sum dg*x + ms * S1 is formed once after the loop.
+    float cg[8], cb[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float mean, rstd, gam, bet, mask;
       channel_affine(a, n, g * 8 + k, mean, rstd, gam, bet, mask);
       const float mk = a.gate_after ? 1.f : mask;
-      rs[k] = rstd;
-      ms[k] = -mean * rstd;
-      cg[k] = gam * mk;
-      cb[k] = bet * mk;
+      cg[k] = rstd * gam * mk;
+      cb[k] = (bet - mean * rstd * gam) * mk;
     }
     const bf16* xb = a.x + pix0 * a.Cp + g * 8;
     const bf16* d1b = dy ? dy + pix0 * dy_Cp + dy_coff + g * 8 : nullptr;
@@ -289,8 +289,7 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
       const Vec8 xv = unpack8(ux), d1 = unpack8(u1), d2 = unpack8(u2);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float xh = xv.v[k] * rs[k] + ms[k];
-        const float gg = xh * cg[k] + cb[k];
+        const float gg = xv.v[k] * cg[k] + cb[k];
         float dg = 0.f;
         if (d1b) dg += d1.v[k] * act_grad(gg, a.act, a.slope);
         if (HAS_D2 && d2b) dg += d2.v[k] * act_grad(gg, act2, a.slope);
@@ -299,7 +298,7 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
           if (d1b) s2[k] += d1.v[k] * act_fwd(gg, a.act, a.slope);
           if (HAS_D2 && d2b) s2[k] += d2.v[k] * act_fwd(gg, act2, a.slope);
         } else {
-          s2[k] += dg * xh;
+          s2[k] += dg * xv.v[k];
         }
       }
     };
@@ -311,6 +310,14 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
     // register double buffer over groups of U pixels (out-of-range pixels load zeros and contribute nothing)
     long long p = (long long)blockIdx.x * lanes + lane;
     uint4 cx[U], c1[U], c2[U], nx[U], n1[U], n2[U];
+    if (!PIPE) {  // U loads in flight, no register double buffer (the other resident warps cover the compute phase)
+      for (; p < a.npix; p += U * step) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) { cx[j] = ldx(p + j * step); c1[j] = ld1(p + j * step); c2[j] = ld2(p + j * step); }
+#pragma unroll
+        for (int j = 0; j < U; ++j) accum(cx[j], c1[j], c2[j]);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < U; ++j) { cx[j] = ldx(p + j * step); c1[j] = ld1(p + j * step); c2[j] = ld2(p + j * step); }
     while (p < a.npix) {
@@ -326,6 +333,11 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
     float* r = sred + ((long long)lane * a.G + g) * 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      if (!a.gate_after) {
+        float mean, rstd, gam, bet, mask;
+        channel_affine(a, n, g * 8 + i, mean, rstd, gam, bet, mask);
+        s2[i] = rstd * (s2[i] - mean * s1[i]);
+      }
       r[i] = s1[i];
       r[8 + i] = s2[i];
     }
@@ -585,7 +597,14 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
     const long long cap = (148LL * 2 + groups - 1) / groups;  // one resident wave (launch bounds: 2 CTAs / SM)
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    if (dy2 == nullptr)   // (4 pixels in flight spill in this kernel and measured 25 % slower)
+    static const int flat = getenv("GCC_B200_NORM_REDUCE_FLAT") ? atoi(getenv("GCC_B200_NORM_REDUCE_FLAT")) : 0;
+    if (dy2 == nullptr && flat == 4)
+      gcc_launch(norm_bwd_reduce_kernel<4, false, false>, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st, a,
+                 lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
+    else if (dy2 == nullptr && flat == 8)
+      gcc_launch(norm_bwd_reduce_kernel<8, false, false>, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st, a,
+                 lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
+    else if (dy2 == nullptr)   // (4 pixels in flight spill in this kernel and measured 25 % slower)
       gcc_launch(norm_bwd_reduce_kernel<2, false>, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st, a,
                  lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
     else

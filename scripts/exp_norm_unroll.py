@@ -1,5 +1,5 @@
-"""norm backward kernels (reduce / apply separately) on the PatchGAN activations at batch 32; run once with
-GCC_B200_NORM_UNROLL=2 and once with =4."""
+"""norm kernels (forward apply / backward reduce / backward apply separately, L2 flushed before every launch) on the
+PatchGAN activations at batch 32.  GCC_B200_NORM_REDUCE_FLAT=4|8 selects the un-pipelined reduce variants."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -33,5 +33,5 @@ for (N, H, W, C) in ((32, 128, 128, 128), (32, 64, 64, 256), (32, 32, 32, 512), 
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
-        print("unroll %s waves %s  [%d,%d,%d,%d]  %-26s %7.1f us  %6.0f GB/s" % (os.environ.get("GCC_B200_NORM_UNROLL", "2"), os.environ.get("GCC_B200_NORM_WAVES", "16"), N, H, W, C, label,
+        print("reduce_flat %s  [%d,%d,%d,%d]  %-26s %7.1f us  %6.0f GB/s" % (os.environ.get("GCC_B200_NORM_REDUCE_FLAT", "0"), N, H, W, C, label,
                                                                       ms * 1e3, mult * nbytes / ms / 1e6), flush=True)
