@@ -21,6 +21,7 @@
 // smem rings of STAGES slots guarded by full/empty mbarriers; accumulator hand-off through tmem_full (/ tmem_empty)
 // mbarriers; every mbarrier wait is bounded and traps instead of hanging.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace gcc {
 
@@ -296,17 +297,35 @@ struct ConvGeom2 {
   // eight 2 KB boxes (128 pixels x 16 B, un-swizzled) land as canonical core matrices, K index = tap * 8 + c,
   // which is exactly the order of the packed weights [R][T][8] read as [R][T * 8].
   int c8;
+  // Tail-wave split: a layer whose tile count leaves the last wave of the persistent grid less than half full (512
+  // tiles on 148 SMs = 3.46 waves: the PatchGAN 1024 -> 512 data gradient) cuts the K loop of those last tiles into
+  // `tail_splits` parts, so the last wave takes 1 / tail_splits of a tile time.  Work items >= tail_begin are
+  // (tile, split) pairs; their fp32 partial tiles go to tail_ws [item][128][BLOCK_N] with plain stores (no atomics, no
+  // memset) and conv_tail_finalize_kernel sums the parts in a fixed order, adds bias / activation / statistics and
+  // writes the bf16 output.  tail_begin == total_tiles: no tail.
+  int tail_begin, tail_splits;
+  float* tail_ws;
 };
 
 struct TileInfo {
   int cls, n_tile, a0, b0, n0, tap0, kb0, kb1;
+  int item;  // >= 0: tail work item (index into tail_ws), -1: an ordinary tile
 };
 
 __device__ __forceinline__ TileInfo decode_tile(const ConvGeom2& p, int tile_id) {
   TileInfo t;
-  int r = tile_id;
-  const int split = r % p.k_splits;
-  r /= p.k_splits;
+  int r = tile_id, split, nsplit;
+  if (tile_id >= p.tail_begin) {  // tail work item (k_splits == 1 whenever a tail exists)
+    t.item = tile_id - p.tail_begin;
+    nsplit = p.tail_splits;
+    split = t.item % nsplit;
+    r = p.tail_begin + t.item / nsplit;
+  } else {
+    t.item = -1;
+    nsplit = p.k_splits;
+    split = r % nsplit;
+    r /= nsplit;
+  }
   const int m_total = p.cls_mtile_begin[p.num_classes];
   int ml = r % m_total;
   t.n_tile = r / m_total;
@@ -324,7 +343,7 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvGeom2& p, int tile_id)
   t.tap0 = p.cls_tap_begin[cls];
   const int ntap = p.cls_tap_begin[cls + 1] - t.tap0;
   const int num_kb = p.c8 ? ntap / 8 : ntap * p.k_chunks;
-  const int per = (num_kb + p.k_splits - 1) / p.k_splits;
+  const int per = (num_kb + nsplit - 1) / nsplit;
   t.kb0 = split * per;
   t.kb1 = min(num_kb, t.kb0 + per);
   return t;
@@ -396,24 +415,28 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
         const TileInfo t = decode_tile(p, tile);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          // timing experiments (scripts/exp_conv_bound.py): debug bit 8 skips the A boxes, bit 9 the B boxes
+          const bool ld_a = !(p.debug & 256), ld_b = !(p.debug & 512);
+          mbar_expect_tx(&full_bar[stage], (ld_a ? kABytes : 0u) + (ld_b ? kBBytes : 0u));
           uint8_t* sa = smem + stage * kStageBytes;
           if (p.c8) {
 #pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 8 && ld_a; ++j) {
               const int tap = t.tap0 + kb * 8 + j;
               tma_load_4d(sa + j * (kBlockM * 16), &p.a_maps[p.tap_map[tap]], &full_bar[stage], 0, t.b0 + p.tap_dw[tap],
                           t.a0 + p.tap_dh[tap], t.n0);
             }
-            tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kb * kBlockK, 0, t.n_tile * BLOCK_N);
+            if (ld_b) tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kb * kBlockK, 0, t.n_tile * BLOCK_N);
           } else {
             const int tl = kb / p.k_chunks;
             const int kc = kb - tl * p.k_chunks;
             const int tap = t.tap0 + tl;
-            tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, t.b0 + p.tap_dw[tap],
-                        t.a0 + p.tap_dh[tap], t.n0);
-            tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK,
-                        p.w_per_image ? t.n0 : (int)p.tap_widx[tap], t.n_tile * BLOCK_N);
+            if (ld_a)
+              tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, t.b0 + p.tap_dw[tap],
+                          t.a0 + p.tap_dh[tap], t.n0);
+            if (ld_b)
+              tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK,
+                          p.w_per_image ? t.n0 : (int)p.tap_widx[tap], t.n_tile * BLOCK_N);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -443,7 +466,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
             const uint64_t da = p.c8 ? make_smem_desc_plain(sa + k * (2 * kBlockM * 16), kBlockM * 16, 128)
                                      : make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_d, da, db, kIdesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            if (!(p.debug & 1024)) umma_bf16(tmem_d, da, db, kIdesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -489,6 +512,29 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      if (t.item >= 0) {
+        // tail work item: this thread's row of the fp32 partial tile goes to the workspace as it is (128 contiguous
+        // bytes per chunk); conv_tail_finalize_kernel sums the parts and applies bias / activation / statistics
+        float* wrow = p.tail_ws + ((long long)t.item * kBlockM + r) * BLOCK_N;
+#pragma unroll 1
+        for (int c0 = half * kHalf; c0 < (half + 1) * kHalf; c0 += 32) {
+          if (t.n_tile * BLOCK_N + c0 >= p.out_cols) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_d + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(wrow + c0 + i) =
+                make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                            __uint_as_float(v[i + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       if (kTmaStore && p.k_splits == 1 && !p.f32_out) {
         uint8_t* obuf = out_base + (uint32_t)(tile_iter & 1) * (kUnits * 16384);
         // the store issued two tiles ago read this buffer: wait for it, then tell everybody
@@ -653,6 +699,47 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Completes the tail tiles of conv_gemm_persistent_kernel (ConvGeom2::tail_*): one CTA per tail tile, thread = output
+// column (coalesced in the workspace and in the NHWC output).  out = bf16(act(sum_parts ws + bias)); the per-channel
+// statistics use the stored bf16 values of the valid rows, exactly like the fused epilogue.
+template <int BLOCK_N>
+__global__ void __launch_bounds__(BLOCK_N) conv_tail_finalize_kernel(const __grid_constant__ ConvGeom2 p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int item0 = blockIdx.x * p.tail_splits;
+  const TileInfo t = decode_tile(p, p.tail_begin + item0);
+  const int col = t.n_tile * BLOCK_N + threadIdx.x;
+  if (col >= p.out_cols) return;
+  // parts with an empty K range were never written
+  int nparts = 0;
+  for (int s = 0; s < p.tail_splits; ++s) {
+    const TileInfo ts = decode_tile(p, p.tail_begin + item0 + s);
+    if (ts.kb1 > ts.kb0) nparts = s + 1;
+  }
+  const float bias = (p.bias != nullptr && col < p.bias_cols) ? __ldg(p.bias + col) : 0.f;
+  const float* ws = p.tail_ws + (long long)item0 * kBlockM * BLOCK_N + threadIdx.x;
+  const int wt_mask = (1 << p.log_wt) - 1, ht_mask = (1 << p.log_ht) - 1;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < kBlockM; ++r) {
+    const int b = t.b0 + (r & wt_mask);
+    const int a = t.a0 + ((r >> p.log_wt) & ht_mask);
+    const int n = t.n0 + (r >> (p.log_wt + p.log_ht));
+    if (!((n < p.GN) && (a < p.cls_GH[t.cls]) && (b < p.cls_GW[t.cls]))) continue;  // block-uniform
+    float v = 0.f;
+    for (int s = 0; s < nparts; ++s) v += ws[((long long)s * kBlockM + r) * BLOCK_N];
+    const bf16 o = __float2bfloat16(apply_act(v + bias, p.act, p.slope));
+    p.out[p.cls_out_off[t.cls] + (long long)n * p.out_sn + (long long)a * p.out_sh + (long long)b * p.out_sw + col] = o;
+    const float xv = __bfloat162float(o);
+    s1 += xv;
+    s2 += xv * xv;
+  }
+  if (p.stats != nullptr) {
+    atomicAdd(p.stats + col, s1);
+    atomicAdd(p.stats + p.stats_ld + col, s2);
+  }
 }
 
 // out[pix, y_coff + c] = bf16(act(partial[pix, c] + bias[c]))
@@ -867,8 +954,8 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     gcc_set_error(__FILE__, __LINE__, "conv gemm: fp32 output needs a workspace and excludes bias / activation / statistics");
     return GCC_ERR_ARG;
   }
-  if (stats != nullptr && (splitk_ws != nullptr || stats_ld < ((R + 7) / 8 * 8))) {
-    gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: fused statistics exclude split-K and need stats_ld >= round8(R)");
+  if (stats != nullptr && stats_ld < ((R + 7) / 8 * 8)) {
+    gcc_set_error(__FILE__, __LINE__, "gcc_conv_gemm_bf16: fused statistics need stats_ld >= round8(R)");
     return GCC_ERR_ARG;
   }
   if (w_per_image && (KH != 1 || KW != 1 || stride != 1 || pad != 0 || transposed)) {
@@ -914,7 +1001,7 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     g.log_nt = 0;
   }
   const int tiles_n = (N + (1 << g.log_nt) - 1) >> g.log_nt;
-  int ntap = 0, ncls = 0, max_kb = 0;
+  int ntap = 0, ncls = 0, max_kb = 0, min_kb = 1 << 30;
   for (int cls = 0; cls < classes; ++cls) {
     int GH, GW, qh = 0, qw = 0;
     const int tap_begin = ntap;
@@ -971,6 +1058,7 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     g.cls_part_off[ncls] = ((long long)qh * OW + qw) * Rp;
     const int kb = c8 ? (ntap - tap_begin) / 8 : (ntap - tap_begin) * g.k_chunks;
     if (kb > max_kb) max_kb = kb;
+    if (kb < min_kb) min_kb = kb;
     ++ncls;
   }
   g.cls_tap_begin[ncls] = ntap;
@@ -1036,7 +1124,9 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     g.part_sw = (long long)Rp * os;
     if (cudaMemsetAsync(splitk_ws, 0, sizeof(float) * out_elems, st) != cudaSuccess) return GCC_ERR_CUDA;
   }
-  if (splitk_ws != nullptr && ws_elems >= out_elems && base_tiles * 2 <= num_sms() && max_kb >= 8) {
+  // (the fused statistics are summed from the stored bf16 tile: not available on the workspace path)
+  if (splitk_ws != nullptr && (stats == nullptr || f32_out) && ws_elems >= out_elems && base_tiles * 2 <= num_sms() &&
+      max_kb >= 8) {
     int ks = num_sms() / base_tiles;
     if (ks > max_kb / 2) ks = max_kb / 2;
     if (ks > 64) ks = 64;
@@ -1052,6 +1142,26 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     }
   }
   g.total_tiles = base_tiles * g.k_splits;
+  g.tail_begin = g.total_tiles;
+  g.tail_splits = 1;
+  // Tail-wave split (ConvGeom2::tail_begin): few waves, a last wave that is at most half full and a K loop long enough
+  // that every part still runs >= 16 k-blocks.  GCC_B200_TAIL_SPLIT=0 / debug bit 11 switch it off (A/B measurements).
+  static const int tail_on = getenv("GCC_B200_TAIL_SPLIT") ? atoi(getenv("GCC_B200_TAIL_SPLIT")) : 1;
+  if (tail_on && !(g_debug_flags & 2048) && splitk_ws != nullptr && g.k_splits == 1 && !f32_out && !c8 && BN >= 128) {
+    const int S = num_sms();
+    const int waves = base_tiles / S, rem = base_tiles % S;
+    if (waves >= 1 && waves <= 8 && rem > 0 && rem * 2 <= S && min_kb >= 32) {
+      int ks = S / rem;
+      if (ks > min_kb / 16) ks = min_kb / 16;
+      if (ks > 4) ks = 4;
+      if (ks >= 2 && ws_elems >= (long long)rem * ks * kBlockM * BN) {
+        g.tail_begin = base_tiles - rem;
+        g.tail_splits = ks;
+        g.tail_ws = splitk_ws;
+        g.total_tiles = g.tail_begin + rem * ks;
+      }
+    }
+  }
   g.debug = g_debug_flags;
   g.stats = stats;
   g.stats_ld = stats_ld;
@@ -1062,6 +1172,12 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
   else if (BN == 128) rc = launch_conv_persistent<128, 6, false>(g, st);
   else rc = launch_conv_persistent<256, 4, false>(g, st);
   if (rc) return rc;
+  if (g.tail_splits > 1) {
+    const unsigned tail_tiles = (unsigned)((g.total_tiles - g.tail_begin) / g.tail_splits);
+    if (BN == 256) gcc_launch(conv_tail_finalize_kernel<256>, tail_tiles, 256, 0, st, g);
+    else gcc_launch(conv_tail_finalize_kernel<128>, tail_tiles, 128, 0, st, g);
+    GCC_CHECK_LAUNCH();
+  }
   if (g.k_splits > 1 && !f32_out) {
     long long b = (out_elems + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;

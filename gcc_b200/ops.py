@@ -65,10 +65,28 @@ def _window(t):
     return t, t.shape[3]
 
 
-def _splitk_ws(n, oh, ow, rows, device):
-    """fp32 split-K scratch for layers with very few output pixels (U-Net inner levels); (ptr, elems)."""
+_TAIL_WS = {}
+_TAIL_WS_ELEMS = 148 * 128 * 256
+
+
+def _tail_ws(device):
+    """Per-device fp32 scratch of the conv kernel's tail-wave split (include/gcc_b200.h, gcc_conv_gemm_bf16 (b)): 19 MB,
+    allocated once (before any graph capture: the eager warm-up iterations touch it), contents undefined between calls.
+    Every convolution of the step runs on ONE stream, so consecutive launches may share it."""
+    ws = _TAIL_WS.get(device)
+    if ws is None:
+        ws = _TAIL_WS[device] = torch.empty(_TAIL_WS_ELEMS, dtype=torch.float32, device=device)
+    return ws
+
+
+def _splitk_ws(n, oh, ow, rows, device, stats=False):
+    """fp32 scratch of a conv launch, (ptr, elems, keep-alive): layers with very few output pixels (U-Net inner levels)
+    get a split-K buffer of their own (not with fused statistics), the large ones the shared tail-wave scratch."""
     pix = n * oh * ow
     if pix > 16384:
+        ws = _tail_ws(device)
+        return ws.data_ptr(), ws.numel(), ws
+    if stats:
         return None, 0, None
     elems = pix * rp8(rows)
     ws = torch.empty(elems, dtype=torch.float32, device=device)
@@ -126,7 +144,7 @@ class ConvFn(torch.autograd.Function):
         pk = layer.packs
         wp = pk.direct if not tr else pk.transposed  # [cout][T][cin_p]
         epi = {ACT_NONE: 0, ACT_LRELU: 1, ACT_TANH: 2}[act]
-        wsp, wse, _keep = (None, 0, None) if stats is not None else _splitk_ws(n, oh, ow, layer.cout, x.device)
+        wsp, wse, _keep = _splitk_ws(n, oh, ow, layer.cout, x.device, stats is not None)
         call("gcc_conv_gemm_bf16", x.data_ptr(), n, h, w, cx, wp.data_ptr(), layer.cout, layer.k * layer.k,
              wp.shape[2], None if bias is None else bias.data_ptr(), y.data_ptr(), oh, ow, cop, 0, tr, layer.k,
              layer.k, layer.stride, layer.pad, epi, slope, 0, wsp, wse,

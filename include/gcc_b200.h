@@ -38,10 +38,14 @@ long long gcc_launch_count(void); /* kernels launched by this library so far (ho
  *   x: [N,H,W,Cx] bf16, w: [R][T=KH*KW][Cw] bf16, y: [N,OH,OW,Cy] bf16, bias: [R] fp32 or NULL.
  *   act: 0 none, 1 leaky-relu(slope), 2 tanh.  stride in {1,2}.
  *   w_per_image=1 (1x1 only): w is [N][R][Cw], one matrix per image (Gram-loss backward dF = F M).
- *   splitk_ws: optional fp32 scratch of >= N*OH*OW*round8(R) elements enabling split-K for layers with very
- *   few output pixels (U-Net inner levels); NULL disables it.
+ *   splitk_ws / ws_elems: optional fp32 scratch (contents undefined on entry and on return), NULL disables both uses:
+ *   (a) >= N*OH*OW*round8(R) elements: split-K for layers with very few output pixels (U-Net inner levels; not with
+ *   `stats`); (b) >= 148*128*256 elements: tail-wave split for layers whose tile count leaves the last wave of the
+ *   148-SM persistent grid at most half full (512 tiles = 3.46 waves: the PatchGAN 1024 -> 512 data gradient) -- the
+ *   K loop of those last tiles is cut in parts that run side by side, a small second kernel sums the parts and
+ *   applies bias / activation / statistics.  Results of (b) are deterministic (plain stores, fixed summation order).
  *   stats: optional zeroed fp32 [2][stats_ld]; the epilogue adds per-output-channel sum / sum of squares of the
- *   stored bf16 values (the statistics nn.BatchNorm2d needs next, Pix2Pix.py:34,288) -- excludes split-K.
+ *   stored bf16 values (the statistics nn.BatchNorm2d needs next, Pix2Pix.py:34,288).
  */
 int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                        const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
@@ -55,7 +59,13 @@ int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void
                         float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched, int accumulate,
                         float scale, void* stream);
 void gcc_debug_force_block_n(int bn);
-void gcc_debug_set_flags(int f); /* timing experiments: bit0 skip conv epilogue stores, bit1 skip TMEM loads */
+/* timing experiments / A-B switches: bit0 skip conv epilogue stores, bit1 skip TMEM loads, bit2/3 wgrad: skip TMA /
+ * MMA, bit4 wgrad 128-row tiles, bit5 per-launch GEMM trace, bit7 no image mode, bit8/9 conv: skip the A / B boxes,
+ * bit10 conv: skip the MMAs, bit11 no tail-wave split.  Bits 0-4 and 8-10 produce garbage results. */
+void gcc_debug_set_flags(int f);
+/* sweep direction of the norm kernels (bit0 forward apply, bit1 backward reduce, bit2 backward apply run from the last
+ * pixel to the first: L2 reuse behind / in front of an ascending conv); -1 restores GCC_B200_NORM_SWEEP / the default */
+void gcc_debug_set_norm_sweep(int mask);
 
 /* ---- norm / gate / activation blocks (norm.cu) ----
  * One block = [BatchNorm2d | InstanceNorm2d | identity] -> [DifferentiableOP gate] -> [(Leaky)ReLU]

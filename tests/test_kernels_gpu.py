@@ -123,6 +123,64 @@ def test_conv_layer_fwd_bwd(G, case):
         assert bool((y.detach()[..., Cout:] == 0).all())
 
 
+# 512 tiles on the 148-SM persistent grid (3.46 waves): the last 68 tiles run as 2 x 68 half-K work items + the finalize
+# kernel (conv_gemm.cu, "tail-wave split").  fprop k4 s1; the data gradient of a k4 s1 conv; a stride-2 transposed conv
+# (four sub-pixel classes).
+TAIL_CASES = [
+    (32, 32, 32, 128, 512, 4, 1, 1, 0),
+    (32, 31, 31, 512, 128, 4, 1, 1, 0),
+    (32, 16, 16, 512, 512, 4, 2, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", TAIL_CASES)
+def test_conv_tail_wave_split(G, case):
+    """The tail-wave split against torch, against the un-split kernel (debug bit 11 switches it off) and with the fused
+    BatchNorm statistics."""
+    N, H, W, Cin, Cout, k, s, p, tr = case
+    A = G.arena.ParamArena("cuda")
+    layer = G.nets.ConvLayer(A, "c", "convT" if tr else "conv", Cin, Cout, k, s, p, bias=True)
+    A.finalize()
+    layer.bind()
+    wshape = (Cin, Cout, k, k) if tr else (Cout, Cin, k, k)
+    w0, b0 = rnd(wshape, 1, 0.05), rnd((Cout,), 2)
+    with torch.no_grad():
+        layer.weight.copy_(w0)
+        layer.bias.copy_(b0)
+    A.mark_dirty()
+    x = rnd((N, Cin, H, W), 3)
+    res = {}
+    for flags in (0, 2048):
+        G.lib.lib().gcc_debug_set_flags(flags)
+        try:
+            l0 = G.lib.lib().gcc_launch_count()
+            xh = nhwc(x, G).requires_grad_(True)
+            y, sums = layer.with_stats(xh)
+            OH, OW = y.shape[1], y.shape[2]
+            gy = rnd((N, Cout, OH, OW), 4)
+            A.zero_grad()
+            y.backward(nhwc(gy, G))
+            torch.cuda.synchronize()
+            res[flags] = (y.detach().clone(), xh.grad.clone(), sums.clone(), G.lib.lib().gcc_launch_count() - l0)
+        finally:
+            G.lib.lib().gcc_debug_set_flags(0)
+    (y1, dx1, st1, n1), (y0, dx0, st0, n0) = res[0], res[2048]
+    assert n1 == n0 + 1, "exactly one of the convs of this case takes the tail-wave split (one extra finalize launch)"
+    xr = bf(x).requires_grad_(True)
+    wr, br = bf(w0), b0
+    yr = F.conv_transpose2d(xr, wr, br, stride=s, padding=p) if tr else F.conv2d(xr, wr, br, stride=s, padding=p)
+    yr.backward(bf(gy))
+    for y_, dx_, st_ in ((y1, dx1, st1), (y0, dx0, st0)):
+        assert rel_err(nchw(y_, Cout, G), yr.detach()) < BF16_TOL
+        assert rel_err(nchw(dx_, Cin, G), xr.grad) < BF16_TOL
+        yf = nchw(y_, Cout, G).double()
+        cp = st_.numel() // 2
+        assert rel_err(st_[:Cout], yf.sum((0, 2, 3))) < 1e-4
+        assert rel_err(st_[cp:cp + Cout], (yf * yf).sum((0, 2, 3))) < 1e-4
+    # split and un-split results differ only by the fp32 summation order of the two K halves
+    assert rel_err(y1.float(), y0.float()) < 1e-3 and rel_err(dx1.float(), dx0.float()) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------ norm
 @pytest.mark.parametrize("mode,gated,act,dual,C", [("bn", False, 1, False, 64), ("bn", True, 1, False, 40),
                                                    ("bn", False, 1, True, 24), ("in", False, 2, False, 32),
@@ -193,6 +251,46 @@ def test_norm_block_fwd_bwd(G, mode, gated, act, dual, C):
         assert rel_err(layer.alpha.grad, ar.grad) < 5e-3
     if C % 8:
         assert bool((y.detach()[..., C:] == 0).all())
+
+
+@pytest.mark.parametrize("mode,gated,dual,C,N,H,W", [("bn", True, False, 40, 3, 33, 17), ("bn", False, True, 24, 2, 16, 16),
+                                                    ("in", False, False, 32, 3, 9, 7), ("id", True, False, 16, 2, 31, 31)])
+def test_norm_sweep_direction(G, mode, gated, dual, C, N, H, W):
+    """The norm kernels swept from the last pixel to the first (NormArgs::rev, all three kernels) against the ascending
+    sweep: the forward outputs are bit-identical, the backward differs only by the fp32 summation order of the reduce."""
+    res = {}
+    for sweep in (0, 7):
+        A, GA = G.arena.ParamArena("cuda"), G.arena.ParamArena("cuda")
+        layer = G.nets.NormLayer(A, "n", C, mode, "cuda", GA if gated else None, "g" if gated else None, 0.5)
+        A.finalize()
+        GA.finalize()
+        layer.bind()
+        with torch.no_grad():
+            if mode == "bn":
+                layer.gamma.copy_(rnd((C,), 1, 0.3) + 1.0)
+                layer.beta.copy_(rnd((C,), 2, 0.5))
+            if gated:
+                layer.alpha.copy_(torch.tensor(([0.7, 0.5, 0.2, 1.0] * C)[:C], device="cuda"))
+        xh = nhwc(rnd((N, C, H, W), 3, 2.0) + 0.5, G).requires_grad_(True)
+        G.lib.lib().gcc_debug_set_norm_sweep(sweep)
+        try:
+            out = layer(xh, 1, 2 if dual else None)
+            outs = list(out) if dual else [out]
+            A.zero_grad()
+            GA.zero_grad()
+            torch.autograd.backward(outs, [nhwc(rnd((N, C, H, W), 4 + i), G) for i in range(len(outs))])
+            torch.cuda.synchronize()
+        finally:
+            G.lib.lib().gcc_debug_set_norm_sweep(-1)
+        grads = [layer.gamma.grad.clone(), layer.beta.grad.clone()] if mode == "bn" else []
+        if gated:
+            grads.append(layer.alpha.grad.clone())
+        res[sweep] = ([o.detach().clone() for o in outs], xh.grad.clone(), grads)
+    for a, b in zip(res[0][0], res[7][0]):
+        assert torch.equal(a, b)
+    assert rel_err(res[7][1].float(), res[0][1].float()) < 1e-3
+    for a, b in zip(res[0][2], res[7][2]):
+        assert rel_err(b, a) < 1e-4
 
 
 def test_bn_eval_mode(G):
