@@ -74,7 +74,9 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 // grid = (r tiles of 128, c tiles of BLOCK_N, taps * splits [* batch])
 // MT = number of 128-row accumulators per CTA (MT = 2: a 256 x BLOCK_N tile, one third less L2->SM traffic per
 // flop, which is what bounds this kernel: both operands are activations streamed from L2).
-template <int BLOCK_N, int STAGES, int MT>
+// kC8 = image mode (GemmGeom::c8) as a compile-time switch (see conv_gemm_persistent_kernel: the single-thread loops
+// are instruction-bound on the small tiles).
+template <int BLOCK_N, int STAGES, int MT, bool kC8>
 __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__ GemmGeom p) {
   constexpr uint32_t kBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
   constexpr uint32_t kABytes = 2 * MT * kBoxBytes;
@@ -135,15 +137,24 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
     // up to six boxes per k-block overlaps instead of serialising.
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
     const CUtensorMap* qmap = &p.a_maps[p.tap_map[tap]];
     constexpr int kBoxes = 2 * MT + BLOCK_N / 64;
-    if (p.c8 && lane >= 2 * MT && lane < 2 * MT + BLOCK_N / 8) {  // image mode: this lane owns tap (lane - 2 MT)
+    if (kC8 && lane >= 2 * MT && lane < 2 * MT + BLOCK_N / 8) {  // image mode: this lane owns tap (lane - 2 MT)
       const int tq = lane - 2 * MT;
       dh = p.tap_dh[tq];
       dw = p.tap_dw[tq];
       qmap = &p.a_maps[p.tap_map[tq]];
     }
+    // this lane's box: destination offset inside a stage, tensor map, channel coordinate, spatial offsets
+    const bool is_p = lane < 2 * MT;
+    const bool active = kC8 ? (lane < 2 * MT + BLOCK_N / 8) : (lane < kBoxes);
+    const uint32_t dst_off = is_p ? lane * kBoxBytes
+                                  : (kC8 ? kABytes + (lane - 2 * MT) * 1024 : kABytes + (lane - 2 * MT) * kBoxBytes);
+    const CUtensorMap* map = is_p ? &p.p_map : qmap;
+    const int c0 = is_p ? r_tile * (128 * MT) + lane * 64 : (kC8 ? 0 : c_tile * BLOCK_N + (lane - 2 * MT) * 64);
+    const int ob = is_p ? 0 : dw, oa = is_p ? 0 : dh;
     // pixel-block coordinates advance incrementally (no integer division in the steady state)
     int tw = pb_begin % p.tiles_w;
     int th = (pb_begin / p.tiles_w) % p.tiles_h;
@@ -156,49 +167,40 @@ __global__ void __launch_bounds__(192) wgrad_gemm_kernel(const __grid_constant__
         if (++th == p.tiles_h) { th = 0; ++tn; }
       }
       if (lane == 0) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (p.debug & 4) mbar_arrive(&full_bar[stage]);
-        else mbar_expect_tx(&full_bar[stage], kStageBytes);
+        mbar_wait_s(empty0 + stage * 8, phase ^ 1);
+        mbar_expect_tx_s(full0 + stage * 8, kStageBytes);
       }
       __syncwarp();
-      uint8_t* sa = smem + stage * kStageBytes;
-      if (p.debug & 4) {
-      } else if (lane < 2 * MT) {
-        tma_load_4d(sa + lane * kBoxBytes, &p.p_map, &full_bar[stage], r_tile * (128 * MT) + lane * 64, b0, a0, n0);
-      } else if (p.c8) {
-        // one 1 KB box (64 pixels x 8 channels, un-swizzled) per tap: canonical MN-major core matrices
-        if (lane < 2 * MT + BLOCK_N / 8)
-          tma_load_4d(sa + kABytes + (lane - 2 * MT) * 1024, qmap, &full_bar[stage], 0, b0 + dw, a0 + dh, n0);
-      } else if (lane < kBoxes) {
-        const int j = lane - 2 * MT;
-        tma_load_4d(sa + kABytes + j * kBoxBytes, qmap, &full_bar[stage], c_tile * BLOCK_N + j * 64, b0 + dw, a0 + dh,
-                    n0);
-      }
+      if (active) tma_load_4d_s(smem0 + stage * kStageBytes + dst_off, map, full0 + stage * 8, c0, b0 + ob, a0 + oa, n0);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // (elect.sync: straight-line MMA issue, see conv_gemm_persistent_kernel)
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      // MN-major SWIZZLE_128B operands: 8-pixel groups are 1024 B apart (SBO), 64-channel atoms 8192 B apart (LBO), a K
+      // step (16 pixels) is 2048 B.  Image mode B: a k-step = 16 pixels = two 8-pixel core-matrix rows 128 B apart (LBO),
+      // the taps (8-column groups of N) are 1 KB apart (SBO), K step 256 B.
+      constexpr uint32_t kSwHi = 0x40004040u, kSwLo = (kBoxBytes >> 4) << 16, kSwStep = 2048 >> 4;
+      constexpr uint32_t kBHi = kC8 ? (0x4000u | (1024u >> 4)) : kSwHi;
+      constexpr uint32_t kBLo = kC8 ? (128u >> 4) << 16 : kSwLo;
+      constexpr uint32_t kBStep = kC8 ? 256 >> 4 : kSwStep;
+      uint32_t accumulate = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_s(full0 + stage * 8, phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-        const uint32_t sb = sa + kABytes;
+        const uint32_t alo = ((smem0 + stage * kStageBytes) >> 4) | kSwLo;
+        const uint32_t blo = ((smem0 + stage * kStageBytes + kABytes) >> 4) | kBLo;
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
 #pragma unroll
-          for (int k = 0; k < 64 / 16; ++k) {
-            // MN-major SW128: 8-pixel groups are 1024 B apart (SBO), 64-channel atoms 8192 B apart (LBO)
-            const uint64_t da = make_smem_desc_sw128(sa + m * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
-            // image mode: a k-step = 16 pixels = two 8-pixel core-matrix rows 128 B apart (LBO); the taps
-            // (8-column groups of N) are 1 KB apart (SBO)
-            const uint64_t db = p.c8 ? make_smem_desc_plain(sb + k * 256, 128, 1024)
-                                     : make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
-            if (!(p.debug & 8)) umma_bf16(tmem_base + m * BLOCK_N, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16(tmem_base + m * BLOCK_N, ((uint64_t)kSwHi << 32) | (alo + m * ((2 * kBoxBytes) >> 4) + k * kSwStep),
+                      ((uint64_t)kBHi << 32) | (blo + k * kBStep), kIdesc, k == 0 ? accumulate : 1u);
         }
-        umma_commit(&empty_bar[stage]);
+        accumulate = 1;
+        umma_commit_s(empty0 + stage * 8);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full_bar);
@@ -349,7 +351,11 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvGeom2& p, int tile_id)
   return t;
 }
 
-template <int BLOCK_N, int STAGES, bool kTmaStore>
+// kC8 = image mode (ConvGeom2::c8) as a compile-time switch: the producer / MMA loops are single-thread instruction
+// streams (~500 cycles per k-block before the clean-up below, measured with the pipeline stages switched off:
+// profiles/r02_conv_pipeline_bound.txt), which is what bounded every BLOCK_N <= 128 layer, so nothing that can be
+// decided at compile time or per tile is left inside them.
+template <int BLOCK_N, int STAGES, bool kTmaStore, bool kC8>
 __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __grid_constant__ ConvGeom2 p) {
   constexpr uint32_t kABytes = kBlockM * 128;
   constexpr uint32_t kBBytes = BLOCK_N * 128;
@@ -408,67 +414,85 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   pdl_launch_dependents();
 
   if (warp == 0) {
-    if (lane == 0) {
+    // One ELECTED thread (elect.sync, not `lane == 0`: the compiler then knows the block is executed by exactly one
+    // thread and emits the TMA / MMA / commit instructions straight instead of inside per-instruction waterfall loops).
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(p, tile);
-        for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          // timing experiments (scripts/exp_conv_bound.py): debug bit 8 skips the A boxes, bit 9 the B boxes
-          const bool ld_a = !(p.debug & 256), ld_b = !(p.debug & 512);
-          mbar_expect_tx(&full_bar[stage], (ld_a ? kABytes : 0u) + (ld_b ? kBBytes : 0u));
-          uint8_t* sa = smem + stage * kStageBytes;
-          if (p.c8) {
+        if (kC8) {
+          for (int kb = t.kb0; kb < t.kb1; ++kb) {
+            mbar_wait_s(empty0 + stage * 8, phase ^ 1);
+            mbar_expect_tx_s(full0 + stage * 8, kStageBytes);
+            const uint32_t sa = smem0 + stage * kStageBytes;
 #pragma unroll 1
-            for (int j = 0; j < 8 && ld_a; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const int tap = t.tap0 + kb * 8 + j;
-              tma_load_4d(sa + j * (kBlockM * 16), &p.a_maps[p.tap_map[tap]], &full_bar[stage], 0, t.b0 + p.tap_dw[tap],
-                          t.a0 + p.tap_dh[tap], t.n0);
+              tma_load_4d_s(sa + j * (kBlockM * 16), &p.a_maps[p.tap_map[tap]], full0 + stage * 8, 0,
+                            t.b0 + p.tap_dw[tap], t.a0 + p.tap_dh[tap], t.n0);
             }
-            if (ld_b) tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kb * kBlockK, 0, t.n_tile * BLOCK_N);
-          } else {
-            const int tl = kb / p.k_chunks;
-            const int kc = kb - tl * p.k_chunks;
-            const int tap = t.tap0 + tl;
-            if (ld_a)
-              tma_load_4d(sa, &p.a_maps[p.tap_map[tap]], &full_bar[stage], kc * kBlockK, t.b0 + p.tap_dw[tap],
-                          t.a0 + p.tap_dh[tap], t.n0);
-            if (ld_b)
-              tma_load_3d(sa + kABytes, &p.b_map, &full_bar[stage], kc * kBlockK,
-                          p.w_per_image ? t.n0 : (int)p.tap_widx[tap], t.n_tile * BLOCK_N);
+            tma_load_3d_s(sa + kABytes, &p.b_map, full0 + stage * 8, kb * kBlockK, 0, t.n_tile * BLOCK_N);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        } else {
+          // k-block kb = (tap tl, channel chunk kc): the tap's table entries are read once per tap, not per k-block
+          int tl = t.kb0 / p.k_chunks;
+          int kc = t.kb0 - tl * p.k_chunks;
+          const int brow = t.n_tile * BLOCK_N;
+          for (int kb = t.kb0; kb < t.kb1; ++tl, kc = 0) {
+            const int tap = t.tap0 + tl;
+            const CUtensorMap* amap = &p.a_maps[p.tap_map[tap]];
+            const int cb = t.b0 + p.tap_dw[tap], ca = t.a0 + p.tap_dh[tap];
+            const int wrow = p.w_per_image ? t.n0 : (int)p.tap_widx[tap];
+            const int kc_end = min(p.k_chunks, kc + (t.kb1 - kb));
+            for (; kc < kc_end; ++kc, ++kb) {
+              mbar_wait_s(empty0 + stage * 8, phase ^ 1);
+              mbar_expect_tx_s(full0 + stage * 8, kStageBytes);
+              const uint32_t sa = smem0 + stage * kStageBytes;
+              tma_load_4d_s(sa, amap, full0 + stage * 8, kc * kBlockK, cb, ca, t.n0);
+              tma_load_3d_s(sa + kABytes, &p.b_map, full0 + stage * 8, kc * kBlockK, wrow, brow);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      // Shared-memory matrix descriptors (common.cuh): the upper word is a constant, the lower word = (address >> 4) |
+      // (leading byte offset >> 4) << 16, and a K step of 16 elements just adds to the address field.
+      //  K-major SWIZZLE_128B (A of the channel mode, B always): LBO 16, SBO 1024, K step 32 bytes.
+      //  image mode A: one MMA (K = 16) spans two taps = two core-matrix columns 2 KB apart (LBO); the 8-pixel row
+      //  groups of a tap are 128 B apart (SBO); K step = two taps = 4 KB.
+      constexpr uint32_t kSwHi = 0x40004040u, kSwLo = 1u << 16, kSwStep = 32 >> 4;
+      constexpr uint32_t kAHi = kC8 ? (0x4000u | (128u >> 4)) : kSwHi;
+      constexpr uint32_t kALo = kC8 ? ((uint32_t)(kBlockM * 16) >> 4) << 16 : kSwLo;
+      constexpr uint32_t kAStep = kC8 ? (2 * kBlockM * 16) >> 4 : kSwStep;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(p, tile);
         if (t.kb1 <= t.kb0) continue;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        uint32_t accumulate = 0;  // the first MMA of a tile overwrites the accumulator
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_s(full0 + stage * 8, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t alo = ((smem0 + stage * kStageBytes) >> 4) | kALo;
+          const uint32_t blo = ((smem0 + stage * kStageBytes + kABytes) >> 4) | kSwLo;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // image mode: one MMA (K = 16) spans two taps = two core-matrix columns 2 KB apart (LBO); the 8-pixel
-            // row groups of a tap are 128 B apart (SBO)
-            const uint64_t da = p.c8 ? make_smem_desc_plain(sa + k * (2 * kBlockM * 16), kBlockM * 16, 128)
-                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (!(p.debug & 1024)) umma_bf16(tmem_d, da, db, kIdesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(tmem_d, ((uint64_t)kAHi << 32) | (alo + k * kAStep), ((uint64_t)kSwHi << 32) | (blo + k * kSwStep),
+                      kIdesc, k == 0 ? accumulate : 1u);
+          accumulate = 1;
+          umma_commit_s(empty0 + stage * 8);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);
@@ -701,9 +725,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// Completes the tail tiles of conv_gemm_persistent_kernel (ConvGeom2::tail_*): one CTA per tail tile, thread = output
-// column (coalesced in the workspace and in the NHWC output).  out = bf16(act(sum_parts ws + bias)); the per-channel
-// statistics use the stored bf16 values of the valid rows, exactly like the fused epilogue.
+// Completes the tail tiles of conv_gemm_persistent_kernel (ConvGeom2::tail_*): grid = (tail tiles, 128 / kTailRows),
+// thread = output column (coalesced in the workspace and in the NHWC output), kTailRows rows per CTA with all their
+// loads in flight.  out = bf16(act(sum_parts ws + bias)); the per-channel statistics use the stored bf16 values of the
+// valid rows, exactly like the fused epilogue.
+static constexpr int kTailRows = 16;
+static constexpr int kTailMaxParts = 4;
 template <int BLOCK_N>
 __global__ void __launch_bounds__(BLOCK_N) conv_tail_finalize_kernel(const __grid_constant__ ConvGeom2 p) {
   pdl_wait();
@@ -719,19 +746,28 @@ __global__ void __launch_bounds__(BLOCK_N) conv_tail_finalize_kernel(const __gri
     if (ts.kb1 > ts.kb0) nparts = s + 1;
   }
   const float bias = (p.bias != nullptr && col < p.bias_cols) ? __ldg(p.bias + col) : 0.f;
-  const float* ws = p.tail_ws + (long long)item0 * kBlockM * BLOCK_N + threadIdx.x;
+  const int r0 = blockIdx.y * kTailRows;
+  const float* __restrict__ ws = p.tail_ws + ((long long)item0 * kBlockM + r0) * BLOCK_N + threadIdx.x;
+  float v[kTailRows];
+#pragma unroll
+  for (int i = 0; i < kTailRows; ++i) {
+    v[i] = 0.f;
+#pragma unroll
+    for (int s = 0; s < kTailMaxParts; ++s)
+      if (s < nparts) v[i] += __ldg(ws + ((long long)s * kBlockM + i) * BLOCK_N);
+  }
   const int wt_mask = (1 << p.log_wt) - 1, ht_mask = (1 << p.log_ht) - 1;
+  bf16* __restrict__ out = p.out + p.cls_out_off[t.cls] + col;
   float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-  for (int r = 0; r < kBlockM; ++r) {
+#pragma unroll
+  for (int i = 0; i < kTailRows; ++i) {
+    const int r = r0 + i;
     const int b = t.b0 + (r & wt_mask);
     const int a = t.a0 + ((r >> p.log_wt) & ht_mask);
     const int n = t.n0 + (r >> (p.log_wt + p.log_ht));
     if (!((n < p.GN) && (a < p.cls_GH[t.cls]) && (b < p.cls_GW[t.cls]))) continue;  // block-uniform
-    float v = 0.f;
-    for (int s = 0; s < nparts; ++s) v += ws[((long long)s * kBlockM + r) * BLOCK_N];
-    const bf16 o = __float2bfloat16(apply_act(v + bias, p.act, p.slope));
-    p.out[p.cls_out_off[t.cls] + (long long)n * p.out_sn + (long long)a * p.out_sh + (long long)b * p.out_sw + col] = o;
+    const bf16 o = __float2bfloat16(apply_act(v[i] + bias, p.act, p.slope));
+    out[(long long)n * p.out_sn + (long long)a * p.out_sh + (long long)b * p.out_sw] = o;
     const float xv = __bfloat162float(o);
     s1 += xv;
     s2 += xv * xv;
@@ -830,20 +866,20 @@ static int cur_device() {
   return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
 
-template <int BLOCK_N, int STAGES, int MT>
+template <int BLOCK_N, int STAGES, int MT, bool C8 = false>
 static int launch_wgrad_gemm(const GemmGeom& g, dim3 grid, cudaStream_t st) {
   const int smem = STAGES * (2 * MT * 8192 + (BLOCK_N / 64) * 8192) + 1024 + 256;
   static bool configured[kMaxDevices] = {};
   const int dev = cur_device();
   if (!configured[dev]) {
-    if (cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N, STAGES, MT, C8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem) != cudaSuccess) {
       gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
       return GCC_ERR_CUDA;
     }
     configured[dev] = true;
   }
-  gcc_launch(wgrad_gemm_kernel<BLOCK_N, STAGES, MT>, grid, 192, smem, st, g);
+  gcc_launch(wgrad_gemm_kernel<BLOCK_N, STAGES, MT, C8>, grid, 192, smem, st, g);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -914,14 +950,14 @@ static int num_sms() {
   return g_num_sms[dev];
 }
 
-template <int BLOCK_N, int STAGES, bool TS>
+template <int BLOCK_N, int STAGES, bool TS, bool C8>
 static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
   const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + (TS ? 2 * (BLOCK_N / 64) * 16384 : 0) + 1024 + 256 +
                    8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
   static bool configured[kMaxDevices] = {};
   const int dev = cur_device();
   if (!configured[dev]) {
-    if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS, C8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem) != cudaSuccess) {
       gcc_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed");
       return GCC_ERR_CUDA;
@@ -929,7 +965,7 @@ static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
     configured[dev] = true;
   }
   const int grid = g.total_tiles < num_sms() ? g.total_tiles : num_sms();
-  gcc_launch(conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS>, grid, 320, smem, st, g);
+  gcc_launch(conv_gemm_persistent_kernel<BLOCK_N, STAGES, TS, C8>, grid, 320, smem, st, g);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
@@ -1153,7 +1189,7 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
     if (waves >= 1 && waves <= 8 && rem > 0 && rem * 2 <= S && min_kb >= 32) {
       int ks = S / rem;
       if (ks > min_kb / 16) ks = min_kb / 16;
-      if (ks > 4) ks = 4;
+      if (ks > kTailMaxParts) ks = kTailMaxParts;
       if (ks >= 2 && ws_elems >= (long long)rem * ks * kBlockM * BN) {
         g.tail_begin = base_tiles - rem;
         g.tail_splits = ks;
@@ -1167,15 +1203,20 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
   g.stats_ld = stats_ld;
 
   trace_begin(st);
-  if (BN == 64) rc = launch_conv_persistent<64, 6, true>(g, st);
-  else if (BN == 128 && max_kb <= 8) rc = launch_conv_persistent<128, 4, true>(g, st);
-  else if (BN == 128) rc = launch_conv_persistent<128, 6, false>(g, st);
-  else rc = launch_conv_persistent<256, 4, false>(g, st);
+  if (c8) {  // image mode: K = 16 taps x 8 channels = 2 k-blocks, always the short-K kernels
+    if (BN == 64) rc = launch_conv_persistent<64, 6, true, true>(g, st);
+    else if (BN == 128) rc = launch_conv_persistent<128, 4, true, true>(g, st);
+    else rc = launch_conv_persistent<256, 4, false, true>(g, st);
+  } else if (BN == 64) rc = launch_conv_persistent<64, 6, true, false>(g, st);
+  else if (BN == 128 && max_kb <= 8) rc = launch_conv_persistent<128, 4, true, false>(g, st);
+  else if (BN == 128) rc = launch_conv_persistent<128, 6, false, false>(g, st);
+  else rc = launch_conv_persistent<256, 4, false, false>(g, st);
   if (rc) return rc;
   if (g.tail_splits > 1) {
     const unsigned tail_tiles = (unsigned)((g.total_tiles - g.tail_begin) / g.tail_splits);
-    if (BN == 256) gcc_launch(conv_tail_finalize_kernel<256>, tail_tiles, 256, 0, st, g);
-    else gcc_launch(conv_tail_finalize_kernel<128>, tail_tiles, 128, 0, st, g);
+    const dim3 fgrid(tail_tiles, kBlockM / kTailRows);
+    if (BN == 256) gcc_launch(conv_tail_finalize_kernel<256>, fgrid, 256, 0, st, g);
+    else gcc_launch(conv_tail_finalize_kernel<128>, fgrid, 128, 0, st, g);
     GCC_CHECK_LAUNCH();
   }
   if (g.k_splits > 1 && !f32_out) {
@@ -1320,7 +1361,9 @@ static int gcc_wgrad_gemm_launch(const void* pmat, int N, int OH, int OW, int Cp
   }
   dim3 grid(r_tiles, c_tiles, g.num_taps * splits * (batched ? N : 1));
   trace_begin(st);
-  if (BN == 64) rc = launch_wgrad_gemm<64, 4, 1>(g, grid, st);
+  if (c8 && MT == 2) rc = launch_wgrad_gemm<128, 4, 2, true>(g, grid, st);
+  else if (c8) rc = launch_wgrad_gemm<128, 3, 1, true>(g, grid, st);
+  else if (BN == 64) rc = launch_wgrad_gemm<64, 4, 1>(g, grid, st);
   else if (BN == 128 && MT == 2) rc = launch_wgrad_gemm<128, 4, 2>(g, grid, st);
   else if (BN == 128) rc = launch_wgrad_gemm<128, 3, 1>(g, grid, st);
   else if (MT == 2) rc = launch_wgrad_gemm<256, 3, 2>(g, grid, st);

@@ -132,10 +132,6 @@ struct NormArgs {
   int act;
   float slope;
   int gate_after;  // 1: y = mask * act(z) (identity norm only: PatchGAN layer 0, Pix2Pix.py:320-322)
-  // 1: the grid sweeps the pixels from the LAST to the first (signed strides).  A kernel that follows an ascending
-  // producer (the conv that wrote x / dy) finds the end of that tensor still in the 126 MB L2 when it starts there,
-  // and leaves the START of its own operands in L2 for an ascending consumer (GCC_B200_NORM_SWEEP, see fill_args).
-  int rev;
 };
 
 __device__ __forceinline__ void channel_affine(const NormArgs& a, int n, int c, float& mean, float& rstd,
@@ -169,7 +165,7 @@ norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict_
   pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
-  const int n = a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int n = blockIdx.y;
   if (lane < lanes) {
     float cp[8], cq[8], cm[8];
 #pragma unroll
@@ -181,11 +177,8 @@ norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict_
       cq[k] = (bet - mean * rstd * gam) * mk;
       cm[k] = a.gate_after ? mask : 1.f;
     }
-    // pixel q of the sweep lives at (pix0 + q) [ascending] or (pix0 + npix - 1 - q) [a.rev]: signed strides
-    const long long pix0 = (a.per_sample ? (long long)n * a.npix : 0) + (a.rev ? a.npix - 1 : 0);
-    const long long sg = a.rev ? -1 : 1;
+    const long long pix0 = a.per_sample ? (long long)n * a.npix : 0;
     const long long step = (long long)gridDim.x * lanes;
-    const long long sx = sg * a.Cp, sy2 = sg * y2_Cp;
     const bf16* xb = a.x + pix0 * a.Cp + g * 8;
     bf16* yb = y ? y + pix0 * a.Cp + g * 8 : nullptr;
     bf16* y2b = DUAL ? y2 + pix0 * y2_Cp + y2_coff + g * 8 : nullptr;
@@ -198,18 +191,18 @@ norm_apply_kernel(NormArgs a, int lanes, bf16* __restrict__ y, bf16* __restrict_
         o.v[k] = act_fwd(z, a.act, a.slope) * cm[k];
         if (DUAL) o2.v[k] = act_fwd(z, act2, a.slope) * cm[k];
       }
-      if (yb) store8(yb + p * sx, o);
-      if (DUAL) store8(y2b + p * sy2, o2);
+      if (yb) store8(yb + p * a.Cp, o);
+      if (DUAL) store8(y2b + p * y2_Cp, o2);
     };
     long long p = (long long)blockIdx.x * lanes + lane;
     for (; p + 3 * step < a.npix; p += 4 * step) {  // four independent 16-byte loads in flight per thread
       uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) u[j] = *reinterpret_cast<const uint4*>(xb + (p + j * step) * sx);
+      for (int j = 0; j < 4; ++j) u[j] = *reinterpret_cast<const uint4*>(xb + (p + j * step) * a.Cp);
 #pragma unroll
       for (int j = 0; j < 4; ++j) emit(u[j], p + j * step);
     }
-    for (; p < a.npix; p += step) emit(*reinterpret_cast<const uint4*>(xb + p * sx), p);
+    for (; p < a.npix; p += step) emit(*reinterpret_cast<const uint4*>(xb + p * a.Cp), p);
   }
   // running statistics (train-mode BatchNorm2d side effect; momentum 0.1, unbiased variance)
   if (running_mean != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && a.sums != nullptr) {
@@ -271,9 +264,8 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
   extern __shared__ float sred[];  // [lanes][G][16]
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
-  const int n = a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-  const long long pix0 = (long long)n * a.npix + (a.rev ? a.npix - 1 : 0);  // blockIdx.y == 0 for batch norm
-  const long long sg = a.rev ? -1 : 1;  // signed strides: pixel q of the sweep lives at pix0 + sg * q
+  const int n = blockIdx.y;
+  const long long pix0 = (long long)n * a.npix;  // blockIdx.y == 0 for batch norm
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
@@ -312,10 +304,9 @@ norm_bwd_reduce_kernel(NormArgs a, int lanes, const bf16* __restrict__ dy, int d
     };
     const uint4 zero = make_uint4(0, 0, 0, 0);
     const long long step = (long long)gridDim.x * lanes;
-    const long long sx = sg * a.Cp, s1y = sg * dy_Cp, s2y = sg * dy2_Cp;
-    auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * sx) : zero; };
-    auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * s1y) : zero; };
-    auto ld2 = [&](long long q) { return (HAS_D2 && d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * s2y) : zero; };
+    auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * a.Cp) : zero; };
+    auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * dy_Cp) : zero; };
+    auto ld2 = [&](long long q) { return (HAS_D2 && d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
     // register double buffer over groups of U pixels (out-of-range pixels load zeros and contribute nothing)
     long long p = (long long)blockIdx.x * lanes + lane;
     uint4 cx[U], c1[U], c2[U], nx[U], n1[U], n2[U];
@@ -373,7 +364,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
   pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int g = tid % a.G, lane = tid / a.G;
-  const int n = a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int n = blockIdx.y;
   const float invM = 1.f / (float)a.stat_npix;
   if (dx != nullptr && lane < lanes) {
     const float* rb = red + (long long)n * 2 * a.Cp;
@@ -396,9 +387,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
         c3[k] = 0.f;
       }
     }
-    const long long pix0 = (a.per_sample ? (long long)n * a.npix : 0) + (a.rev ? a.npix - 1 : 0);
-    const long long sg = a.rev ? -1 : 1;  // signed strides: pixel q of the sweep lives at pix0 + sg * q
-    const long long sx = sg * a.Cp, s1y = sg * dy_Cp, s2y = sg * dy2_Cp;
+    const long long pix0 = a.per_sample ? (long long)n * a.npix : 0;
     const long long step = (long long)gridDim.x * lanes;
     const bf16* xb = a.x + pix0 * a.Cp + g * 8;
     const bf16* d1b = dy ? dy + pix0 * dy_Cp + dy_coff + g * 8 : nullptr;
@@ -415,12 +404,12 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(NormArgs a, int 
         if (HAS_D2 && d2b) dg += d2.v[k] * act_grad(gg, act2, a.slope);
         o.v[k] = c1[k] * dg - c2[k] - c3[k] * xv.v[k];
       }
-      store8(ob + p * sx, o);
+      store8(ob + p * a.Cp, o);
     };
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * sx) : zero; };
-    auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * s1y) : zero; };
-    auto ld2 = [&](long long q) { return (HAS_D2 && d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * s2y) : zero; };
+    auto ldx = [&](long long q) { return q < a.npix ? *reinterpret_cast<const uint4*>(xb + q * a.Cp) : zero; };
+    auto ld1 = [&](long long q) { return (d1b && q < a.npix) ? *reinterpret_cast<const uint4*>(d1b + q * dy_Cp) : zero; };
+    auto ld2 = [&](long long q) { return (HAS_D2 && d2b && q < a.npix) ? *reinterpret_cast<const uint4*>(d2b + q * dy2_Cp) : zero; };
     // register double buffer over groups of U pixels
     long long p = (long long)blockIdx.x * lanes + lane;
     uint4 cx[U], e1[U], e2[U], nx[U], n1[U], n2[U];
@@ -484,24 +473,11 @@ static int fill_args(NormArgs& a, const void* x, int N, long long HW, int Cp, in
   a.sums = sums; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
   a.thr = thr; a.eps = eps; a.act = act; a.slope = slope;
   a.gate_after = gate_after;
-  a.rev = 0;
   if (gate_after && sums != nullptr) {
     gcc_set_error(__FILE__, __LINE__, "norm: gate_after_act is only defined for the identity norm");
     return GCC_ERR_ARG;
   }
   return GCC_OK;
-}
-
-// Sweep direction of the three big norm kernels (NormArgs::rev): bit 0 forward apply, bit 1 backward reduce, bit 2
-// backward apply sweep from the last pixel to the first.  Default GCC_B200_NORM_SWEEP (else kDefaultSweep);
-// gcc_debug_set_norm_sweep(mask) overrides it in-process (-1: back to the default).  Results do not depend on it
-// beyond the fp32 summation order of the reduce kernel.
-static constexpr int kDefaultSweep = 0;
-static int g_norm_sweep = -1;
-extern "C" void gcc_debug_set_norm_sweep(int mask) { g_norm_sweep = mask; }
-static int norm_sweep() {
-  static const int env = getenv("GCC_B200_NORM_SWEEP") ? atoi(getenv("GCC_B200_NORM_SWEEP")) : kDefaultSweep;
-  return (g_norm_sweep >= 0 ? g_norm_sweep : env) & 7;
 }
 
 // blocks for a (group, lane) kernel: each thread visits >= `per` pixels, whole grid <= ~16 CTAs per SM
@@ -522,9 +498,20 @@ static int ew_blocks(long long nvec) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-// sums: fp32 [N if per_sample else 1][2][Cp]; zeroed here.
+// sums: fp32 [N if per_sample else 1][2][Cp]; zeroed here (zero_sums) or by the caller (gcc_norm_stats_acc_bf16: the
+// host side hands out pre-zeroed scratch that one fill per training phase clears, instead of one memset node per call).
+static int norm_stats_launch(const void* x, int N, long long HW, int Cp, int per_sample, float* sums, int zero_sums,
+                             void* stream);
 extern "C" int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, int per_sample, float* sums,
                                    void* stream) {
+  return norm_stats_launch(x, N, HW, Cp, per_sample, sums, 1, stream);
+}
+extern "C" int gcc_norm_stats_acc_bf16(const void* x, int N, long long HW, int Cp, int per_sample, float* sums,
+                                       void* stream) {
+  return norm_stats_launch(x, N, HW, Cp, per_sample, sums, 0, stream);
+}
+static int norm_stats_launch(const void* x, int N, long long HW, int Cp, int per_sample, float* sums, int zero_sums,
+                             void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (Cp % 8 || Cp / 8 > 512) {
     gcc_set_error(__FILE__, __LINE__, "norm_stats: bad channel count");
@@ -533,7 +520,7 @@ extern "C" int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, i
   const int G = Cp / 8;
   const int groups = per_sample ? N : 1;
   const long long npix = per_sample ? HW : (long long)N * HW;
-  if (cudaMemsetAsync(sums, 0, sizeof(float) * 2 * Cp * groups, st) != cudaSuccess) return GCC_ERR_CUDA;
+  if (zero_sums && cudaMemsetAsync(sums, 0, sizeof(float) * 2 * Cp * groups, st) != cudaSuccess) return GCC_ERR_CUDA;
   int lanes;
   const int threads = stats_threads(G, &lanes);
   long long bx = (npix + lanes * 8 - 1) / (lanes * 8);
@@ -561,7 +548,6 @@ extern "C" int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, 
     return GCC_ERR_ARG;
   }
   const int groups = per_sample ? N : 1;
-  a.rev = norm_sweep() & 1;
   int lanes;
   const int threads = stats_threads(a.G, &lanes);
   const int bx = lane_blocks(a.npix, lanes, groups, 4);
@@ -590,8 +576,8 @@ extern "C" int gcc_norm_apply_eval_bf16(const void* x, void* y, int N, long long
   return GCC_OK;
 }
 
-// red: fp32 workspace [N if per_sample else 1][2][Cp] (zeroed here).  dx may be NULL (only parameter
-// gradients wanted); dgamma/dbeta/dalpha may be NULL.
+// red: fp32 workspace [N if per_sample else 1][2][Cp] (zeroed here unless phase has bit 2 set: `red` is then
+// pre-zeroed scratch of the caller).  dx may be NULL (only parameter gradients wanted); dgamma/dbeta/dalpha may be NULL.
 extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int C, int per_sample, const float* sums,
                                  const float* gamma, const float* beta, const float* alpha, float thr, float eps,
                                  int act, float slope, int gate_after, const void* dy, int dy_Cp, int dy_coff,
@@ -608,6 +594,8 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
     return GCC_ERR_ARG;
   }
   const int groups = per_sample ? N : 1;
+  const bool prezeroed = (phase & 4) != 0;
+  phase &= ~4;
   if (phase < 0 || phase > 2) {
     gcc_set_error(__FILE__, __LINE__, "norm_bwd: phase must be 0 (both), 1 (reduce) or 2 (apply)");
     return GCC_ERR_ARG;
@@ -615,16 +603,14 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
   if (red_param == nullptr) red_param = red;
   const bool need_red = ((sums != nullptr) || dgamma || dbeta || dalpha || phase == 1) && phase != 2;
   if (need_red) {
-    if (cudaMemsetAsync(red, 0, sizeof(float) * 2 * Cp * groups, st) != cudaSuccess) return GCC_ERR_CUDA;
+    if (!prezeroed && cudaMemsetAsync(red, 0, sizeof(float) * 2 * Cp * groups, st) != cudaSuccess) return GCC_ERR_CUDA;
     int lanes;
     const int threads = stats_threads(a.G, &lanes);
     long long bx = (a.npix + lanes * 8 - 1) / (lanes * 8);
     const long long cap = (148LL * 2 + groups - 1) / groups;  // one resident wave (launch bounds: 2 CTAs / SM)
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    a.rev = (norm_sweep() >> 1) & 1;
-    static const int flat_env = getenv("GCC_B200_NORM_REDUCE_FLAT") ? atoi(getenv("GCC_B200_NORM_REDUCE_FLAT")) : 0;
-    const int flat = g_norm_sweep >= 0 && (g_norm_sweep >> 8) ? (g_norm_sweep >> 8) & 15 : flat_env;  // experiment switch
+    static const int flat = getenv("GCC_B200_NORM_REDUCE_FLAT") ? atoi(getenv("GCC_B200_NORM_REDUCE_FLAT")) : 0;
     if (dy2 == nullptr && flat == 4)
       gcc_launch(norm_bwd_reduce_kernel<4, false, false>, dim3((unsigned)bx, groups), threads, sizeof(float) * lanes * a.G * 16, st, a,
                  lanes, (const bf16*)dy, dy_Cp, dy_coff, (const bf16*)dy2, dy2_Cp, dy2_coff, act2, red);
@@ -640,7 +626,6 @@ extern "C" int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int
     GCC_CHECK_LAUNCH();
   }
   if (phase == 1) return GCC_OK;
-  a.rev = (norm_sweep() >> 2) & 1;
   int alanes;
   const int athreads = stats_threads(a.G, &alanes);
   const int bx = dx ? lane_blocks(a.npix, alanes, groups, 2, 2) : 1;

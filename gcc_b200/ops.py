@@ -104,7 +104,7 @@ class _ZeroPool:
     def take(self, n, device):
         ent = self.bufs.get(device)
         if ent is None:
-            ent = self.bufs[device] = [torch.zeros(1 << 20, dtype=torch.float32, device=device), 0]
+            ent = self.bufs[device] = [torch.zeros(1 << 22, dtype=torch.float32, device=device), 0]
         buf, off = ent
         n8 = (n + 7) // 8 * 8
         if off + n8 > buf.numel():
@@ -618,13 +618,12 @@ class NormActFn(torch.autograd.Function):
                 if sums_in is not None and not per_sample:
                     sums = sums_in  # accumulated by the producing conv's epilogue
                 else:
-                    sums = torch.empty((n if per_sample else 1) * 2 * cp, dtype=torch.float32, device=x.device)
-                    call("gcc_norm_stats_bf16", x.data_ptr(), n, h * w, cp, per_sample, sums.data_ptr(), st)
+                    sums = zero_pool.take((n if per_sample else 1) * 2 * cp, x.device)
+                    call("gcc_norm_stats_acc_bf16", x.data_ptr(), n, h * w, cp, per_sample, sums.data_ptr(), st)
                 if layer.stats_hook is not None:
                     layer.stats_hook(sums)
                 if GLOBAL_BATCH_SYNC and mode == "bn":
-                    if sums_in is not None:
-                        sums = sums.clone()      # the producer's buffer belongs to the shared zero pool
+                    sums = sums.clone()      # the buffer belongs to the shared zero pool
                     _allreduce_sum(sums)
             stat_count = n * h * w * _world() if mode == "bn" else 0
             rm = rv = None
@@ -665,7 +664,7 @@ class NormActFn(torch.autograd.Function):
         dbeta = arena_of(beta) if (beta is not None and ctx.needs_input_grad[2]) else None
         dalpha = arena_of(alpha) if (alpha is not None and ctx.needs_input_grad[3]) else None
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        red = torch.empty((n if per_sample else 1) * 2 * cp, dtype=torch.float32, device=x.device)
+        red = zero_pool.take((n if per_sample else 1) * 2 * cp, x.device)   # pre-zeroed: phase | 4 below
         gate_after = 1 if (getattr(layer, "gate_after", layer.mode == "id") and layer.mode == "id" and alpha is not None) else 0
 
         def bwd(phase, red_param):
@@ -673,7 +672,7 @@ class NormActFn(torch.autograd.Function):
                  None if sums is None else sums.data_ptr(), None if gamma is None else gamma.data_ptr(),
                  None if beta is None else beta.data_ptr(), None if alpha is None else alpha.data_ptr(), layer.thr, BN_EPS,
                  ctx.act, layer.slope, gate_after, p1, c1, 0, p2, c2, 0, ctx.act2 or 0, red.data_ptr(),
-                 None if dx is None else dx.data_ptr(), dgamma, dbeta, dalpha, ctx.stat_count, phase,
+                 None if dx is None else dx.data_ptr(), dgamma, dbeta, dalpha, ctx.stat_count, phase | 4,
                  None if red_param is None else red_param.data_ptr(), st)
 
         if GLOBAL_BATCH_SYNC and layer.mode == "bn":

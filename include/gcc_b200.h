@@ -59,13 +59,9 @@ int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void
                         float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched, int accumulate,
                         float scale, void* stream);
 void gcc_debug_force_block_n(int bn);
-/* timing experiments / A-B switches: bit0 skip conv epilogue stores, bit1 skip TMEM loads, bit2/3 wgrad: skip TMA /
- * MMA, bit4 wgrad 128-row tiles, bit5 per-launch GEMM trace, bit7 no image mode, bit8/9 conv: skip the A / B boxes,
- * bit10 conv: skip the MMAs, bit11 no tail-wave split.  Bits 0-4 and 8-10 produce garbage results. */
+/* timing experiments / A-B switches: bit0 skip conv epilogue stores, bit1 skip TMEM loads (both: garbage results),
+ * bit4 wgrad 128-row tiles, bit5 per-launch GEMM trace, bit7 no image mode, bit11 no tail-wave split. */
 void gcc_debug_set_flags(int f);
-/* sweep direction of the norm kernels (bit0 forward apply, bit1 backward reduce, bit2 backward apply run from the last
- * pixel to the first: L2 reuse behind / in front of an ascending conv); -1 restores GCC_B200_NORM_SWEEP / the default */
-void gcc_debug_set_norm_sweep(int mask);
 
 /* ---- norm / gate / activation blocks (norm.cu) ----
  * One block = [BatchNorm2d | InstanceNorm2d | identity] -> [DifferentiableOP gate] -> [(Leaky)ReLU]
@@ -78,6 +74,8 @@ void gcc_debug_set_norm_sweep(int mask);
  *   gate_after=1 (identity norm only): y = mask*act(z), the conv -> LeakyReLU -> gate order of the first
  *   MaskNLayerDiscriminator layer (Pix2Pix.py:320-322), whose gate gradient is sum dy*act(z). */
 int gcc_norm_stats_bf16(const void* x, int N, long long HW, int Cp, int per_sample, float* sums, void* stream);
+/* the same, ACCUMULATING into caller-zeroed `sums` (no memset node per call) */
+int gcc_norm_stats_acc_bf16(const void* x, int N, long long HW, int Cp, int per_sample, float* sums, void* stream);
 int gcc_norm_apply_bf16(const void* x, void* y, int N, long long HW, int Cp, int C, int per_sample, const float* sums,
                         const float* gamma, const float* beta, const float* alpha, float thr, float eps,
                         float* running_mean, float* running_var, float momentum, int act, float slope,
@@ -94,7 +92,8 @@ int gcc_norm_apply_eval_bf16(const void* x, void* y, int N, long long HW, int Cp
  * when the caller has all-reduced them over the ranks (0 = this device's N*HW); `phase` 1 runs only the reduction
  * (red = this device's sum dg, sum dg*xhat), the caller all-reduces a copy, and `phase` 2 runs only the apply pass with
  * the global `red` for dx and `red_param` (this device's sums, NULL = red) for dgamma / dbeta / dalpha; phase 0 = both
- * (the same argument `stat_count` exists on gcc_norm_apply_bf16). */
+ * (the same argument `stat_count` exists on gcc_norm_apply_bf16).  `phase | 4`: `red` is pre-zeroed by the caller
+ * (otherwise the reduction zeroes it with a memset node of its own). */
 int gcc_norm_bwd_bf16(const void* x, int N, long long HW, int Cp, int C, int per_sample, const float* sums,
                       const float* gamma, const float* beta, const float* alpha, float thr, float eps, int act,
                       float slope, int gate_after, const void* dy, int dy_Cp, int dy_coff, const void* dy2, int dy2_Cp,

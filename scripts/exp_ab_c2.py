@@ -1,7 +1,6 @@
 """A/B harness on the c2 bench workload in ONE process: the model is built once, every variant re-captures the
 iteration as a CUDA graph with its switches set (they are read on the host at launch = capture time) and times N replays.
-Variants: tail-wave split of the conv kernel (debug bit 11 = off), sweep direction of the norm kernels
-(gcc_debug_set_norm_sweep).  Usage: python scripts/exp_ab_c2.py [config] [replays]"""
+Variants: tail-wave split of the conv kernel (debug bit 11 = off).  Usage: python scripts/exp_ab_c2.py [config] [replays]"""
 import os
 import sys
 
@@ -30,17 +29,9 @@ for i in range(2):
     factory.run_iteration(model, devb[i][0], devb[i][1])
 torch.cuda.synchronize()
 
-VARIANTS = [("baseline (no tail split, ascending sweeps)", 2048, 0),
-            ("tail split", 0, 0),
-            ("tail split + fwd apply descending", 0, 1),
-            ("tail split + bwd reduce descending", 0, 2),
-            ("tail split + fwd apply & bwd reduce descending", 0, 3),
-            ("tail split + fwd apply & bwd apply descending", 0, 5),
-            ("tail split + un-pipelined reduce, 4 in flight", 0, 4 << 8),
-            ("baseline again", 2048, 0)]
-for name, flags, sweep in VARIANTS:
+VARIANTS = [("baseline (no tail split)", 2048), ("tail split", 0), ("baseline again", 2048), ("tail split again", 0)]
+for name, flags in VARIANTS:
     L.gcc_debug_set_flags(flags)
-    L.gcc_debug_set_norm_sweep(sweep)
     graphed = GraphedIteration(model).capture(devb[0][0], devb[0][1], warmup=1)
     for i in range(3):
         graphed.run(devb[i % 2][0], devb[i % 2][1])
@@ -57,4 +48,3 @@ for name, flags, sweep in VARIANTS:
     del graphed
     torch.cuda.empty_cache()
 L.gcc_debug_set_flags(0)
-L.gcc_debug_set_norm_sweep(-1)

@@ -1,7 +1,7 @@
-"""What bounds the persistent conv kernel on a given layer?  Times one launch with parts of the pipeline switched off
-(gcc_debug_set_flags: bit 0 no epilogue stores, bit 8 no A boxes, bit 9 no B boxes, bit 10 no MMAs; results are then
-garbage, only the time means something) and the tail-wave split on / off (bit 11) on the layers it targets.
-Output: one line per (layer, variant) with the time per launch and per k-block per SM."""
+"""Single-launch timings of the persistent conv kernel on the layers that were furthest from their bound: full, without
+the epilogue stores (debug bit 0; garbage results), and the tail-wave split on / off (bit 11) on the layers it targets.
+(The revision that produced profiles/r02_conv_pipeline_bound.txt also had switches for the A boxes / B boxes / MMAs
+inside the producer and MMA loops; they were removed with the instruction clean-up of those loops.)"""
 import os
 import sys
 
@@ -58,7 +58,7 @@ LAYERS = [
     ("D fprop 512->1024 k4s1 (BN256)", (B, 32, 32, 512, 1024, 4, 1, 1, 0)),
 ]
 for label, shp in LAYERS:
-    for fl in (0, 1, 256, 512, 768, 1024, 1025, 1792):
+    for fl in (0, 1):
         run(label, *shp, flags=fl)
 print()
 for label, shp, stats in (("D dgrad 1024->512 k4s1 (512 tiles)", (B, 31, 31, 1024, 512, 4, 1, 1, 1), False),

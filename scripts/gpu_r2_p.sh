@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2, call O (1 GPU): validation of HEAD (norm reduce on raw x, tail-wave split, sweep switch) + A/B measurements
+# round 2, call P (1 GPU): instruction clean-up of the GEMM issue loops, parallel tail finalize, pooled norm scratch: tests + A/B + bench + launch list
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout=300 > gpurun_out/pytest_o.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_o.log
-grep -E "passed|failed|FAILED|Error|Timeout|^E  |exit" gpurun_out/pytest_o.log | cut -c1-300 | tail -25
+timeout 900 python -m pytest tests -m gpu -q --timeout=300 > gpurun_out/pytest_p.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_p.log
+grep -E "passed|failed|FAILED|Error|Timeout|^E  |exit" gpurun_out/pytest_p.log | cut -c1-300 | tail -25
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-300
 timeout 200 python scripts/exp_conv_bound.py > gpurun_out/conv_bound.txt 2>&1; cat gpurun_out/conv_bound.txt | cut -c1-150
 timeout 400 python scripts/exp_ab_c2.py c2 15 > gpurun_out/ab_c2.txt 2>&1; cat gpurun_out/ab_c2.txt | cut -c1-150

@@ -148,6 +148,7 @@ def test_conv_tail_wave_split(G, case):
         layer.weight.copy_(w0)
         layer.bias.copy_(b0)
     A.mark_dirty()
+    A.ensure_packed()
     x = rnd((N, Cin, H, W), 3)
     res = {}
     for flags in (0, 2048):
@@ -251,46 +252,6 @@ def test_norm_block_fwd_bwd(G, mode, gated, act, dual, C):
         assert rel_err(layer.alpha.grad, ar.grad) < 5e-3
     if C % 8:
         assert bool((y.detach()[..., C:] == 0).all())
-
-
-@pytest.mark.parametrize("mode,gated,dual,C,N,H,W", [("bn", True, False, 40, 3, 33, 17), ("bn", False, True, 24, 2, 16, 16),
-                                                    ("in", False, False, 32, 3, 9, 7), ("id", True, False, 16, 2, 31, 31)])
-def test_norm_sweep_direction(G, mode, gated, dual, C, N, H, W):
-    """The norm kernels swept from the last pixel to the first (NormArgs::rev, all three kernels) against the ascending
-    sweep: the forward outputs are bit-identical, the backward differs only by the fp32 summation order of the reduce."""
-    res = {}
-    for sweep in (0, 7):
-        A, GA = G.arena.ParamArena("cuda"), G.arena.ParamArena("cuda")
-        layer = G.nets.NormLayer(A, "n", C, mode, "cuda", GA if gated else None, "g" if gated else None, 0.5)
-        A.finalize()
-        GA.finalize()
-        layer.bind()
-        with torch.no_grad():
-            if mode == "bn":
-                layer.gamma.copy_(rnd((C,), 1, 0.3) + 1.0)
-                layer.beta.copy_(rnd((C,), 2, 0.5))
-            if gated:
-                layer.alpha.copy_(torch.tensor(([0.7, 0.5, 0.2, 1.0] * C)[:C], device="cuda"))
-        xh = nhwc(rnd((N, C, H, W), 3, 2.0) + 0.5, G).requires_grad_(True)
-        G.lib.lib().gcc_debug_set_norm_sweep(sweep)
-        try:
-            out = layer(xh, 1, 2 if dual else None)
-            outs = list(out) if dual else [out]
-            A.zero_grad()
-            GA.zero_grad()
-            torch.autograd.backward(outs, [nhwc(rnd((N, C, H, W), 4 + i), G) for i in range(len(outs))])
-            torch.cuda.synchronize()
-        finally:
-            G.lib.lib().gcc_debug_set_norm_sweep(-1)
-        grads = [layer.gamma.grad.clone(), layer.beta.grad.clone()] if mode == "bn" else []
-        if gated:
-            grads.append(layer.alpha.grad.clone())
-        res[sweep] = ([o.detach().clone() for o in outs], xh.grad.clone(), grads)
-    for a, b in zip(res[0][0], res[7][0]):
-        assert torch.equal(a, b)
-    assert rel_err(res[7][1].float(), res[0][1].float()) < 1e-3
-    for a, b in zip(res[0][2], res[7][2]):
-        assert rel_err(b, a) < 1e-4
 
 
 def test_bn_eval_mode(G):
