@@ -693,19 +693,20 @@ __global__ void im2col_k4s2_c8_kernel(const uint4* __restrict__ img, uint4* __re
 }
 // img[n,iy,ix,c] = act(bias[c] + sum_{kh,kw} col[n,(iy+1-kh)/2,(ix+1-kw)/2, idx(kh,kw,c)]) over the taps whose
 // source index is integral and inside the col grid.  order 0: idx = (kh*4+kw)*8+c, order 1: idx = c*16+kh*4+kw.
+// idx_t = unsigned when N*H*W < 2^31 (always, in practice): the three divisions per pixel are then 32-bit.
+template <typename idx_t>
 __global__ void col2im_k4s2_c8_kernel(const bf16* __restrict__ col, int Ccol, int order, int C,
                                       const float* __restrict__ bias, int act, uint4* __restrict__ img, int N, int H,
                                       int W) {
   pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
   pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2;
-  const long long total = (long long)N * H * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ix = (int)(i % W);
-    long long t = i / W;
-    const int iy = (int)(t % H);
-    const long long n = t / H;
+  const idx_t total = (idx_t)N * (idx_t)H * (idx_t)W;
+  for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (idx_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % (idx_t)W);
+    idx_t t = i / (idx_t)W;
+    const int iy = (int)(t % (idx_t)H);
+    const long long n = (long long)(t / (idx_t)H);
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = (bias != nullptr && c < C) ? bias[c] : 0.f;
@@ -1293,8 +1294,12 @@ extern "C" int gcc_col2im_k4s2_c8(const void* col, int Ccol, int order, int C, c
     gcc_set_error(__FILE__, __LINE__, "col2im: bad arguments");
     return GCC_ERR_ARG;
   }
-  gcc_launch(col2im_k4s2_c8_kernel, blocks_for((long long)N * H * W), 256, 0, (cudaStream_t)stream, 
-      (const bf16*)col, Ccol, order, C, bias, act, (uint4*)img, N, H, W);
+  if ((long long)N * H * W < (1LL << 31) - (1LL << 24))   // (headroom for the grid-stride increment)
+    gcc_launch(col2im_k4s2_c8_kernel<unsigned>, blocks_for((long long)N * H * W), 256, 0, (cudaStream_t)stream,
+               (const bf16*)col, Ccol, order, C, bias, act, (uint4*)img, N, H, W);
+  else
+    gcc_launch(col2im_k4s2_c8_kernel<long long>, blocks_for((long long)N * H * W), 256, 0, (cudaStream_t)stream,
+               (const bf16*)col, Ccol, order, C, bias, act, (uint4*)img, N, H, W);
   GCC_CHECK_LAUNCH();
   return GCC_OK;
 }
