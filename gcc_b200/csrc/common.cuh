@@ -312,26 +312,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }  // namespace gcc
 
 // ------------------------------------------------------ host: internal entry points shared between translation units
-// Fused norm-backward reduction (gcc_conv_gemm_bnred_bf16): the conv's output IS the gradient dy of a norm block whose
-// pre-norm activation `x` has the output's layout; see conv_gemm.cu.
-struct GccBnRed {
-  const void* x;        // bf16 [N][OH][OW][Cy]
-  const float* sums;    // fp32 [2][Cy] (sum x, sum x^2) or NULL (identity norm)
-  float inv_count;      // 1 / pixels behind `sums`
-  const float *gamma, *beta, *alpha;  // may be NULL
-  float thr, eps;
-  int act;              // norm.cu coding: 0 none, 1 leaky-relu, 2 relu
-  float slope;
-  int gate_after;
-  int C;                // logical channels
-  float* red;           // fp32 [2][Cy], pre-zeroed: += sum dg, += sum dg * xhat   (gate_after: += sum dy * act(z))
-  int* fused;           // host int: 1 when the launch took the fused epilogue
-};
 int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                          const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH, int KW,
                          int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
-                         long long ws_elems, float* stats, int stats_ld, int f32_out, int rowwin, void* stream,
-                         const GccBnRed* bnred = nullptr);
+                         long long ws_elems, float* stats, int stats_ld, int f32_out, int rowwin, void* stream);
 extern "C" int gcc_wgrad_gemm_bf16(const void* p, int N, int OH, int OW, int Cp, const void* q, int H, int W, int Cq,
                                    float* dw, int R, int C, int KH, int KW, int stride, int pad, int batched,
                                    int accumulate, float scale, void* stream);

@@ -307,16 +307,6 @@ struct ConvGeom2 {
   // writes the bf16 output.  tail_begin == total_tiles: no tail.
   int tail_begin, tail_splits;
   float* tail_ws;
-  // Fused norm-backward reduction (GccBnRed, common.cuh): this conv's output is the gradient dy of a norm block
-  // [BatchNorm | identity] -> [gate] -> activation whose pre-norm activation nx has the output's layout.  The staged
-  // epilogue re-computes g = nx * cg + cb per element, dg = dy * act'(g), and accumulates per output channel
-  // sum dg and sum dg * nx (gate_after: sum dy * act(g)) -- the two sums gcc_norm_bwd_bf16's reduce pass would read dy
-  // and nx a second time for (4 B / element, one launch per norm block and backward pass).
-  const bf16* nx;
-  const float *nsums, *ngamma, *nbeta, *nalpha;
-  float ninv_count, nthr, neps, nslope;
-  int nact, ngate_after, nC;
-  float* nred;
 };
 
 struct TileInfo {
@@ -361,32 +351,6 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvGeom2& p, int tile_id)
   return t;
 }
 
-// norm-block activation (norm.cu coding: 1 leaky-relu, 2 relu) for the fused backward reduction
-__device__ __forceinline__ float nact_fwd(float g, int act, float slope) {
-  if (act == 1) return g > 0.f ? g : g * slope;
-  if (act == 2) return g > 0.f ? g : 0.f;
-  return g;
-}
-__device__ __forceinline__ float nact_grad(float g, int act, float slope) {
-  if (act == 1) return g > 0.f ? 1.f : slope;
-  if (act == 2) return g > 0.f ? 1.f : 0.f;
-  return 1.f;
-}
-// v[j] of the 32 lanes -> lane j returns sum over lanes of v[j]  (recursive halving: 16 + 8 + 4 + 2 + 1 shuffles)
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? v[i] : v[i + off];
-      const float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
 // kC8 = image mode (ConvGeom2::c8) as a compile-time switch: the producer / MMA loops are single-thread instruction
 // streams (~500 cycles per k-block before the clean-up below, measured with the pipeline stages switched off:
 // profiles/r02_conv_pipeline_bound.txt), which is what bounded every BLOCK_N <= 128 layer, so nothing that can be
@@ -418,9 +382,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   constexpr int kStagePitch = 80;  // 64 B of data + 16 B pad per staged row (spreads banks)
   uint8_t* stage_base = out_base + kOutBytes + 256;                    // 8 warps x 32 rows x 80 B
   float* bias_base = reinterpret_cast<float*>(stage_base + 8 * 32 * kStagePitch);  // 8 warps x 32 floats
-  float* sstat = bias_base + 8 * 32;   // [2][BLOCK_N] BN statistics (fprop) / backward-reduction sums (p.nred)
-  float* scoef = sstat + 2 * BLOCK_N;  // [4][BLOCK_N] p.nred: cg, cb, rstd, mean of the current column block
-  if (p.stats != nullptr || p.nred != nullptr)
+  float* sstat = bias_base + 8 * 32;                                                // [2][BLOCK_N] BN statistics
+  if (p.stats != nullptr)
     for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sstat[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
@@ -559,66 +522,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
-    // fused norm-backward reduction: per column block, the coefficients g = x * cg + cb of the norm block (the same fp32
-    // formulas as norm.cu's channel_affine) are loaded once; the partial sums are flushed like the statistics
-    auto load_coefs = [&](int nt) {
-      for (int i = et; i < BLOCK_N; i += 256) {
-        const int c = nt * BLOCK_N + i;
-        float mean = 0.f, rstd = 1.f, cg = 0.f, cb = 0.f;
-        if (c < p.nC) {
-          if (p.nsums != nullptr) {
-            mean = p.nsums[c] * p.ninv_count;
-            const float var = fmaxf(p.nsums[p.out_cols + c] * p.ninv_count - mean * mean, 0.f);
-            rstd = rsqrtf(var + p.neps);
-          }
-          const float gam = p.ngamma != nullptr ? p.ngamma[c] : 1.f;
-          const float bet = p.nbeta != nullptr ? p.nbeta[c] : 0.f;
-          float mask = 1.f;
-          if (p.nalpha != nullptr && !p.ngate_after) {
-            const float d = p.nalpha[c] - p.nthr;
-            mask = ((d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) + 1.f) * 0.5f;
-          }
-          cg = rstd * gam * mask;
-          cb = (bet - mean * rstd * gam) * mask;
-        } else {
-          mean = 0.f;
-          rstd = 0.f;
-        }
-        scoef[i] = cg;
-        scoef[BLOCK_N + i] = cb;
-        scoef[2 * BLOCK_N + i] = rstd;
-        scoef[3 * BLOCK_N + i] = mean;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    };
-    auto flush_red = [&](int nt) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = et; i < BLOCK_N; i += 256) {
-        const int c = nt * BLOCK_N + i;
-        const float s1 = sstat[i];
-        float s2 = sstat[BLOCK_N + i];
-        // sum dg * xhat = rstd * (sum dg * x - mean * sum dg): linear, so every CTA converts its own partial sums
-        if (!p.ngate_after) s2 = scoef[2 * BLOCK_N + i] * (s2 - scoef[3 * BLOCK_N + i] * s1);
-        if (c < p.out_cols) {
-          atomicAdd(p.nred + c, s1);
-          atomicAdd(p.nred + p.out_cols + c, s2);
-        }
-        sstat[i] = 0.f;
-        sstat[BLOCK_N + i] = 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    };
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(p, tile);
       if (t.kb1 <= t.kb0) continue;
       if (p.stats != nullptr && t.n_tile != cur_nt) {
         if (cur_nt >= 0) flush_stats(cur_nt);
         cur_nt = t.n_tile;
-      }
-      if (p.nred != nullptr && t.n_tile != cur_nt) {
-        if (cur_nt >= 0) flush_red(cur_nt);
-        cur_nt = t.n_tile;
-        load_coefs(cur_nt);
       }
       const int b = t.b0 + (r & wt_mask);
       const int a = t.a0 + ((r >> p.log_wt) & ht_mask);
@@ -780,35 +689,6 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
               }
             }
           }
-          if (p.nred != nullptr) {
-            // fused norm-backward reduction on this thread's row: dy = the bf16 values just stored (read back from
-            // the thread's own staged row), x = the norm block's pre-norm activation at the same address offset
-            const bf16* xrow = p.nx + (orow - p.out) + col0;
-            float d1[32], d2[32];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const bool ok = valid && (col0 + g * 8 < p.out_cols);
-              const uint4 du = srow[g];
-              const uint4 xu = ok ? __ldg(reinterpret_cast<const uint4*>(xrow + g * 8)) : make_uint4(0, 0, 0, 0);
-              const uint32_t dw[4] = {du.x, du.y, du.z, du.w}, xw[4] = {xu.x, xu.y, xu.z, xu.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float dyv = (i & 1) ? bf16_hi(dw[i >> 1]) : bf16_lo(dw[i >> 1]);
-                const float xv = (i & 1) ? bf16_hi(xw[i >> 1]) : bf16_lo(xw[i >> 1]);
-                const int cc = c0 + g * 8 + i;
-                const float gg = xv * scoef[cc] + scoef[BLOCK_N + cc];
-                const float dg = ok ? dyv * nact_grad(gg, p.nact, p.nslope) : 0.f;
-                d1[g * 8 + i] = dg;
-                d2[g * 8 + i] = p.ngate_after ? (ok ? dyv * nact_fwd(gg, p.nact, p.nslope) : 0.f) : dg * xv;
-              }
-            }
-            const float s1 = warp_transpose_sum(d1, lane);
-            const float s2 = warp_transpose_sum(d2, lane);
-            if (col0 + lane < p.out_cols) {
-              atomicAdd(&sstat[c0 + lane], s1);
-              atomicAdd(&sstat[BLOCK_N + c0 + lane], s2);
-            }
-          }
           __syncwarp();
         }
       } else {
@@ -838,7 +718,6 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.stats != nullptr && cur_nt >= 0) flush_stats(cur_nt);
-    if (p.nred != nullptr && cur_nt >= 0) flush_red(cur_nt);
     if (kTmaStore && et == 0) tma_store_wait_all();
   }
   tc_fence_before();
@@ -1076,7 +955,7 @@ static int num_sms() {
 template <int BLOCK_N, int STAGES, bool TS, bool C8>
 static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
   const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + (TS ? 2 * (BLOCK_N / 64) * 16384 : 0) + 1024 + 256 +
-                   8 * 32 * 80 + 8 * 32 * 4 + 6 * BLOCK_N * 4;
+                   8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
   static bool configured[kMaxDevices] = {};
   const int dev = cur_device();
   if (!configured[dev]) {
@@ -1100,10 +979,8 @@ static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
 int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
                          const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH, int KW,
                          int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
-                         long long ws_elems, float* stats, int stats_ld, int f32_out, int rowwin, void* stream,
-                         const GccBnRed* bnred) {
+                         long long ws_elems, float* stats, int stats_ld, int f32_out, int rowwin, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (bnred != nullptr && bnred->fused != nullptr) *bnred->fused = 0;
   // rowwin = 1: x is a pre-padded 8-channel image [N][H][W][8] followed by >= 128 readable bytes, w = [R][KH * KB][64]
   // with KB = ceil(KW / 8) (gcc_rowwin_weight_pack_bf16), T = KH * KB, Cw = 64, stride 1, pad 0.
   if (rowwin && (transposed || w_per_image || Cx != 8 || Cw != 64 || stride != 1 || pad != 0 || T != KH * ((KW + 7) / 8) ||
@@ -1305,37 +1182,15 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
   g.total_tiles = base_tiles * g.k_splits;
   g.tail_begin = g.total_tiles;
   g.tail_splits = 1;
-  // Fused norm-backward reduction: only the staged bf16 epilogue (BLOCK_N = 256, or 128 with a long K loop) of a launch
-  // that owns whole output rows computes it; anything else reports *fused = 0 and the caller runs the reduce pass.
-  bool fuse_red = false;
-  if (bnred != nullptr && bnred->red != nullptr && bnred->x != nullptr && stats == nullptr && !f32_out && !c8 &&
-      g.k_splits == 1 && y_coff == 0 && Rp == Cy && (BN == 256 || (BN == 128 && max_kb > 8))) {
-    fuse_red = true;
-    g.nx = reinterpret_cast<const bf16*>(bnred->x);
-    g.nsums = bnred->sums;
-    g.ngamma = bnred->gamma;
-    g.nbeta = bnred->beta;
-    g.nalpha = bnred->alpha;
-    g.ninv_count = bnred->inv_count;
-    g.nthr = bnred->thr;
-    g.neps = bnred->eps;
-    g.nslope = bnred->slope;
-    g.nact = bnred->act;
-    g.ngate_after = bnred->gate_after;
-    g.nC = bnred->C;
-    g.nred = bnred->red;
-    if (bnred->fused != nullptr) *bnred->fused = 1;
-  }
   // Tail-wave split (ConvGeom2::tail_begin): few waves, a last wave that is at most half full and a LONG K loop.
-  // Measured after the issue-loop clean-up (profiles/r02_conv_pipeline_bound.txt, second table): 1024 -> 512 k4 s1 data
+  // Measured after the issue-loop clean-up (profiles/r02_conv_pipeline_bound.txt, last table): 1024 -> 512 k4 s1 data
   // gradient (256 k-blocks) 367 -> 351 us including the finalize kernel; with 64 / 32 k-blocks per tile (256 -> 512 and
   // 128 -> 512 k4 s2 forward) the split loses 5-8 us, so it is taken from 128 k-blocks per tile on.
   // GCC_B200_TAIL_SPLIT=0 / debug bit 11 switch it off, GCC_B200_TAIL_MIN_KB moves the threshold (A/B measurements).
   static const int tail_on = getenv("GCC_B200_TAIL_SPLIT") ? atoi(getenv("GCC_B200_TAIL_SPLIT")) : 1;
   static const int tail_min_kb_env = getenv("GCC_B200_TAIL_MIN_KB") ? atoi(getenv("GCC_B200_TAIL_MIN_KB")) : 128;
   const int tail_min_kb = g_tail_min_kb > 0 ? g_tail_min_kb : tail_min_kb_env;
-  if (tail_on && !fuse_red && !(g_debug_flags & 2048) && splitk_ws != nullptr && g.k_splits == 1 && !f32_out && !c8 &&
-      BN >= 128) {
+  if (tail_on && !(g_debug_flags & 2048) && splitk_ws != nullptr && g.k_splits == 1 && !f32_out && !c8 && BN >= 128) {
     const int S = num_sms();
     const int waves = base_tiles / S, rem = base_tiles % S;
     if (waves >= 1 && waves <= 8 && rem > 0 && rem * 2 <= S && min_kb >= 32 && min_kb >= tail_min_kb) {
@@ -1389,36 +1244,6 @@ extern "C" int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, co
                                   float* splitk_ws, long long ws_elems, float* stats, int stats_ld, void* stream) {
   return gcc_conv_gemm_launch(x, N, H, W, Cx, w, R, T, Cw, bias, y, OH, OW, Cy, y_coff, transposed, KH, KW, stride, pad,
                               act, slope, w_per_image, splitk_ws, ws_elems, stats, stats_ld, 0, 0, stream);
-}
-
-extern "C" int gcc_conv_gemm_bnred_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
-                                        const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed,
-                                        int KH, int KW, int stride, int pad, int act, float slope, int w_per_image,
-                                        float* splitk_ws, long long ws_elems, const void* nx, const float* nsums,
-                                        long long stat_count, const float* ngamma, const float* nbeta,
-                                        const float* nalpha, float thr, float eps, int nact, float nslope, int gate_after,
-                                        int nC, float* red, int* fused, void* stream) {
-  if (gate_after && nsums != nullptr) {
-    gcc_set_error(__FILE__, __LINE__, "conv gemm: gate_after is only defined for the identity norm");
-    return GCC_ERR_ARG;
-  }
-  GccBnRed br;
-  br.x = nx;
-  br.sums = nsums;
-  br.inv_count = stat_count > 0 ? 1.f / (float)stat_count : 1.f / (float)((long long)N * OH * OW);
-  br.gamma = ngamma;
-  br.beta = nbeta;
-  br.alpha = nalpha;
-  br.thr = thr;
-  br.eps = eps;
-  br.act = nact;
-  br.slope = nslope;
-  br.gate_after = gate_after;
-  br.C = nC;
-  br.red = red;
-  br.fused = fused;
-  return gcc_conv_gemm_launch(x, N, H, W, Cx, w, R, T, Cw, bias, y, OH, OW, Cy, y_coff, transposed, KH, KW, stride, pad,
-                              act, slope, w_per_image, splitk_ws, ws_elems, nullptr, 0, 0, 0, stream, &br);
 }
 
 extern "C" int gcc_conv_rowwin_bf16(const void* x, int N, int Hrows, int Wp, const void* w_rowpack, int R, int KH, int KW,
@@ -1518,14 +1343,23 @@ static int gcc_wgrad_gemm_launch(const void* pmat, int N, int OH, int OW, int Cp
     const double t_kb = 2.0 * BN * MT * 1.4;             // MMA cycles per 64-pixel block (x1.4: L2-bound operands)
     const double t_epi = 40.0 * BN * MT + 6000.0;        // atomics epilogue + prologue
     const int slots = kNumSMs * ((BN <= 128 && MT == 1) ? 2 : 1);
+    // every integer factor is a candidate (16 base CTAs x 9 = 144 fills the 148 SMs where 16 x 8 = 128 leaves 20
+    // idle); among the factors within 3 % of the cheapest the smallest wins (fewer atomic epilogues)
+    const int sp_max = c8 ? 256 : 64;
     double best = 1e30;
-    for (int sp = 1; sp <= (c8 ? 256 : 64); sp *= 2) {
+    auto cost_of = [&](int sp) {
       const int kb = (total_pb + sp - 1) / sp;
-      if (sp > 1 && kb < 8) break;
       const long long ctas = (long long)base_ctas * sp;
       const double waves = (double)((ctas + slots - 1) / slots);
-      const double cost = waves * (kb * t_kb + t_epi);
-      if (cost < best * 0.97) { best = cost; splits = sp; }
+      return waves * (kb * t_kb + t_epi);
+    };
+    for (int sp = 1; sp <= sp_max; ++sp) {
+      if (sp > 1 && (total_pb + sp - 1) / sp < 8) break;
+      best = cost_of(sp) < best ? cost_of(sp) : best;
+    }
+    for (int sp = 1; sp <= sp_max; ++sp) {
+      if (sp > 1 && (total_pb + sp - 1) / sp < 8) break;
+      if (cost_of(sp) <= best * 1.03) { splits = sp; break; }
     }
   }
   g.splits = splits;

@@ -123,13 +123,7 @@ class NormLayer:
         self.alpha = self.gate_arena.params[self.gate_name + ".alpha"] if self.gate_name else None
 
     def __call__(self, x, act=ACT_NONE, act2=None, sums=None, y_into=None, y2_into=None):
-        out = ops.NormActFn.apply(x, self.gamma, self.beta, self.alpha, self, act, act2, sums, y_into, y2_into)
-        link = getattr(self, "_last_link", None)
-        if link is not None:          # (ops.NormBwdLink: the consumer conv may fold this block's backward reduction)
-            self._last_link = None
-            if torch.is_tensor(out):
-                out._gcc_bnlink = link
-        return out
+        return ops.NormActFn.apply(x, self.gamma, self.beta, self.alpha, self, act, act2, sums, y_into, y2_into)
 
 
 class _Net(nn.Module):

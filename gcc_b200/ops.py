@@ -6,9 +6,6 @@ owning ``ParamArena``'s flat gradient buffer (zeroed by ``arena.zero_grad()``), 
 parameter's ``requires_grad`` flag exactly like the reference's set_requires_grad toggles
 (models/Pix2Pix.py:574-590).
 """
-import ctypes
-import os
-
 import torch
 
 from . import _lib
@@ -131,51 +128,12 @@ def conv_out_hw(h, w, k, stride, pad, transposed, outpad=0):
     return (h - 1) * stride - 2 * pad + k + outpad, (w - 1) * stride - 2 * pad + k + outpad
 
 
-class NormBwdLink:
-    """Hand-off between a norm block and the convolution that consumes its output: the conv's data-gradient kernel
-    produces exactly the dy the block's backward needs, so its epilogue can accumulate the block's backward reduction
-    (gcc_conv_gemm_bnred_bf16) and the separate reduce pass over dy and x disappears.  ``NormActFn.forward`` creates the
-    link, ``NormLayer.__call__`` hangs it on the output tensor, ``ConvFn.forward`` picks it up, ``ConvFn.backward``
-    fills ``fused = (dx, version, red)`` and ``NormActFn.backward`` uses ``red`` only if the gradient it receives IS
-    that dx, untouched (another consumer of the block's output makes autograd hand over a sum instead)."""
-    __slots__ = ("x", "sums", "gamma", "beta", "alpha", "layer", "act", "stat_count", "gate_after", "fused")
-
-    def __init__(self, x, sums, gamma, beta, alpha, layer, act, stat_count, gate_after):
-        self.x, self.sums, self.gamma, self.beta, self.alpha = x, sums, gamma, beta, alpha
-        self.layer, self.act, self.stat_count, self.gate_after = layer, act, stat_count, gate_after
-        self.fused = None
-
-
-FUSE_NORM_BWD = os.environ.get("GCC_B200_FUSE_NORM_BWD", "1") != "0"
-
-
-def _dgrad_gemm(link, dx, args, st):
-    """Data-gradient GEMM writing ``dx``; ``args`` = the leading arguments of gcc_conv_gemm_bf16 up to ws_elems.  When
-    ``dx`` is the dy of a linked norm block, the block's backward reduction rides in the epilogue (NormBwdLink)."""
-    (x, n, h, w, cx, wgt, r, t, cw, bias, y, oh, ow, cy, ycoff, trans, kh, kw, stride, pad, act, slope, wpi, wsp,
-     wse) = args
-    if link is not None and FUSE_NORM_BWD and not GLOBAL_BATCH_SYNC and link.x.shape == dx.shape:
-        red = zero_pool.take(2 * dx.shape[3], dx.device)
-        flag = ctypes.c_int(0)
-        nl = link.layer
-        call("gcc_conv_gemm_bnred_bf16", x, n, h, w, cx, wgt, r, t, cw, bias, y, oh, ow, cy, ycoff, trans, kh, kw, stride,
-             pad, act, slope, wpi, wsp, wse, link.x.data_ptr(), None if link.sums is None else link.sums.data_ptr(),
-             link.stat_count, None if link.gamma is None else link.gamma.data_ptr(),
-             None if link.beta is None else link.beta.data_ptr(), None if link.alpha is None else link.alpha.data_ptr(),
-             nl.thr, BN_EPS, link.act, nl.slope, link.gate_after, nl.c, red.data_ptr(), ctypes.addressof(flag), st)
-        link.fused = (dx, dx._version, red) if flag.value else None
-    else:
-        call("gcc_conv_gemm_bf16", x, n, h, w, cx, wgt, r, t, cw, bias, y, oh, ow, cy, ycoff, trans, kh, kw, stride, pad,
-             act, slope, wpi, wsp, wse, None, 0, st)
-
-
 class ConvFn(torch.autograd.Function):
     """nn.Conv2d / nn.ConvTranspose2d (+ bias, + fused LeakyReLU/Tanh epilogue) on tcgen05."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, layer, act, slope, stats=None):
         _check(x)
-        ctx.bnlink = getattr(x, "_gcc_bnlink", None) if x.is_contiguous() else None
         x = x.contiguous()
         layer.arena.ensure_packed()
         n, h, w, cx = x.shape
@@ -219,12 +177,11 @@ class ConvFn(torch.autograd.Function):
             wp = pk.transposed if not tr else pk.direct  # [cin][T][cout_p]
             dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=x.device)
             wsp, wse, _keep = _splitk_ws(n, h, w, layer.cin, x.device)
+            call("gcc_conv_gemm_bf16", dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin, T, wp.shape[2], None,
+                 dx.data_ptr(), h, w, dx.shape[3], 0, 0 if tr else 1, layer.k, layer.k, layer.stride, layer.pad, 0,
+                 0.0, 0, wsp, wse, None, 0, st)
             if dx.shape[3] != cx:
                 raise _lib.GccB200Error("conv input channel padding mismatch")
-            # (if x came straight out of a norm block, dx is that block's dy: its backward reduction rides along)
-            _dgrad_gemm(ctx.bnlink, dx, (dpre.data_ptr(), n, oh, ow, cop, wp.data_ptr(), layer.cin, T, wp.shape[2], None,
-                                         dx.data_ptr(), h, w, dx.shape[3], 0, 0 if tr else 1, layer.k, layer.k,
-                                         layer.stride, layer.pad, 0, 0.0, 0, wsp, wse), st)
         if ctx.needs_input_grad[1]:
             gw = layer.arena.flat_grad[layer.wname]
             if not tr:  # dW[co][tap][ci] = sum dy[.., co] * x[gather, ci]
@@ -365,7 +322,6 @@ class HeadConvFn(torch.autograd.Function):
         _check(x)
         if act != ACT_NONE:
             raise _lib.GccB200Error("head conv has no fused activation")
-        ctx.bnlink = getattr(x, "_gcc_bnlink", None) if x.is_contiguous() else None
         x = x.contiguous()
         layer.arena.ensure_packed()
         st = _st()
@@ -399,8 +355,8 @@ class HeadConvFn(torch.autograd.Function):
             layer.arena.ensure_packed()
             wp = layer.packs.transposed  # [cin][16][8] viewed as [cin][1][128]
             dx = torch.empty(n, h, w, rp8(layer.cin), dtype=torch.bfloat16, device=dev)
-            _dgrad_gemm(ctx.bnlink, dx, (dcol.data_ptr(), n, h, w, 128, wp.data_ptr(), layer.cin, 1, 128, None,
-                                         dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0), st)
+            call("gcc_conv_gemm_bf16", dcol.data_ptr(), n, h, w, 128, wp.data_ptr(), layer.cin, 1, 128, None,
+                 dx.data_ptr(), h, w, dx.shape[3], 0, 0, 1, 1, 1, 0, 0, 0.0, 0, None, 0, None, 0, st)
         if ctx.needs_input_grad[1]:
             tmp = torch.empty(128, layer.cin, dtype=torch.float32, device=dev)
             call("gcc_wgrad_gemm_bf16", dcol.data_ptr(), n, h, w, 128, x.data_ptr(), h, w, cx, tmp.data_ptr(), 128,
@@ -682,15 +638,6 @@ class NormActFn(torch.autograd.Function):
         ctx.layer, ctx.act, ctx.act2 = layer, act, act2
         ctx.save_for_backward(x, sums, gamma, beta, alpha)
         ctx.set_materialize_grads(False)
-        # plain single-output batch-norm / identity blocks in training mode can take their backward reduction from the
-        # consumer's data-gradient kernel (NormBwdLink)
-        ctx.link = None
-        layer._last_link = None
-        if (FUSE_NORM_BWD and y2ret is None and y_into is None and not ctx.eval_bn and mode in ("bn", "id")
-                and (mode == "bn" or alpha is not None) and any(ctx.needs_input_grad)):
-            ga = 1 if (getattr(layer, "gate_after", mode == "id") and mode == "id" and alpha is not None) else 0
-            if mode == "bn" or ga:
-                ctx.link = layer._last_link = NormBwdLink(x, sums, gamma, beta, alpha, layer, act, ctx.stat_count, ga)
         if y2ret is None:
             return yret
         return yret, y2ret
@@ -717,14 +664,7 @@ class NormActFn(torch.autograd.Function):
         dbeta = arena_of(beta) if (beta is not None and ctx.needs_input_grad[2]) else None
         dalpha = arena_of(alpha) if (alpha is not None and ctx.needs_input_grad[3]) else None
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        fused, link = None, getattr(ctx, "link", None)
-        if link is not None:
-            fused, link.fused = link.fused, None
-            if fused is not None and not (dy2 is None and dy is not None and dy.data_ptr() == fused[0].data_ptr()
-                                          and dy.shape == fused[0].shape and dy._version == fused[1]
-                                          and dy.is_contiguous()):
-                fused = None      # the gradient is not the consumer conv's dx alone (a second consumer, a copy ...)
-        red = fused[2] if fused is not None else zero_pool.take((n if per_sample else 1) * 2 * cp, x.device)
+        red = zero_pool.take((n if per_sample else 1) * 2 * cp, x.device)   # pre-zeroed: phase | 4 below
         gate_after = 1 if (getattr(layer, "gate_after", layer.mode == "id") and layer.mode == "id" and alpha is not None) else 0
 
         def bwd(phase, red_param):
@@ -741,8 +681,6 @@ class NormActFn(torch.autograd.Function):
             red_local = red.clone()
             _allreduce_sum(red)
             bwd(2, red_local)
-        elif fused is not None:
-            bwd(2, None)          # the reduction came out of the consumer conv's data-gradient epilogue
         else:
             bwd(0, None)
         return dx, None, None, None, None, None, None, None, None, None

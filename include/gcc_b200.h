@@ -51,21 +51,6 @@ int gcc_conv_gemm_bf16(const void* x, int N, int H, int W, int Cx, const void* w
                        const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
                        int KW, int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
                        long long ws_elems, float* stats, int stats_ld, void* stream);
-/* gcc_conv_gemm_bf16 whose OUTPUT y is the gradient dy entering the backward of a norm block
- * [BatchNorm2d | identity] -> [DifferentiableOP gate] -> (Leaky)ReLU (models/Pix2Pix.py:284-300,320-341): the epilogue
- * also accumulates the two per-channel sums that gcc_norm_bwd_bf16's reduction pass computes (red[0][c] += sum dg,
- * red[1][c] += sum dg*xhat; gate_after: sum dy*act(z)), so that pass -- a second read of dy and of the pre-norm
- * activation, one launch per norm block and backward pass -- disappears: the caller then runs gcc_norm_bwd_bf16 with
- * phase 2 | 4.  nx: the block's pre-norm activation, bf16 [N,OH,OW,Cy] (the layout of y); nsums / ngamma / nbeta / nalpha /
- * thr / eps / nact / nslope / gate_after / nC / stat_count as in gcc_norm_bwd_bf16; red: PRE-ZEROED fp32 [2][Cy].
- * *fused (host int) = 1 when the launch computed the sums, 0 when this shape runs a kernel variant without the fused
- * epilogue (short K, <= 64 output channels, split-K): y is complete either way, red is then untouched. */
-int gcc_conv_gemm_bnred_bf16(const void* x, int N, int H, int W, int Cx, const void* w, int R, int T, int Cw,
-                             const float* bias, void* y, int OH, int OW, int Cy, int y_coff, int transposed, int KH,
-                             int KW, int stride, int pad, int act, float slope, int w_per_image, float* splitk_ws,
-                             long long ws_elems, const void* nx, const float* nsums, long long stat_count,
-                             const float* ngamma, const float* nbeta, const float* nalpha, float thr, float eps, int nact,
-                             float nslope, int gate_after, int nC, float* red, int* fused, void* stream);
 /* gcc_wgrad_gemm_bf16: dw[b][r][kh*KW+kw][c] (+)= scale * sum_{n,oy,ox} p[n,oy,ox,r] * q[n,stride*oy+kh-pad,stride*ox+kw-pad,c]
  *   weight gradient of Conv2d (p = dy, q = x) and ConvTranspose2d (p = x, q = dy); with batched=1,
  *   KH=KW=1, p == q it is the per-sample Gram matrix f f^T (models/Pix2Pix.py:733-740).

@@ -1,7 +1,6 @@
 """A/B harness on the c2 bench workload in ONE process: the model is built once, every variant re-captures the
 iteration as a CUDA graph with its switches set (they are read on the host at launch = capture time) and times N replays.
-Variants: tail-wave split of the conv kernel (debug bit 11 = off), norm-backward reduction fused into the data-gradient
-kernels (ops.FUSE_NORM_BWD).  Usage: python scripts/exp_ab_c2.py [config] [replays]"""
+Variants: tail-wave split of the conv kernel (debug bit 11 = off).  Usage: python scripts/exp_ab_c2.py [config] [replays]"""
 import os
 import sys
 
@@ -9,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import bench
-from gcc_b200 import _lib, factory, ops
+from gcc_b200 import _lib, factory
 from gcc_b200.graph import GraphedIteration
 
 config = sys.argv[1] if len(sys.argv) > 1 else "c2"
@@ -30,13 +29,9 @@ for i in range(2):
     factory.run_iteration(model, devb[i][0], devb[i][1])
 torch.cuda.synchronize()
 
-VARIANTS = [("default: fused norm-backward reduction + tail split", 0, True),
-            ("without the fused reduction", 0, False),
-            ("without the tail split", 2048, True),
-            ("default again", 0, True)]
-for name, flags, fuse in VARIANTS:
+VARIANTS = [("baseline (no tail split)", 2048), ("tail split", 0), ("baseline again", 2048), ("tail split again", 0)]
+for name, flags in VARIANTS:
     L.gcc_debug_set_flags(flags)
-    ops.FUSE_NORM_BWD = fuse
     graphed = GraphedIteration(model).capture(devb[0][0], devb[0][1], warmup=1)
     for i in range(3):
         graphed.run(devb[i % 2][0], devb[i % 2][1])
@@ -53,4 +48,3 @@ for name, flags, fuse in VARIANTS:
     del graphed
     torch.cuda.empty_cache()
 L.gcc_debug_set_flags(0)
-ops.FUSE_NORM_BWD = True

@@ -256,69 +256,6 @@ def test_norm_block_fwd_bwd(G, mode, gated, act, dual, C):
         assert bool((y.detach()[..., C:] == 0).all())
 
 
-# conv1 -> norm block -> conv2: conv2's data-gradient kernel produces the block's dy, so its epilogue can carry the
-# block's backward reduction (gcc_conv_gemm_bnred_bf16, ops.NormBwdLink).
-#            C1,  mode, gated, conv2 = (cout, k, stride, pad)
-FUSE_CASES = [(256, "bn", False, (64, 3, 1, 1)),     # BLOCK_N 256, stride-1 data gradient
-              (256, "bn", True, (128, 4, 2, 1)),     # four sub-pixel classes, gate folded into the norm
-              (128, "bn", False, (64, 4, 1, 1)),     # BLOCK_N 128 with a long K loop
-              (128, "id", True, (64, 4, 1, 1)),      # conv -> LeakyReLU -> gate (gate_after): dalpha = sum dy * act(z)
-              (256, "bn", False, (1, 4, 1, 1)),      # PatchGAN logits head (HeadConvFn: 1x1 GEMM data gradient)
-              (40, "bn", False, (64, 3, 1, 1))]      # <= 64 channels: TMA-store kernel, no fused epilogue -> fallback
-
-
-@pytest.mark.parametrize("case", FUSE_CASES)
-def test_norm_bwd_reduction_fused_into_dgrad(G, case):
-    C1, mode, gated, (C2, k2, s2, p2) = case
-    N, H, W = 8, 96, 96
-    res = {}
-    for fuse in (True, False):
-        A, GA = G.arena.ParamArena("cuda"), G.arena.ParamArena("cuda")
-        conv1 = G.nets.ConvLayer(A, "c1", "conv", 32, C1, 4, 2, 1, bias=False)
-        norm = G.nets.NormLayer(A, "n", C1, mode, "cuda", GA if gated else None, "g" if gated else None, 0.5)
-        conv2 = G.nets.ConvLayer(A, "c2", "conv", C1, C2, k2, s2, p2, bias=False)
-        A.finalize()
-        GA.finalize()
-        for l in (conv1, norm, conv2):
-            l.bind()
-        with torch.no_grad():
-            conv1.weight.copy_(rnd((C1, 32, 4, 4), 1, 0.05))
-            conv2.weight.copy_(rnd((C2, C1, k2, k2), 2, 0.05))
-            if mode == "bn":
-                norm.gamma.copy_(rnd((C1,), 3, 0.3) + 1.0)
-                norm.beta.copy_(rnd((C1,), 4, 0.5))
-            if gated:
-                norm.alpha.copy_(torch.tensor(([0.7, 0.5, 0.2, 1.0] * C1)[:C1], device="cuda"))
-        A.mark_dirty()
-        A.ensure_packed()
-        xh = nhwc(rnd((N, 32, H, W), 5), G).requires_grad_(True)
-        G.ops.FUSE_NORM_BWD = fuse
-        try:
-            h1 = conv1(xh)
-            h2 = norm(h1, 1)
-            out = conv2(h2)
-            gy = nhwc(rnd((N, C2, out.shape[1], out.shape[2]), 6), G)
-            A.zero_grad()
-            GA.zero_grad()
-            l0 = G.lib.lib().gcc_launch_count()
-            out.backward(gy)
-            torch.cuda.synchronize()
-            launches = G.lib.lib().gcc_launch_count() - l0
-        finally:
-            G.ops.FUSE_NORM_BWD = True
-        grads = [conv1.weight.grad.clone(), conv2.weight.grad.clone()]
-        if mode == "bn":
-            grads += [norm.gamma.grad.clone(), norm.beta.grad.clone()]
-        if gated:
-            grads.append(norm.alpha.grad.clone())
-        res[fuse] = (xh.grad.clone(), grads, launches)
-    fused_expected = C1 > 64
-    assert res[True][2] == res[False][2] - (1 if fused_expected else 0), (res[True][2], res[False][2])
-    assert rel_err(res[True][0].float(), res[False][0].float()) < 2e-3
-    for a, b in zip(res[True][1], res[False][1]):
-        assert rel_err(a, b) < 1e-3
-
-
 def test_bn_eval_mode(G):
     C = 24
     A = G.arena.ParamArena("cuda")
