@@ -383,6 +383,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   uint8_t* stage_base = out_base + kOutBytes + 256;                    // 8 warps x 32 rows x 80 B
   float* bias_base = reinterpret_cast<float*>(stage_base + 8 * 32 * kStagePitch);  // 8 warps x 32 floats
   float* sstat = bias_base + 8 * 32;                                                // [2][BLOCK_N] BN statistics
+  // biases of the current block of output columns: loaded ONCE per column-block change by the epilogue threads (the
+  // per-chunk __ldg they replace put an L2 round trip on the critical path of every 32-column chunk of every tile of
+  // the short-K, store-bound layers); zeros when the conv has no bias
+  float* tbias = sstat + 2 * BLOCK_N;                                               // [BLOCK_N]
+  for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) tbias[i] = 0.f;
   if (p.stats != nullptr)
     for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sstat[i] = 0.f;
 
@@ -508,7 +513,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
     const int wt_mask = (1 << p.log_wt) - 1, ht_mask = (1 << p.log_ht) - 1;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int cur_nt = -1;
+    int cur_nt = -1, bias_nt = -1;
     int tile_iter = 0;
     const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
     // per-CTA statistics live in smem and are flushed (one global atomic per channel) when the CTA moves on to
@@ -528,6 +533,15 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
       if (p.stats != nullptr && t.n_tile != cur_nt) {
         if (cur_nt >= 0) flush_stats(cur_nt);
         cur_nt = t.n_tile;
+      }
+      if (p.bias != nullptr && t.n_tile != bias_nt) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // every epilogue thread is done with the previous block's biases
+        for (int i = et; i < BLOCK_N; i += 256) {
+          const int c = t.n_tile * BLOCK_N + i;
+          tbias[i] = c < p.bias_cols ? __ldg(p.bias + c) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        bias_nt = t.n_tile;
       }
       const int b = t.b0 + (r & wt_mask);
       const int a = t.a0 + ((r >> p.log_wt) & ht_mask);
@@ -565,15 +579,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
         if (et == 0) tma_store_wait_read<1>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        float* sbias = bias_base + (warp - 2) * 32;
 #pragma unroll 1
         for (int c0 = half * kHalf; c0 < (half + 1) * kHalf; c0 += 32) {
           const int col0 = t.n_tile * BLOCK_N + c0;
           if (col0 >= p.out_cols) break;  // warp-uniform
           uint32_t v[32];
           tmem_ld_32x32(tmem_d + c0, v);
-          const float bl = (p.bias != nullptr && col0 + lane < p.bias_cols) ? __ldg(p.bias + col0 + lane) : 0.f;
-          sbias[lane] = bl;
           tmem_ld_wait();
           __syncwarp();
           // row r of unit (c0 / 64): 128 B, 16-byte chunks XOR-swizzled with (r & 7) (= CU_TENSOR_MAP_SWIZZLE_128B)
@@ -584,7 +595,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              f[i] = apply_act(__uint_as_float(v[g * 8 + i]) + sbias[g * 8 + i], p.act, p.slope);
+              f[i] = apply_act(__uint_as_float(v[g * 8 + i]) + tbias[c0 + g * 8 + i], p.act, p.slope);
             *reinterpret_cast<uint4*>(urow + (((ch0 + g) ^ (r & 7)) << 4)) =
                 make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
           }
@@ -634,7 +645,6 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
         const unsigned long long orow_u = reinterpret_cast<unsigned long long>(orow);
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         uint8_t* stage = stage_base + (warp - 2) * (32 * kStagePitch);
-        float* sbias = bias_base + (warp - 2) * 32;
 #pragma unroll 1
         for (int c0 = half * kHalf; c0 < (half + 1) * kHalf; c0 += 32) {
           const int col0 = t.n_tile * BLOCK_N + c0;
@@ -646,8 +656,6 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0;
           }
-          const float bl = (p.bias != nullptr && col0 + lane < p.bias_cols) ? __ldg(p.bias + col0 + lane) : 0.f;
-          sbias[lane] = bl;
           if (!(p.debug & 2)) tmem_ld_wait();
           __syncwarp();
           uint4* srow = reinterpret_cast<uint4*>(stage + lane * kStagePitch);
@@ -656,7 +664,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              f[i] = apply_act(__uint_as_float(v[g * 8 + i]) + sbias[g * 8 + i], p.act, p.slope);
+              f[i] = apply_act(__uint_as_float(v[g * 8 + i]) + tbias[c0 + g * 8 + i], p.act, p.slope);
             srow[g] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
                                  pack_bf16(f[6], f[7]));
           }
@@ -955,7 +963,7 @@ static int num_sms() {
 template <int BLOCK_N, int STAGES, bool TS, bool C8>
 static int launch_conv_persistent(const ConvGeom2& g, cudaStream_t st) {
   const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + (TS ? 2 * (BLOCK_N / 64) * 16384 : 0) + 1024 + 256 +
-                   8 * 32 * 80 + 8 * 32 * 4 + 2 * BLOCK_N * 4;
+                   8 * 32 * 80 + 8 * 32 * 4 + 3 * BLOCK_N * 4;
   static bool configured[kMaxDevices] = {};
   const int dev = cur_device();
   if (!configured[dev]) {

@@ -20,9 +20,20 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16* __restr
   pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
   pdl_launch_dependents();
   const long long total = (long long)N * HW;
+  // the <= 8-channel images of the step (one 16-byte pixel): the whole pixel is assembled in registers and written with
+  // ONE vector store (the general path below writes eight 2-byte values per pixel)
+  const bool pixel8 = (Cp == 8 && c_off == 0 && zero_to == 8 && C <= 8);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / HW, p = i % HW;
+    if (pixel8) {
+      float v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = c < C ? src[(n * C + c) * HW + p] : 0.f;
+      *reinterpret_cast<uint4*>(dst + i * 8) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      continue;
+    }
     bf16* d = dst + i * Cp;
     for (int c = 0; c < C; ++c) d[c_off + c] = __float2bfloat16(src[(n * C + c) * HW + p]);
     for (int c = c_off + C; c < zero_to; ++c) d[c] = __float2bfloat16(0.f);
