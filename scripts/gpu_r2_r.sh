@@ -23,6 +23,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm
 tail -1 gpurun_out/ncu_full.log; ls -la gpurun_out/*.ncu-rep
 timeout 200 python bench.py --trace 1 --graph 0 > /dev/null 2> gpurun_out/trace_c2.err
 python scripts/summarize_trace.py gpurun_out/trace_c2.err > gpurun_out/gemm_trace_c2.txt 2>&1; head -8 gpurun_out/gemm_trace_c2.txt | cut -c1-150
+timeout 200 python scripts/exp_ab_c2.py c2 15 > gpurun_out/ab_c2.txt 2>&1; cat gpurun_out/ab_c2.txt | cut -c1-150
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -1 gpurun_out/bench_reference.json | cut -c1-300
 for cfg in c2_pruned c2_resnet cyclegan srgan sagan; do
   timeout 200 python bench.py --config $cfg --skip_cpu_baseline > gpurun_out/bench_$cfg.json 2> gpurun_out/bench_$cfg.err
