@@ -1,6 +1,8 @@
 #!/bin/bash
 # round 2, call Q (1 GPU): norm-backward reduction fused into the data-gradient epilogue, 64x64 weight-pack tiles,
 # 32-bit col2im indices, tail split from 128 k-blocks on: tests + A/B + bench + launch list + per-shape trace + ncu full
+# (historical: the fused reduction measured slower and was removed in the following commit, see
+# profiles/r02_fused_norm_bwd_negative.txt; GCC_B200_FUSE_NORM_BWD no longer exists)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q --timeout=300 > gpurun_out/pytest_q.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_q.log
