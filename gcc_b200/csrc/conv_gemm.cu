@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persistent_kernel(const __gr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   constexpr int kStagePitch = 80;  // 64 B of data + 16 B pad per staged row (spreads banks)
   uint8_t* stage_base = out_base + kOutBytes + 256;                    // 8 warps x 32 rows x 80 B
-  float* bias_base = reinterpret_cast<float*>(stage_base + 8 * 32 * kStagePitch);  // 8 warps x 32 floats
+  float* bias_base = reinterpret_cast<float*>(stage_base + 8 * 32 * kStagePitch);  // 8 x 32 floats (round 1's per-warp bias slots, now unused: tbias below)
   float* sstat = bias_base + 8 * 32;                                                // [2][BLOCK_N] BN statistics
   // biases of the current block of output columns: loaded ONCE per column-block change by the epilogue threads (the
   // per-chunk __ldg they replace put an L2 round trip on the critical path of every 32-column chunk of every tile of
