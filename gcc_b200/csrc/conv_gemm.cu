@@ -926,6 +926,24 @@ static int fill_gather_taps(GemmGeom& g, int KH, int KW, int stride, int pad) {
   return GCC_OK;
 }
 
+// Tail-wave split of the persistent conv kernel (ConvGeom2::tail_begin): number of K parts (0 = no split) of the last
+// `*rem` tiles of a launch of `base_tiles` tiles with >= `min_kb` k-blocks each on `sms` SMs: few waves, a last wave that
+// is at most half full, a K loop of >= tail_min_kb (and >= 32) k-blocks so that every part keeps >= 16.  Pure host
+// arithmetic (exported for the CPU tests as gcc_plan_conv_tail).
+static int plan_conv_tail(int base_tiles, int min_kb, int sms, int tail_min_kb, int* rem_out) {
+  const int S = sms;
+  const int waves = base_tiles / S, rem = base_tiles % S;
+  if (rem_out) *rem_out = rem;
+  if (!(waves >= 1 && waves <= 8 && rem > 0 && rem * 2 <= S && min_kb >= 32 && min_kb >= tail_min_kb)) return 0;
+  int ks = S / rem;
+  if (ks > min_kb / 16) ks = min_kb / 16;
+  if (ks > kTailMaxParts) ks = kTailMaxParts;
+  return ks >= 2 ? ks : 0;
+}
+extern "C" int gcc_plan_conv_tail(int base_tiles, int min_kb, int sms, int tail_min_kb) {
+  return plan_conv_tail(base_tiles, min_kb, sms, tail_min_kb, nullptr);
+}
+
 static int g_debug_flags = 0;
 extern "C" void gcc_debug_set_flags(int f) { g_debug_flags = f; }
 static int g_tail_min_kb = 0;  // test hook: k-blocks per tile from which the tail-wave split is taken (0 = default)
@@ -1199,18 +1217,13 @@ int gcc_conv_gemm_launch(const void* x, int N, int H, int W, int Cx, const void*
   static const int tail_min_kb_env = getenv("GCC_B200_TAIL_MIN_KB") ? atoi(getenv("GCC_B200_TAIL_MIN_KB")) : 128;
   const int tail_min_kb = g_tail_min_kb > 0 ? g_tail_min_kb : tail_min_kb_env;
   if (tail_on && !(g_debug_flags & 2048) && splitk_ws != nullptr && g.k_splits == 1 && !f32_out && !c8 && BN >= 128) {
-    const int S = num_sms();
-    const int waves = base_tiles / S, rem = base_tiles % S;
-    if (waves >= 1 && waves <= 8 && rem > 0 && rem * 2 <= S && min_kb >= 32 && min_kb >= tail_min_kb) {
-      int ks = S / rem;
-      if (ks > min_kb / 16) ks = min_kb / 16;
-      if (ks > kTailMaxParts) ks = kTailMaxParts;
-      if (ks >= 2 && ws_elems >= (long long)rem * ks * kBlockM * BN) {
-        g.tail_begin = base_tiles - rem;
-        g.tail_splits = ks;
-        g.tail_ws = splitk_ws;
-        g.total_tiles = g.tail_begin + rem * ks;
-      }
+    int rem = 0;
+    const int ks = plan_conv_tail(base_tiles, min_kb, num_sms(), tail_min_kb, &rem);
+    if (ks >= 2 && ws_elems >= (long long)rem * ks * kBlockM * BN) {
+      g.tail_begin = base_tiles - rem;
+      g.tail_splits = ks;
+      g.tail_ws = splitk_ws;
+      g.total_tiles = g.tail_begin + rem * ks;
     }
   }
   g.debug = g_debug_flags;
@@ -1259,6 +1272,37 @@ extern "C" int gcc_conv_rowwin_bf16(const void* x, int N, int Hrows, int Wp, con
                                     int stats_ld, void* stream) {
   return gcc_conv_gemm_launch(x, N, Hrows, Wp, 8, w_rowpack, R, KH * ((KW + 7) / 8), 64, bias, y, OH, OW, Cy, 0, 0, KH, KW, 1,
                               0, act, slope, 0, nullptr, 0, stats, stats_ld, 0, 1, stream);
+}
+
+// Split-K factor of a weight-gradient launch from a small cost model (cycles): CTAs run one per SM for the big tiles,
+// every split adds a full tile of fp32 atomics, and a partially filled last wave costs a whole wave.  Every integer
+// factor is a candidate (16 base CTAs x 9 = 144 fills the 148 SMs where 16 x 8 = 128 leaves 20 idle); among the factors
+// within 3 % of the cheapest the smallest wins (fewer atomic epilogues).  Pure host arithmetic (exported for the CPU
+// tests as gcc_plan_wgrad_splits).
+static int plan_wgrad_splits(int base_ctas, int total_pb, int BN, int MT, int c8) {
+  const double t_kb = 2.0 * BN * MT * 1.4;             // MMA cycles per 64-pixel block (x1.4: L2-bound operands)
+  const double t_epi = 40.0 * BN * MT + 6000.0;        // atomics epilogue + prologue
+  const int slots = kNumSMs * ((BN <= 128 && MT == 1) ? 2 : 1);
+  const int sp_max = c8 ? 256 : 64;
+  double best = 1e30;
+  auto cost_of = [&](int sp) {
+    const int kb = (total_pb + sp - 1) / sp;
+    const long long ctas = (long long)base_ctas * sp;
+    const double waves = (double)((ctas + slots - 1) / slots);
+    return waves * (kb * t_kb + t_epi);
+  };
+  for (int sp = 1; sp <= sp_max; ++sp) {
+    if (sp > 1 && (total_pb + sp - 1) / sp < 8) break;
+    best = cost_of(sp) < best ? cost_of(sp) : best;
+  }
+  for (int sp = 1; sp <= sp_max; ++sp) {
+    if (sp > 1 && (total_pb + sp - 1) / sp < 8) break;
+    if (cost_of(sp) <= best * 1.03) return sp;
+  }
+  return 1;
+}
+extern "C" int gcc_plan_wgrad_splits(int base_ctas, int total_pb, int BN, int MT, int c8) {
+  return plan_wgrad_splits(base_ctas, total_pb, BN, MT, c8);
 }
 
 // dW[b][r][t][c] (+)= scale * sum_{pix} P[n, oh, ow, r] * Q[n, s*oh + kh - p, s*ow + kw - p, c]
@@ -1346,30 +1390,7 @@ static int gcc_wgrad_gemm_launch(const void* pmat, int N, int OH, int OW, int Cp
   const int base_ctas = r_tiles * c_tiles * g.num_taps * (batched ? N : 1);
   // split-K factor from a small cost model (cycles): CTAs run one per SM for the big tiles, every split adds a
   // full tile of fp32 atomics, and a partially filled last wave costs a whole wave
-  int splits = 1;
-  {
-    const double t_kb = 2.0 * BN * MT * 1.4;             // MMA cycles per 64-pixel block (x1.4: L2-bound operands)
-    const double t_epi = 40.0 * BN * MT + 6000.0;        // atomics epilogue + prologue
-    const int slots = kNumSMs * ((BN <= 128 && MT == 1) ? 2 : 1);
-    // every integer factor is a candidate (16 base CTAs x 9 = 144 fills the 148 SMs where 16 x 8 = 128 leaves 20
-    // idle); among the factors within 3 % of the cheapest the smallest wins (fewer atomic epilogues)
-    const int sp_max = c8 ? 256 : 64;
-    double best = 1e30;
-    auto cost_of = [&](int sp) {
-      const int kb = (total_pb + sp - 1) / sp;
-      const long long ctas = (long long)base_ctas * sp;
-      const double waves = (double)((ctas + slots - 1) / slots);
-      return waves * (kb * t_kb + t_epi);
-    };
-    for (int sp = 1; sp <= sp_max; ++sp) {
-      if (sp > 1 && (total_pb + sp - 1) / sp < 8) break;
-      best = cost_of(sp) < best ? cost_of(sp) : best;
-    }
-    for (int sp = 1; sp <= sp_max; ++sp) {
-      if (sp > 1 && (total_pb + sp - 1) / sp < 8) break;
-      if (cost_of(sp) <= best * 1.03) { splits = sp; break; }
-    }
-  }
+  const int splits = plan_wgrad_splits(base_ctas, total_pb, BN, MT, c8);
   g.splits = splits;
   g.batched = batched;
   g.atomic_out = (splits > 1 || accumulate) ? 1 : 0;

@@ -64,6 +64,12 @@ void gcc_debug_force_block_n(int bn);
 void gcc_debug_set_flags(int f);
 /* test hook: k-blocks per tile from which the conv kernel's tail-wave split is taken (0 = the default, 128) */
 void gcc_debug_set_tail_min_kb(int kb);
+/* Host-side launch planning, pure arithmetic (no device needed; tests/test_host_cpu.py):
+ * gcc_plan_conv_tail: K parts (0 = none) the tail-wave split cuts the last base_tiles % sms tiles of a persistent conv
+ * launch into; gcc_plan_wgrad_splits: split-K factor of a weight-gradient launch of base_ctas CTAs over total_pb
+ * 64-pixel blocks (BN = tile columns, MT = 128-row accumulators per CTA, c8 = image mode). */
+int gcc_plan_conv_tail(int base_tiles, int min_kb, int sms, int tail_min_kb);
+int gcc_plan_wgrad_splits(int base_ctas, int total_pb, int BN, int MT, int c8);
 
 /* ---- norm / gate / activation blocks (norm.cu) ----
  * One block = [BatchNorm2d | InstanceNorm2d | identity] -> [DifferentiableOP gate] -> [(Leaky)ReLU]

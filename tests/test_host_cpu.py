@@ -23,6 +23,50 @@ def test_library_exports_every_declared_symbol():
     assert lib.gcc_abi_version() == 1
 
 
+def test_launch_planning_is_pure_host_arithmetic():
+    """The two launch-planning decisions of the GEMM kernels (tail-wave split of the persistent conv kernel, split-K
+    factor of the weight-gradient kernel) are exported as pure host functions: pinned here on the shapes of the c2
+    iteration and against an independent restatement of the cost model."""
+    from gcc_b200 import _build, _lib
+    lib = ctypes.CDLL(_build.build())
+    for name in ("gcc_plan_conv_tail", "gcc_plan_wgrad_splits"):
+        getattr(lib, name).restype = ctypes.c_int
+        getattr(lib, name).argtypes = [ctypes.c_int] * len(_lib.parse_header()[name][1])
+    tail = lib.gcc_plan_conv_tail
+    # 512 tiles on 148 SMs = 3.46 waves, 68 tiles in the last one
+    assert tail(512, 256, 148, 128) == 2          # PatchGAN 1024 -> 512 data gradient (256 k-blocks per tile)
+    assert tail(512, 64, 148, 128) == 0           # 256 -> 512 k4 s2 forward: below the default threshold (measured slower)
+    assert tail(512, 64, 148, 32) == 2            # ... taken when the threshold is lowered (the unit test's setting)
+    assert tail(512, 24, 148, 16) == 0            # never below 32 k-blocks: a part keeps >= 16
+    assert tail(1024, 256, 148, 128) == 0         # 6.92 waves: the last wave is 92 % full
+    assert tail(454, 256, 148, 128) == 4          # 10 tiles left: 14 parts would fit, at most 4 are taken
+    assert tail(100, 256, 148, 128) == 0          # less than one wave: the classic split-K path decides
+    assert tail(148 * 9 + 10, 256, 148, 128) == 0 # many waves: the tail does not matter
+    assert tail(444, 256, 148, 128) == 0          # whole waves
+
+    def model(base_ctas, total_pb, bn, mt, c8):
+        t_kb, t_epi = 2.0 * bn * mt * 1.4, 40.0 * bn * mt + 6000.0
+        slots = 148 * (2 if (bn <= 128 and mt == 1) else 1)
+        cands = []
+        for sp in range(1, (256 if c8 else 64) + 1):
+            kb = (total_pb + sp - 1) // sp
+            if sp > 1 and kb < 8:
+                break
+            waves = (base_ctas * sp + slots - 1) // slots
+            cands.append((sp, waves * (kb * t_kb + t_epi)))
+        best = min(c for _, c in cands)
+        return next(sp for sp, c in cands if c <= best * 1.03)
+
+    splits = lib.gcc_plan_wgrad_splits
+    assert splits(128, 512, 256, 2, 0) == 1       # PatchGAN 512 -> 1024: 128 CTAs, one long K loop each
+    assert splits(16, 2048, 128, 2, 0) == 9       # 128 -> 256 k4 s2: 16 x 9 = 144 CTAs fill the 148 SMs (8 left 20 idle)
+    for base in (1, 4, 16, 32, 128, 512):
+        for pb in (4, 16, 128, 512, 2048, 8192):
+            for bn, mt in ((64, 1), (128, 1), (128, 2), (256, 1), (256, 2)):
+                assert splits(base, pb, bn, mt, 0) == model(base, pb, bn, mt, 0), (base, pb, bn, mt)
+    assert splits(1, 8192, 128, 1, 1) == model(1, 8192, 128, 1, 1)
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly without a GPU instead of computing on the CPU."""
     if torch.cuda.is_available():
