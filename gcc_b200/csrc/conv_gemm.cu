@@ -59,7 +59,7 @@ struct GemmGeom {
   int batched;           // 1: one output matrix per image n (Gram)
   int atomic_out;        // 1: red.add into dw, 0: plain store
   float scale;
-  int debug;             // timing experiments: bit2 skip TMA loads, bit3 skip MMAs, bit0 skip epilogue stores
+  int debug;             // timing experiments: bit0 skip epilogue stores
   int c8;                // wgrad: 1 = Q is an 8-channel image, the N dimension is (tap, channel) = T * 8 columns
 };
 
